@@ -1,0 +1,41 @@
+// Shared host/device helpers for the centerpose_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/centerpose_b200.h"
+
+namespace cpb {
+
+extern thread_local char g_err[512];
+extern std::atomic<unsigned long long> g_launches;
+
+inline int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+inline int check_launch(const char *what) {
+  cudaError_t e = cudaGetLastError();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) return fail(CPB200_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return CPB200_OK;
+}
+
+#define CPB_CUDA(call)                                                                 \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return cpb::fail(CPB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));      \
+  } while (0)
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace cpb

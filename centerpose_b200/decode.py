@@ -1,0 +1,92 @@
+"""Host-side mirror of the reference's decode module (``lib/models/decode.py``).
+
+``multi_pose_decode`` keeps the reference signature and semantics
+(``lib/models/decode.py:235-308``) but is ONE fused CUDA kernel launched through the C ABI
+(``cpb200_multi_pose_decode``, ``include/centerpose_b200.h``).  CUDA tensors only — there
+is no CPU path in the product.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+_ws_cache = {}
+
+
+def _workspace(device, B, J, K):
+    stream = torch.cuda.current_stream(device)
+    key = (device.index, stream.cuda_stream, B, J, K)
+    ws = _ws_cache.get(key)
+    if ws is None:
+        nbytes = _lib.lib().cpb200_decode_workspace_bytes(B, J, K)
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)   # zero ONCE; kernel self-cleans
+        if len(_ws_cache) > 64:
+            _ws_cache.clear()
+        _ws_cache[key] = ws
+    return ws
+
+
+def _prep(t, name, shape=None):
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"multi_pose_decode: `{name}` must be a CUDA tensor "
+                           "(centerpose_b200 has no CPU decode path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    if not t.is_contiguous():
+        t = t.contiguous()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise RuntimeError(f"multi_pose_decode: `{name}` has shape {tuple(t.shape)}, expected {tuple(shape)}")
+    return t
+
+
+def multi_pose_decode(heat, wh, kps, reg=None, hm_hp=None, hp_offset=None, K=100,
+                      apply_sigmoid=False, out=None):
+    """Same contract as the reference (``decode.py:235-236``): ``heat``/``hm_hp`` already
+    sigmoid'ed (unless ``apply_sigmoid=True`` — additive: the kernel then applies the logistic
+    itself, replacing ``multi_pose.py:35-37``), returns ``(B, K, 5+3J)`` fp32 on the input device.
+    """
+    heat = _prep(heat, "heat")
+    if heat.dim() != 4:
+        raise RuntimeError("multi_pose_decode: heat must be (B,C,H,W)")
+    B, cat, H, W = heat.shape
+    if cat != 1:
+        raise RuntimeError("multi_pose_decode: only NUM_CLASSES == 1 is supported (person), got %d" % cat)
+    kps = _prep(kps, "kps")
+    J = kps.shape[1] // 2
+    kps = _prep(kps, "kps", (B, 2 * J, H, W))
+    wh = _prep(wh, "wh", (B, 2, H, W))
+    reg = _prep(reg, "reg", (B, 2, H, W))
+    if hm_hp is None:
+        # the reference raises here too: decode.py:307 uses hm_score unconditionally
+        raise NameError("name 'hm_score' is not defined")
+    hm_hp = _prep(hm_hp, "hm_hp", (B, J, H, W))
+    hp_offset = _prep(hp_offset, "hp_offset", (B, 2, H, W))
+    K = int(K)
+    if K > H * W:
+        raise RuntimeError("selected index k out of range")   # torch.topk's message
+    dev = heat.device
+    if out is None:
+        out = torch.empty((B, K, 5 + 3 * J), dtype=torch.float32, device=dev)
+    ws = _workspace(dev, B, J, K)
+    ptr = lambda t: None if t is None else t.data_ptr()
+    with torch.cuda.device(dev):
+        st = _lib.lib().cpb200_multi_pose_decode(
+            ptr(heat), ptr(wh), ptr(kps), ptr(reg), ptr(hm_hp), ptr(hp_offset), out.data_ptr(),
+            B, H, W, J, K, 1 if apply_sigmoid else 0, ws.data_ptr(), ws.numel(),
+            torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(st, "multi_pose_decode")
+    return out
+
+
+def sigmoid_(x: torch.Tensor) -> torch.Tensor:
+    """In-place logistic on a CUDA fp32 tensor (``multi_pose.py:35-37`` ``hm.sigmoid_()``)."""
+    if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
+        raise RuntimeError("sigmoid_: contiguous CUDA fp32 tensor required")
+    with torch.cuda.device(x.device):
+        st = _lib.lib().cpb200_sigmoid_inplace(x.data_ptr(), x.numel(),
+                                               torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(st, "sigmoid_")
+    return x
