@@ -19,8 +19,10 @@ def main():
     dev = torch.device("cuda:0")
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     res = []
-    for B in (32, 256, 1024):
-        base = synth_decode_inputs(8, 128, 128, seed=3, kind="smooth")
+    sizes = [int(v) for v in os.environ.get("DECODE_BENCH_B", "32,256,1024").split(",")]
+    kind = os.environ.get("DECODE_BENCH_KIND", "smooth")
+    for B in sizes:
+        base = synth_decode_inputs(8, 128, 128, seed=3, kind=kind)
         t = {k: torch.from_numpy(v).to(dev).repeat(B // 8, 1, 1, 1).contiguous() for k, v in base.items()}
         out = torch.empty(B, 100, 56, device=dev)
         run = lambda: multi_pose_decode(t["heat"], t["wh"], t["kps"], t["reg"], t["hm_hp"], t["hp_offset"], K=100, out=out)
@@ -30,6 +32,7 @@ def main():
         for _ in range(20):
             flush.zero_()
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            torch.cuda._sleep(3_000_000)      # keep the GPU busy while the host enqueues (hides launch latency)
             e0.record(); run(); e1.record(); torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
         times.sort()
