@@ -1,0 +1,447 @@
+// CUDA-core (SIMT) implementations of the fused network ops, fp32 accumulate, activations
+// fp32 or bf16 NHWC.  This is the "precise" path (act_dtype = fp32 reproduces the reference's
+// fp32 arithmetic up to summation order) and the fallback for layers whose shapes the
+// tcgen05 path (net_tc.cu) does not take.  Reference semantics per op:
+//   CONV          torch.nn.Conv2d + folded eval BatchNorm2d (+ residual add) (+ ReLU)
+//                 e.g. pose_dla_dcn.py:43-57 (BasicBlock), :155-163 (Root: the torch.cat of
+//                 the children is never materialised — each child is one K-slab), :199-204
+//   STEM          pose_dla_dcn.py:226-231 base_layer (7x7, 3->16) on the NCHW fp32 image
+//   MAXPOOL       pose_dla_dcn.py:196 nn.MaxPool2d(stride), msra_resnet.py:126
+//   DWDECONV_ADD  pose_dla_dcn.py:361-364,374-377: depthwise ConvTranspose2d(2f, stride f,
+//                 pad f/2) followed by `+ layers[i-1]`
+//   DCN           DCNv2/dcn_v2.py:117-127 + DCNv2/src/cuda/dcn_v2_im2col_cuda.cu:25-54,125-195
+//                 + dcn_v2_cuda.cu:123-163: sigmoid(mask) * bilinear sample, then the GEMM —
+//                 fused here: the sampled im2col tile lives in shared memory only (the
+//                 reference round-trips a (B, 9C, HW) fp32 `columns` buffer through HBM).
+#include "common.cuh"
+#include <algorithm>
+
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+template <typename T> struct Act;
+template <> struct Act<float> {
+  __device__ static float4 ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+  __device__ static float ld(const float *p) { return __ldg(p); }
+  __device__ static void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+  __device__ static void st(float *p, float v) { *p = v; }
+};
+template <> struct Act<bf16> {
+  __device__ static float4 ld4(const bf16 *p) {
+    uint2 r = __ldg(reinterpret_cast<const uint2 *>(p));
+    float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&r.x));
+    float2 b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162 *>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  __device__ static float ld(const bf16 *p) { return __bfloat162float(*p); }
+  __device__ static void st4(bf16 *p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r; r.x = *reinterpret_cast<unsigned *>(&a); r.y = *reinterpret_cast<unsigned *>(&b);
+    *reinterpret_cast<uint2 *>(p) = r;
+  }
+  __device__ static void st(bf16 *p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+struct ConvArgs {
+  const void *src[4];
+  int cin[4];
+  int nsrc;
+  const void *res;
+  const float *aux;       // DCN: (B,H,W,27) fp32 offsets+mask logits
+  void *dst;
+  const float *weight;    // [taps][cin_total][cout_pad]
+  const float *bias;
+  int B, H, W, Ho, Wo, Hd, Wd;
+  int cin_total, cout, cout_pad;
+  int kh, kw, stride, pad_h, pad_w;
+  int out_sy, out_sx, out_oy, out_ox;
+  int out_ch_off, out_ch_total;
+  unsigned flags;
+};
+
+constexpr int BK = 16;
+
+// Implicit-GEMM conv: M = B*Ho*Wo output pixels, N = cout, K = taps * cin_total.
+// CTA = 256 threads computes a BM x BN tile, 4x4 outputs per thread... (TM x TN generic).
+template <typename T, int BM, int BN, bool DCN>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
+  constexpr int TM = 4;
+  constexpr int TN = (BM * BN) / (256 * TM);       // 64x64 -> 4, 128x32 -> 4, 256x16 -> 4
+  static_assert(TN == 4, "tile must give 4x4 outputs per thread");
+  constexpr int TX = BN / TN;                       // threads along N
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  __shared__ int s_coff[DCN ? 4 : 1][DCN ? BM : 1];     // DCN: 4 corner element offsets per pixel
+  __shared__ float s_cwt[DCN ? 4 : 1][DCN ? BM : 1];    // DCN: 4 corner weights (x mask x validity)
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const long long M = (long long)a.B * a.Ho * a.Wo;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  // per-thread A-load assignment: pixel slots i = lid/4 (+64 per round), channel quad kq = lid%4
+  constexpr int A_ROUNDS = BM / 64;
+  int pb[A_ROUNDS], pho[A_ROUNDS], pwo[A_ROUNDS];
+  bool pok[A_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < A_ROUNDS; ++r) {
+    const long long m = m0 + (tid >> 2) + 64 * r;
+    pok[r] = m < M;
+    const long long mm = pok[r] ? m : 0;
+    pb[r] = (int)(mm / ((long long)a.Ho * a.Wo));
+    const int rem = (int)(mm % ((long long)a.Ho * a.Wo));
+    pho[r] = rem / a.Wo; pwo[r] = rem % a.Wo;
+  }
+  const int kq = tid & 3;
+  const int taps = a.kh * a.kw;
+
+  for (int tap = 0; tap < taps; ++tap) {
+    const int r_ = tap / a.kw, q_ = tap % a.kw;
+    if (DCN) {
+      __syncthreads();
+      for (int i = tid; i < BM; i += 256) {
+        const long long m = m0 + i;
+        int off[4] = {0, 0, 0, 0}; float wt[4] = {0.f, 0.f, 0.f, 0.f};
+        if (m < M) {
+          const int b = (int)(m / ((long long)a.Ho * a.Wo));
+          const int rem = (int)(m % ((long long)a.Ho * a.Wo));
+          const int ho = rem / a.Wo, wo = rem % a.Wo;
+          const float *om = a.aux + ((size_t)m) * 27;
+          const float oh = __ldg(om + 2 * tap), ow = __ldg(om + 2 * tap + 1);
+          const float mk = 1.0f / (1.0f + expf(-__ldg(om + 18 + tap)));      // dcn_v2.py:121
+          const float h_im = (float)(ho * a.stride - a.pad_h + r_) + oh;      // im2col_cuda.cu:177-178
+          const float w_im = (float)(wo * a.stride - a.pad_w + q_) + ow;
+          if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {   // :180
+            const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+            const int h_high = h_low + 1, w_high = w_low + 1;
+            const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+            const size_t rowb = (size_t)b * a.H;
+            if (h_low >= 0 && w_low >= 0) { off[0] = (int)(((rowb + h_low) * a.W + w_low)); wt[0] = hh * hw * mk; }
+            if (h_low >= 0 && w_high <= a.W - 1) { off[1] = (int)(((rowb + h_low) * a.W + w_high)); wt[1] = hh * lw * mk; }
+            if (h_high <= a.H - 1 && w_low >= 0) { off[2] = (int)(((rowb + h_high) * a.W + w_low)); wt[2] = lh * hw * mk; }
+            if (h_high <= a.H - 1 && w_high <= a.W - 1) { off[3] = (int)(((rowb + h_high) * a.W + w_high)); wt[3] = lh * lw * mk; }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { s_coff[c][i] = off[c]; s_cwt[c][i] = wt[c]; }
+      }
+      __syncthreads();
+    }
+    int cbase = 0;
+    for (int s = 0; s < a.nsrc; ++s) {
+      const T *src = static_cast<const T *>(a.src[s]);
+      const int cs = a.cin[s];
+      for (int c0 = 0; c0 < cs; c0 += BK) {
+        // ---- A tile: BM pixels x 16 channels ----
+        float4 av[A_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < A_ROUNDS; ++r) {
+          av[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!DCN) {
+            const int hi = pho[r] * a.stride - a.pad_h + r_, wi = pwo[r] * a.stride - a.pad_w + q_;
+            if (pok[r] && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W)
+              av[r] = Act<T>::ld4(src + (((size_t)pb[r] * a.H + hi) * a.W + wi) * cs + c0 + kq * 4);
+          } else {
+            const int i = (tid >> 2) + 64 * r;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float wgt = s_cwt[c][i];
+              if (wgt != 0.f) {
+                const float4 v = Act<T>::ld4(src + (size_t)s_coff[c][i] * cs + c0 + kq * 4);
+                av[r].x += wgt * v.x; av[r].y += wgt * v.y; av[r].z += wgt * v.z; av[r].w += wgt * v.w;
+              }
+            }
+          }
+        }
+        // ---- B tile: 16 x BN weights ----
+        constexpr int B_LOADS = (BK * BN / 4 + 255) / 256;     // float4 loads per thread
+        float4 bv[B_LOADS];
+#pragma unroll
+        for (int l = 0; l < B_LOADS; ++l) {
+          const int e = tid + 256 * l;
+          const int k = e / (BN / 4), nq = e % (BN / 4);
+          bv[l] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < BK && n0 + nq * 4 < a.cout_pad)
+            bv[l] = __ldg(reinterpret_cast<const float4 *>(
+                a.weight + ((size_t)tap * a.cin_total + cbase + c0 + k) * a.cout_pad + n0 + nq * 4));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < A_ROUNDS; ++r) {
+          const int i = (tid >> 2) + 64 * r;
+          As[kq * 4 + 0][i] = av[r].x; As[kq * 4 + 1][i] = av[r].y;
+          As[kq * 4 + 2][i] = av[r].z; As[kq * 4 + 3][i] = av[r].w;
+        }
+#pragma unroll
+        for (int l = 0; l < B_LOADS; ++l) {
+          const int e = tid + 256 * l;
+          const int k = e / (BN / 4), nq = e % (BN / 4);
+          if (k < BK) *reinterpret_cast<float4 *>(&Bs[k][nq * 4]) = bv[l];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+          const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * TM]);
+          const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[k][tx * TN]);
+          const float ar[4] = {a4.x, a4.y, a4.z, a4.w}, br[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+        }
+      }
+      cbase += cs;
+    }
+  }
+
+  // ---- epilogue ----
+  const bool relu = a.flags & CPB200_FLAG_RELU;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const long long m = m0 + ty * TM + i;
+    if (m >= M) continue;
+    const int b = (int)(m / ((long long)a.Ho * a.Wo));
+    const int rem = (int)(m % ((long long)a.Ho * a.Wo));
+    const int ho = rem / a.Wo, wo = rem % a.Wo;
+    const int hd = ho * a.out_sy + a.out_oy, wd = wo * a.out_sx + a.out_ox;
+    const size_t pix = ((size_t)b * a.Hd + hd) * a.Wd + wd;
+    float v[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      v[j] = acc[i][j] + ((a.bias && n < a.cout) ? __ldg(a.bias + n) : 0.f);
+    }
+    const int nb = n0 + tx * TN;
+    if (a.flags & CPB200_FLAG_OUT_NCHW_F32) {
+      float *o = static_cast<float *>(a.dst);
+#pragma unroll
+      for (int j = 0; j < TN; ++j)
+        if (nb + j < a.cout) {
+          float x = v[j]; if (relu) x = fmaxf(x, 0.f);
+          o[(((size_t)b * a.out_ch_total + a.out_ch_off + nb + j) * a.Hd + hd) * a.Wd + wd] = x;
+        }
+    } else if (a.flags & CPB200_FLAG_OUT_F32) {
+      float *o = static_cast<float *>(a.dst) + pix * a.cout;
+#pragma unroll
+      for (int j = 0; j < TN; ++j)
+        if (nb + j < a.cout) { float x = v[j]; if (relu) x = fmaxf(x, 0.f); o[nb + j] = x; }
+    } else {
+      T *o = static_cast<T *>(a.dst) + pix * a.cout;
+      const T *rs = a.res ? static_cast<const T *>(a.res) + pix * a.cout : nullptr;
+      if (nb + TN <= a.cout && (a.cout & 3) == 0) {
+        float4 x = make_float4(v[0], v[1], v[2], v[3]);
+        if (rs) { float4 r4 = Act<T>::ld4(rs + nb); x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w; }
+        if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+        Act<T>::st4(o + nb, x);
+      } else {
+#pragma unroll
+        for (int j = 0; j < TN; ++j)
+          if (nb + j < a.cout) {
+            float x = v[j];
+            if (rs) x += Act<T>::ld(rs + nb + j);
+            if (relu) x = fmaxf(x, 0.f);
+            Act<T>::st(o + nb + j, x);
+          }
+      }
+    }
+  }
+}
+
+// ---- STEM: NCHW fp32 (B,Cin<=4,H,W) -> NHWC (B,Ho,Wo,Cout<=32), direct conv, bias + ReLU ----
+// weight layout: [kh*kw*cin][cout] fp32.  One thread = one output pixel, all couts.
+template <typename T, int COUT>
+__global__ void __launch_bounds__(128) stem_kernel(const float *__restrict__ x, T *__restrict__ y,
+                                                   const float *__restrict__ w, const float *__restrict__ bias,
+                                                   int B, int Cin, int H, int W, int Ho, int Wo,
+                                                   int kh, int kw, int stride, int pad_h, int pad_w, int relu) {
+  extern __shared__ float sw[];                      // kh*kw*cin*COUT
+  const int nw = kh * kw * Cin * COUT;
+  for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const long long M = (long long)B * Ho * Wo;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int b = (int)(m / ((long long)Ho * Wo));
+  const int rem = (int)(m % ((long long)Ho * Wo));
+  const int ho = rem / Wo, wo = rem % Wo;
+  float acc[COUT];
+#pragma unroll
+  for (int n = 0; n < COUT; ++n) acc[n] = bias ? bias[n] : 0.f;
+  for (int r = 0; r < kh; ++r) {
+    const int hi = ho * stride - pad_h + r;
+    if (hi < 0 || hi >= H) continue;
+    for (int q = 0; q < kw; ++q) {
+      const int wi = wo * stride - pad_w + q;
+      if (wi < 0 || wi >= W) continue;
+      for (int c = 0; c < Cin; ++c) {
+        const float v = __ldg(x + (((size_t)b * Cin + c) * H + hi) * W + wi);
+        const float *wp = sw + ((r * kw + q) * Cin + c) * COUT;
+#pragma unroll
+        for (int n = 0; n < COUT; ++n) acc[n] = fmaf(v, wp[n], acc[n]);
+      }
+    }
+  }
+  T *o = y + (size_t)m * COUT;
+#pragma unroll
+  for (int n = 0; n < COUT; n += 4) {
+    float4 v = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    Act<T>::st4(o + n, v);
+  }
+}
+
+// ---- MAXPOOL k x k / stride / pad, NHWC, 4 channels per thread ----
+template <typename T>
+__global__ void maxpool_kernel(const T *__restrict__ x, T *__restrict__ y, int B, int H, int W, int C,
+                               int Ho, int Wo, int k, int stride, int pad) {
+  const int C4 = C >> 2;
+  const long long total = (long long)B * Ho * Wo * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long long p = i / C4;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int r = 0; r < k; ++r) {
+      const int hi = ho * stride - pad + r;
+      if (hi < 0 || hi >= H) continue;
+      for (int q = 0; q < k; ++q) {
+        const int wi = wo * stride - pad + q;
+        if (wi < 0 || wi >= W) continue;
+        const float4 v = Act<T>::ld4(x + (((size_t)b * H + hi) * W + wi) * C + c4 * 4);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    Act<T>::st4(y + (((size_t)b * Ho + ho) * Wo + wo) * C + c4 * 4, m);
+  }
+}
+
+// ---- depthwise ConvTranspose2d(k=2f, stride f, pad f/2) + skip add, NHWC ----
+// out[b,ho,wo,c] = skip[b,ho,wo,c] + sum_{kh,kw : (ho+p-kh)%f==0, (wo+p-kw)%f==0} x[b,(ho+p-kh)/f,(wo+p-kw)/f,c] * w[kh,kw,c]
+template <typename T>
+__global__ void dwdeconv_add_kernel(const T *__restrict__ x, const T *__restrict__ skip, T *__restrict__ y,
+                                    const float *__restrict__ w, int B, int H, int W, int C, int Ho, int Wo,
+                                    int k, int f, int pad) {
+  const int C4 = C >> 2;
+  const long long total = (long long)B * Ho * Wo * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long long p = i / C4;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const size_t opix = (((size_t)b * Ho + ho) * Wo + wo) * C + c4 * 4;
+    float4 acc = skip ? Act<T>::ld4(skip + opix) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // valid kh: kh ≡ (ho+pad) mod f, 0 <= kh < k
+    for (int khh = (ho + pad) % f; khh < k; khh += f) {
+      const int hi = (ho + pad - khh) / f;
+      if (hi < 0 || hi >= H || ho + pad - khh < 0) continue;
+      for (int kww = (wo + pad) % f; kww < k; kww += f) {
+        const int wi = (wo + pad - kww) / f;
+        if (wi < 0 || wi >= W || wo + pad - kww < 0) continue;
+        const float4 v = Act<T>::ld4(x + (((size_t)b * H + hi) * W + wi) * C + c4 * 4);
+        const float4 ww = __ldg(reinterpret_cast<const float4 *>(w + ((size_t)khh * k + kww) * C + c4 * 4));
+        acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
+        acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
+      }
+    }
+    Act<T>::st4(y + opix, acc);
+  }
+}
+
+template <typename T, bool DCN>
+int launch_conv(const cpb200_op &op, cudaStream_t st) {
+  ConvArgs a;
+  a.cin_total = 0;
+  for (int i = 0; i < 4; ++i) {
+    a.src[i] = op.src[i]; a.cin[i] = (i < op.nsrc) ? op.cin[i] : 0;
+    if (i < op.nsrc) {
+      if (op.cin[i] % BK) return cpb::fail(CPB200_ERR_ARG, "conv: input channels %d not a multiple of %d", op.cin[i], BK);
+      a.cin_total += op.cin[i];
+    }
+  }
+  a.nsrc = op.nsrc; a.res = op.res; a.aux = static_cast<const float *>(op.aux); a.dst = op.dst;
+  a.weight = static_cast<const float *>(op.weight); a.bias = op.bias;
+  a.B = op.B; a.H = op.H; a.W = op.W; a.Ho = op.Ho; a.Wo = op.Wo; a.Hd = op.Hd; a.Wd = op.Wd;
+  a.cout = op.cout; a.cout_pad = (op.cout + 3) / 4 * 4;
+  a.kh = op.kh; a.kw = op.kw; a.stride = op.stride; a.pad_h = op.pad_h; a.pad_w = op.pad_w;
+  a.out_sy = op.out_sy; a.out_sx = op.out_sx; a.out_oy = op.out_oy; a.out_ox = op.out_ox;
+  a.out_ch_off = op.out_ch_off; a.out_ch_total = op.out_ch_total; a.flags = op.flags;
+  const long long M = (long long)op.B * op.Ho * op.Wo;
+  if (op.cout <= 16) {
+    dim3 grid((unsigned)((M + 255) / 256), (op.cout + 15) / 16);
+    conv_simt_kernel<T, 256, 16, DCN><<<grid, 256, 0, st>>>(a);
+  } else if (op.cout <= 32) {
+    dim3 grid((unsigned)((M + 127) / 128), (op.cout + 31) / 32);
+    conv_simt_kernel<T, 128, 32, DCN><<<grid, 256, 0, st>>>(a);
+  } else {
+    dim3 grid((unsigned)((M + 63) / 64), (op.cout + 63) / 64);
+    conv_simt_kernel<T, 64, 64, DCN><<<grid, 256, 0, st>>>(a);
+  }
+  return cpb::check_launch("conv_simt_kernel");
+}
+
+template <typename T>
+int run_op_simt(const cpb200_op &op, cudaStream_t st) {
+  switch (op.type) {
+    case CPB200_OP_CONV: return launch_conv<T, false>(op, st);
+    case CPB200_OP_DCN:
+      if (op.kh != 3 || op.kw != 3 || !op.aux) return cpb::fail(CPB200_ERR_ARG, "dcn: needs 3x3 kernel and offset/mask tensor");
+      return launch_conv<T, true>(op, st);
+    case CPB200_OP_STEM: {
+      const long long M = (long long)op.B * op.Ho * op.Wo;
+      const int cin = op.cin[0];
+      const size_t smem = (size_t)op.kh * op.kw * cin * op.cout * sizeof(float);
+      if (cin > 4 || smem > 48 * 1024) return cpb::fail(CPB200_ERR_ARG, "stem: unsupported shape");
+      const unsigned grid = (unsigned)((M + 127) / 128);
+      const int relu = (op.flags & CPB200_FLAG_RELU) ? 1 : 0;
+#define STEM_CASE(CO)                                                                              \
+  case CO: stem_kernel<T, CO><<<grid, 128, smem, st>>>(static_cast<const float *>(op.src[0]),     \
+      static_cast<T *>(op.dst), static_cast<const float *>(op.weight), op.bias, op.B, cin, op.H,  \
+      op.W, op.Ho, op.Wo, op.kh, op.kw, op.stride, op.pad_h, op.pad_w, relu); break;
+      switch (op.cout) { STEM_CASE(16) STEM_CASE(32) STEM_CASE(64)
+        default: return cpb::fail(CPB200_ERR_ARG, "stem: cout %d unsupported", op.cout); }
+#undef STEM_CASE
+      return cpb::check_launch("stem_kernel");
+    }
+    case CPB200_OP_MAXPOOL: {
+      if (op.cin[0] % 4) return cpb::fail(CPB200_ERR_ARG, "maxpool: C %% 4 != 0");
+      const long long total = (long long)op.B * op.Ho * op.Wo * (op.cin[0] / 4);
+      const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 32);
+      maxpool_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(op.src[0]), static_cast<T *>(op.dst),
+                                              op.B, op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h);
+      return cpb::check_launch("maxpool_kernel");
+    }
+    case CPB200_OP_DWDECONV_ADD: {
+      if (op.cin[0] % 4) return cpb::fail(CPB200_ERR_ARG, "dwdeconv: C %% 4 != 0");
+      const long long total = (long long)op.B * op.Ho * op.Wo * (op.cin[0] / 4);
+      const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 32);
+      dwdeconv_add_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(op.src[0]),
+          static_cast<const T *>(op.aux), static_cast<T *>(op.dst), static_cast<const float *>(op.weight),
+          op.B, op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h);
+      return cpb::check_launch("dwdeconv_add_kernel");
+    }
+    default: return cpb::fail(CPB200_ERR_ARG, "unknown op type %d", op.type);
+  }
+}
+
+}  // namespace
+
+namespace cpb {
+int run_op_simt_dispatch(const cpb200_op &op, cudaStream_t st) {
+  if (op.act_dtype == CPB200_F32) return run_op_simt<float>(op, st);
+  if (op.act_dtype == CPB200_BF16) return run_op_simt<__nv_bfloat16>(op, st);
+  return fail(CPB200_ERR_ARG, "bad act_dtype %d", op.act_dtype);
+}
+}  // namespace cpb

@@ -72,6 +72,77 @@ int cpb200_multi_pose_decode(const float *heat, const float *wh, const float *kp
 /* In-place logistic on n floats — lib/detectors/multi_pose.py:35-37 `hm.sigmoid_()`. */
 int cpb200_sigmoid_inplace(float *x, size_t n, void *stream);
 
+
+/* ------------------------------------------------------------------------------------
+ * Network forward.  Replaces `BackBoneWithHead.forward` (lib/models/model.py:57-59): the
+ * backbone modules of lib/models/backbones/pose_dla_dcn.py (DLA-34 + DCN IDAUp) /
+ * msra_resnet.py (ResNet-50 + deconvs), the vendored `_ext.dcn_v2_forward`
+ * (lib/models/backbones/DCNv2/src/dcn_v2.h:9-39, src/cuda/dcn_v2_cuda.cu:42-172,
+ * src/cuda/dcn_v2_im2col_cuda.cu:125-195) and `KeypointHead.forward`
+ * (lib/models/heads/keypoint.py:40-42).
+ *
+ * The host (Python graph builder, centerpose_b200/plan.py) lowers the module tree to a flat
+ * program of fused ops — eval-mode BatchNorm folded into weights/bias, ReLU / residual-add /
+ * channel-concat fused into the producing or consuming op — and hands it over as an array of
+ * cpb200_op.  cpb200_run_ops enqueues the whole program on `stream` (one C call per forward).
+ *
+ * Activations are NHWC (channels innermost), dtype CPB200_F32 or CPB200_BF16 (fp32
+ * accumulate either way).  The network input is the reference's NCHW fp32 image batch and
+ * the six head maps are written NCHW fp32, exactly what lib/models/decode.py consumes.
+ * ---------------------------------------------------------------------------------- */
+#define CPB200_F32 0
+#define CPB200_BF16 1
+
+enum cpb200_op_type {
+  CPB200_OP_CONV = 1,        /* k x k conv (+bias)(+residual)(+ReLU); up to 4 channel-concatenated inputs */
+  CPB200_OP_STEM = 2,        /* NCHW fp32 image -> NHWC, small-Cin direct conv (+bias+ReLU)                */
+  CPB200_OP_MAXPOOL = 3,     /* k x k / stride s / pad p max-pool, NHWC                                     */
+  CPB200_OP_DWDECONV_ADD = 4,/* depthwise ConvTranspose2d(k=2f,s=f,p=f/2) (+ skip add), NHWC  (IDAUp up_*) */
+  CPB200_OP_DCN = 5          /* modulated deformable 3x3 conv (DCNv2 forward) (+bias)(+ReLU)                */
+};
+/* A dense ConvTranspose2d(k4,s2,p1) (msra_resnet.py:168-193) is lowered by the host into four
+ * 2x2 CONV ops, one per output parity, using pad_h/pad_w and the strided-output fields below. */
+
+#define CPB200_FLAG_RELU 1u          /* ReLU in the epilogue                                     */
+#define CPB200_FLAG_OUT_NCHW_F32 2u  /* write fp32 NCHW into dst (channel slice out_ch_off..)    */
+#define CPB200_FLAG_OUT_F32 4u       /* write fp32 NHWC regardless of act_dtype (DCN offsets)    */
+#define CPB200_FLAG_TC 8u            /* run on the tcgen05 tensor-core path (bf16 only)          */
+
+typedef struct cpb200_op {
+  int32_t type;              /* enum cpb200_op_type */
+  uint32_t flags;
+  int32_t act_dtype;         /* CPB200_F32 / CPB200_BF16: dtype of src/res/dst activations */
+  int32_t B, H, W;           /* input batch / spatial size  */
+  int32_t Ho, Wo;            /* output spatial size         */
+  int32_t nsrc;              /* number of concatenated inputs (1..4) */
+  int32_t cin[4];            /* channels of each input      */
+  int32_t cout;              /* output channels             */
+  int32_t kh, kw, stride;
+  int32_t pad_h, pad_w;      /* top / left zero padding (bottom / right follow from the bounds) */
+  int32_t out_ch_off, out_ch_total;   /* NCHW output: channel offset / total channels of dst */
+  int32_t Hd, Wd;            /* spatial size of the dst tensor (== Ho,Wo unless strided output) */
+  int32_t out_sy, out_sx, out_oy, out_ox; /* output pixel (ho,wo) lands at (ho*out_sy+out_oy, wo*out_sx+out_ox) */
+  int32_t reserved0;
+  const void *src[4];        /* inputs (NHWC act_dtype; STEM: NCHW fp32) */
+  const void *res;           /* optional residual, same shape/dtype as the NHWC output */
+  const void *aux;           /* DCN: offset/mask tensor (B,H,W,27) fp32; DWDECONV_ADD: skip tensor */
+  void *dst;
+  const void *weight;        /* packed by centerpose_b200/plan.py, layout per op type */
+  const float *bias;         /* fp32 [cout] (BatchNorm folded), may be NULL */
+  void *tc;                  /* opaque tensor-core state prepared by cpb200_prepare_ops, or NULL */
+  uint64_t reserved1[2];
+} cpb200_op;
+
+/* Validate the program and build device-side descriptors (TMA tensor maps) for ops flagged
+ * CPB200_FLAG_TC.  Must be called once after the pointers in `ops` are final. */
+int cpb200_prepare_ops(cpb200_op *ops, int n);
+/* Release what cpb200_prepare_ops attached. */
+int cpb200_release_ops(cpb200_op *ops, int n);
+/* Enqueue ops[0..n) in order on `stream`. */
+int cpb200_run_ops(const cpb200_op *ops, int n, void *stream);
+/* sizeof(cpb200_op) as compiled, so the host binding can verify its struct layout. */
+size_t cpb200_sizeof_op(void);
+
 #ifdef __cplusplus
 }
 #endif
