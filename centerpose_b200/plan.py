@@ -1,0 +1,317 @@
+"""Graph builder: lowers a backbone + head description to a flat program of fused CUDA ops
+(``cpb200_op``, ``include/centerpose_b200.h``) and owns the device buffers it runs on.
+
+What gets fused at lowering time (reference modules in brackets):
+  * eval-mode ``BatchNorm2d`` folded into the preceding conv / DCN weights and bias
+    (``pose_dla_dcn.py:43-57,155-163,199-204,336-348``; eps 1e-5);
+  * ReLU and residual add run in the conv epilogue (``BasicBlock.forward``);
+  * ``Root``'s ``torch.cat`` is never materialised: each child is one K-slab input of the 1x1
+    conv (``pose_dla_dcn.py:155-163``);
+  * IDAUp's depthwise ``ConvTranspose2d`` + ``layers[i] + layers[i-1]`` is one op
+    (``pose_dla_dcn.py:371-377``);
+  * DCN: offset/mask conv -> one op; sigmoid(mask) * bilinear gather * GEMM + BN + ReLU ->
+    one op (``DCNv2/dcn_v2.py:117-127``), no ``columns`` scratch in HBM.
+
+All torch usage here is plumbing (device memory, one-time weight re-layout).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+
+OP_CONV, OP_STEM, OP_MAXPOOL, OP_DWDECONV_ADD, OP_DCN = 1, 2, 3, 4, 5
+FLAG_RELU, FLAG_OUT_NCHW_F32, FLAG_OUT_F32, FLAG_TC = 1, 2, 4, 8
+F32, BF16 = 0, 1
+BN_EPS = 1e-5
+
+
+class OpStruct(ctypes.Structure):
+    _fields_ = [
+        ("type", ctypes.c_int32), ("flags", ctypes.c_uint32), ("act_dtype", ctypes.c_int32),
+        ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+        ("Ho", ctypes.c_int32), ("Wo", ctypes.c_int32), ("nsrc", ctypes.c_int32),
+        ("cin", ctypes.c_int32 * 4), ("cout", ctypes.c_int32),
+        ("kh", ctypes.c_int32), ("kw", ctypes.c_int32), ("stride", ctypes.c_int32),
+        ("pad_h", ctypes.c_int32), ("pad_w", ctypes.c_int32),
+        ("out_ch_off", ctypes.c_int32), ("out_ch_total", ctypes.c_int32),
+        ("Hd", ctypes.c_int32), ("Wd", ctypes.c_int32),
+        ("out_sy", ctypes.c_int32), ("out_sx", ctypes.c_int32),
+        ("out_oy", ctypes.c_int32), ("out_ox", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32),
+        ("src", ctypes.c_void_p * 4), ("res", ctypes.c_void_p), ("aux", ctypes.c_void_p),
+        ("dst", ctypes.c_void_p), ("weight", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+        ("tc", ctypes.c_void_p), ("reserved1", ctypes.c_uint64 * 2),
+    ]
+
+
+class Sym:
+    """Symbolic activation tensor (NHWC unless kind says otherwise)."""
+    __slots__ = ("C", "H", "W", "kind", "name", "buf", "producer", "last_use", "fixed")
+
+    def __init__(self, C, H, W, kind="act", name=""):
+        self.C, self.H, self.W, self.kind, self.name = C, H, W, kind, name
+        self.buf = None          # torch tensor once allocated
+        self.producer = -1
+        self.last_use = -1
+        self.fixed = False       # externally provided storage (network input / outputs)
+
+
+class _PendingOp:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def fold_bn(w: torch.Tensor, b: Optional[torch.Tensor], bn: Optional[dict]):
+    """conv weight (Co,Ci,kh,kw) [+bias] followed by eval BatchNorm -> equivalent weight/bias."""
+    w = w.float()
+    co = w.shape[0]
+    b = torch.zeros(co, device=w.device) if b is None else b.float()
+    if bn is None:
+        return w, b
+    scale = bn["weight"].float() / torch.sqrt(bn["running_var"].float() + BN_EPS)
+    return w * scale.view(-1, 1, 1, 1), (b - bn["running_mean"].float()) * scale + bn["bias"].float()
+
+
+class PlanBuilder:
+    def __init__(self, B: int, H: int, W: int, precision: str, device: torch.device):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.B, self.H, self.W = B, H, W
+        self.device = device
+        self.act_dtype = F32 if precision == "fp32" else BF16
+        self.torch_act = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.ops: List[_PendingOp] = []
+        self.keep: List[torch.Tensor] = []      # weights / biases kept alive
+        self.syms: List[Sym] = []
+        self.use_tc = False
+
+    # ---- symbolic tensors -------------------------------------------------------------
+    def _sym(self, C, H, W, kind="act", name=""):
+        s = Sym(C, H, W, kind, name)
+        self.syms.append(s)
+        return s
+
+    def input(self, C=3):
+        s = self._sym(C, self.H, self.W, "nchw_in", "input")
+        s.fixed = True
+        return s
+
+    def external(self, t: torch.Tensor, kind="act"):
+        """Wrap an existing NHWC device tensor (B,H,W,C) as a program input (tests, partial graphs)."""
+        B, H, W, C = t.shape
+        assert B == self.B and t.is_contiguous()
+        s = self._sym(C, H, W, kind, "external")
+        s.fixed = True
+        s.buf = t
+        return s
+
+    def output(self, C, H, W, name):
+        s = self._sym(C, H, W, "nchw_out", name)
+        s.fixed = True
+        return s
+
+    def _emit(self, op: _PendingOp, srcs: Sequence[Sym], dst: Sym, extra: Sequence[Optional[Sym]] = ()):
+        idx = len(self.ops)
+        for s in list(srcs) + [e for e in extra if e is not None]:
+            s.last_use = max(s.last_use, idx)
+        if dst.producer < 0:
+            dst.producer = idx
+        dst.last_use = max(dst.last_use, idx)
+        op.srcs, op.dst, op.extra = list(srcs), dst, list(extra)
+        self.ops.append(op)
+
+    def _dev(self, t: torch.Tensor, dtype=torch.float32):
+        t = t.detach().to(device=self.device, dtype=dtype).contiguous()
+        self.keep.append(t)
+        return t
+
+    # ---- weight packing ------------------------------------------------------------------
+    def _pack_conv(self, w: torch.Tensor):
+        """(Co,Ci,kh,kw) fp32 -> SIMT layout [kh*kw][Ci][Co_pad4] fp32."""
+        co, ci, kh, kw = w.shape
+        cop = (co + 3) // 4 * 4
+        p = torch.zeros(kh * kw, ci, cop, dtype=torch.float32, device=w.device)
+        p[:, :, :co] = w.permute(2, 3, 1, 0).reshape(kh * kw, ci, co)
+        return self._dev(p)
+
+    # ---- ops -------------------------------------------------------------------------------
+    def stem(self, x: Sym, w, b, k, stride, pad, relu=True):
+        co, ci = w.shape[0], w.shape[1]
+        Ho = (x.H + 2 * pad - k) // stride + 1; Wo = (x.W + 2 * pad - k) // stride + 1
+        y = self._sym(co, Ho, Wo)
+        wp = self._dev(w.permute(2, 3, 1, 0).reshape(k * k * ci, co))
+        self._emit(_PendingOp(type=OP_STEM, flags=FLAG_RELU if relu else 0, k=(k, k), stride=stride,
+                              pad=(pad, pad), weight=wp, bias=self._dev(b), cout=co), [x], y)
+        return y
+
+    def conv(self, srcs: Sequence[Sym], w, b, stride=1, pad=0, relu=False, res: Optional[Sym] = None,
+             out: str = "act", dst: Optional[Sym] = None, ch_off: int = 0, pad_hw=None,
+             out_map=None):
+        """w (Co, sum(Ci), kh, kw) already BN-folded; b (Co).  out: 'act' | 'f32' | 'nchw'.
+        pad_hw=(top,left) overrides symmetric padding; out_map=(Hd,Wd,sy,sx,oy,ox,Ho,Wo) writes a
+        strided sub-lattice of a larger dst (used to lower dense ConvTranspose2d)."""
+        co, ci, kh, kw = w.shape
+        assert ci == sum(s.C for s in srcs), (ci, [s.C for s in srcs])
+        H, W = srcs[0].H, srcs[0].W
+        ph, pw = pad_hw if pad_hw is not None else (pad, pad)
+        if out_map is None:
+            Ho = (H + 2 * pad - kh) // stride + 1; Wo = (W + 2 * pad - kw) // stride + 1
+            Hd, Wd, sy, sx, oy, ox = Ho, Wo, 1, 1, 0, 0
+        else:
+            Hd, Wd, sy, sx, oy, ox, Ho, Wo = out_map
+        flags = FLAG_RELU if relu else 0
+        if out == "nchw":
+            assert dst is not None
+            flags |= FLAG_OUT_NCHW_F32
+            y = dst
+        elif out == "f32":
+            flags |= FLAG_OUT_F32
+            y = dst if dst is not None else self._sym(co, Hd, Wd, "f32")
+        else:
+            y = dst if dst is not None else self._sym(co, Hd, Wd)
+        self._emit(_PendingOp(type=OP_CONV, flags=flags, k=(kh, kw), stride=stride, pad=(ph, pw),
+                              weight=self._pack_conv(w), bias=self._dev(b), cout=co, ch_off=ch_off,
+                              out_map=(Hd, Wd, sy, sx, oy, ox), HoWo=(Ho, Wo), w_raw=w), srcs, y, [res])
+        return y
+
+    def maxpool(self, x: Sym, k=2, stride=2, pad=0):
+        Ho = (x.H + 2 * pad - k) // stride + 1; Wo = (x.W + 2 * pad - k) // stride + 1
+        y = self._sym(x.C, Ho, Wo)
+        self._emit(_PendingOp(type=OP_MAXPOOL, flags=0, k=(k, k), stride=stride, pad=(pad, pad),
+                              weight=None, bias=None, cout=x.C), [x], y)
+        return y
+
+    def up_add(self, x: Sym, skip: Optional[Sym], w):
+        """depthwise ConvTranspose2d weight (C,1,2f,2f), stride f, pad f//2, + skip."""
+        C, _, k, _ = w.shape
+        f = k // 2
+        Ho = (x.H - 1) * f - 2 * (f // 2) + k; Wo = (x.W - 1) * f - 2 * (f // 2) + k
+        y = self._sym(C, Ho, Wo)
+        wp = self._dev(w.float().reshape(C, k * k).t())          # [k*k][C]
+        self._emit(_PendingOp(type=OP_DWDECONV_ADD, flags=0, k=(k, k), stride=f, pad=(f // 2, f // 2),
+                              weight=wp, bias=None, cout=C), [x], y, [skip])
+        return y
+
+    def dcn(self, x: Sym, w, b, om_w, om_b, relu=True):
+        """DCN module (dcn_v2.py:117-127) with BN already folded into (w, b)."""
+        om = self.conv([x], om_w.float(), om_b.float(), stride=1, pad=1, relu=False, out="f32")
+        co = w.shape[0]
+        y = self._sym(co, x.H, x.W)
+        self._emit(_PendingOp(type=OP_DCN, flags=FLAG_RELU if relu else 0, k=(3, 3), stride=1, pad=(1, 1),
+                              weight=self._pack_conv(w), bias=self._dev(b), cout=co, w_raw=w), [x], y, [om])
+        return y
+
+    # ---- finalisation -----------------------------------------------------------------------
+    def build(self) -> "Plan":
+        return Plan(self)
+
+
+class Plan:
+    """Allocated, ready-to-run op program for one (B, H, W, precision)."""
+
+    def __init__(self, pb: PlanBuilder):
+        self.pb = pb
+        self.device = pb.device
+        self._allocate(pb)
+        n = len(pb.ops)
+        self.ops = (OpStruct * n)()
+        self.in_slots = []      # (op index, src slot) fed by the network input
+        self.out_slots = {}     # output name -> list of op indices writing it
+        for i, po in enumerate(pb.ops):
+            o = self.ops[i]
+            o.type = po.type; o.flags = po.flags; o.act_dtype = pb.act_dtype
+            s0 = po.srcs[0]
+            o.B, o.H, o.W = pb.B, s0.H, s0.W
+            o.nsrc = len(po.srcs)
+            for j, s in enumerate(po.srcs):
+                o.cin[j] = s.C
+                if s.kind == "nchw_in":
+                    self.in_slots.append((i, j))
+                else:
+                    o.src[j] = s.buf.data_ptr()
+            o.cout = po.cout
+            o.kh, o.kw = po.k; o.stride = po.stride; o.pad_h, o.pad_w = po.pad
+            d = po.dst
+            if po.type == OP_CONV:
+                o.Hd, o.Wd, o.out_sy, o.out_sx, o.out_oy, o.out_ox = po.out_map
+                o.Ho, o.Wo = po.HoWo
+            else:
+                o.Ho, o.Wo, o.Hd, o.Wd = d.H, d.W, d.H, d.W
+                o.out_sy = o.out_sx = 1
+            o.out_ch_off = getattr(po, "ch_off", 0)
+            o.out_ch_total = d.C
+            if d.kind == "nchw_out":
+                self.out_slots.setdefault(d.name, []).append(i)
+            else:
+                o.dst = d.buf.data_ptr()
+            ex = po.extra
+            if po.type == OP_CONV and ex and ex[0] is not None:
+                o.res = ex[0].buf.data_ptr()
+            if po.type in (OP_DCN, OP_DWDECONV_ADD) and ex and ex[0] is not None:
+                o.aux = ex[0].buf.data_ptr()
+            if po.weight is not None:
+                o.weight = po.weight.data_ptr()
+            if po.bias is not None:
+                o.bias = po.bias.data_ptr()
+        if ctypes.sizeof(OpStruct) != _lib.lib().cpb200_sizeof_op():
+            raise RuntimeError("cpb200_op layout mismatch between Python binding and library")
+        self.n = n
+        self._prepared = False
+
+    def _allocate(self, pb: PlanBuilder):
+        """Liveness-based buffer reuse: a buffer returns to the pool after its last consumer."""
+        pool = {}
+        release_at = {}
+        esize = {"act": 4 if pb.act_dtype == F32 else 2, "f32": 4}
+        self.buffers = []
+        total = 0
+        for i, po in enumerate(pb.ops):
+            d = po.dst
+            if not d.fixed and d.buf is None:
+                nbytes = pb.B * d.H * d.W * d.C * esize[d.kind]
+                cand = [k for k in pool if k >= nbytes and pool[k]]
+                if cand:
+                    raw = pool[min(cand)].pop()
+                else:
+                    raw = torch.empty(nbytes, dtype=torch.uint8, device=pb.device)
+                    self.buffers.append(raw); total += nbytes
+                d.buf = raw
+                release_at.setdefault(d.last_use, []).append(d)
+            for s in release_at.pop(i, []):
+                pool.setdefault(s.buf.numel(), []).append(s.buf)
+        self.activation_bytes = total
+
+    def tensor(self, sym: Sym) -> torch.Tensor:
+        """View of an internal NHWC activation (valid until a later op reuses its buffer)."""
+        dt = torch.float32 if (sym.kind == "f32" or self.pb.act_dtype == F32) else torch.bfloat16
+        if sym.fixed:
+            return sym.buf
+        n = self.pb.B * sym.H * sym.W * sym.C
+        return sym.buf[: n * (4 if dt == torch.float32 else 2)].view(dt).view(self.pb.B, sym.H, sym.W, sym.C)
+
+    def bind(self, x: torch.Tensor, outs: dict):
+        """Point the program at this call's input and output tensors."""
+        for (i, j) in self.in_slots:
+            self.ops[i].src[j] = x.data_ptr()
+        for name, idxs in self.out_slots.items():
+            p = outs[name].data_ptr()
+            for i in idxs:
+                self.ops[i].dst = p
+
+    def run(self, stream: int):
+        L = _lib.lib()
+        if not self._prepared:
+            _lib.check(L.cpb200_prepare_ops(self.ops, self.n), "prepare_ops")
+            self._prepared = True
+        _lib.check(L.cpb200_run_ops(self.ops, self.n, stream), "run_ops")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_prepared", False):
+                _lib.lib().cpb200_release_ops(self.ops, self.n)
+        except Exception:
+            pass

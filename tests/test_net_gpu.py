@@ -1,0 +1,230 @@
+"""GPU parity tests of the fused network ops and the DLA-34 forward (through the C ABI op
+program) against torch-CPU fp32 references / the oracle / the reference-generated goldens.
+
+Tolerances (floating point, stated here as the task requires):
+  fp32 activations : |err| <= 2e-4 * max|ref|   (fp32 accumulate, different summation order)
+  bf16 activations : relative L2 error <= 3e-2 end to end, <= 1e-2 per op
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+
+def _nhwc(t, dtype):
+    return t.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)
+
+
+def _nchw(t):
+    return t.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def _check(got, ref, precision, op_tol=None):
+    scale = ref.abs().max().item() + 1e-12
+    if precision == "fp32":
+        assert (got - ref).abs().max().item() <= (op_tol or 2e-4) * scale
+    else:
+        rel = ((got - ref).norm() / (ref.norm() + 1e-12)).item()
+        assert rel <= (op_tol or 1e-2), rel
+
+
+def _builder(B, precision):
+    from centerpose_b200.plan import PlanBuilder
+    return PlanBuilder(B, 1, 1, precision, torch.device(DEV))
+
+
+def _run(pb, y):
+    plan = pb.build()
+    plan.run(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return plan.tensor(y).clone()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("cins,cout,k,stride,H,W,res,relu", [
+    ([16], 16, 3, 1, 20, 24, False, True), ([16], 32, 3, 2, 20, 24, False, True),
+    ([64], 64, 3, 1, 17, 13, True, True), ([32], 64, 1, 1, 9, 9, False, False),
+    ([64, 64, 32], 128, 1, 1, 10, 12, False, True), ([128], 27, 3, 1, 8, 8, False, False),
+    ([256], 34, 1, 1, 8, 8, False, False), ([64], 256, 3, 1, 12, 12, False, True),
+    ([512], 512, 3, 1, 4, 4, True, True),
+])
+def test_conv_op(precision, cins, cout, k, stride, H, W, res, relu):
+    B = 2
+    g = torch.Generator().manual_seed(sum(cins) + cout + k)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    xs = [torch.randn(B, c, H, W, generator=g) for c in cins]
+    if precision == "bf16":
+        xs = [x.bfloat16().float() for x in xs]
+    w = torch.randn(cout, sum(cins), k, k, generator=g) / (sum(cins) * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    pad = k // 2
+    ref = F.conv2d(torch.cat(xs, 1), w, b, stride=stride, padding=pad)
+    r = None
+    if res:
+        r = torch.randn(ref.shape, generator=g)
+        if precision == "bf16":
+            r = r.bfloat16().float()
+        ref = ref + r
+    if relu:
+        ref = F.relu(ref)
+    pb = _builder(B, precision)
+    sx = [pb.external(_nhwc(x, dt)) for x in xs]
+    sr = pb.external(_nhwc(r, dt)) if res else None
+    y = pb.conv(sx, w.to(DEV), b.to(DEV), stride=stride, pad=pad, relu=relu, res=sr)
+    _check(_nchw(_run(pb, y)), ref, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_conv_nchw_and_f32_outputs(precision):
+    B, C, H, W = 2, 32, 6, 10
+    g = torch.Generator().manual_seed(1)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    x = torch.randn(B, C, H, W, generator=g).bfloat16().float()
+    w = torch.randn(5, C, 1, 1, generator=g) * 0.2; b = torch.randn(5, generator=g)
+    ref = F.conv2d(x, w, b)
+    pb = _builder(B, precision)
+    out = torch.zeros(B, 7, H, W, device=DEV)
+    dst = pb.output(7, H, W, "o")
+    pb.conv([pb.external(_nhwc(x, dt))], w.to(DEV), b.to(DEV), out="nchw", dst=dst, ch_off=2)
+    y32 = pb.conv([pb.external(_nhwc(x, dt))], w.to(DEV), b.to(DEV), out="f32")
+    plan = pb.build()
+    plan.bind(torch.zeros(1, device=DEV), {"o": out})
+    plan.run(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    _check(out[:, 2:7].cpu(), ref, precision, 2e-3 if precision == "bf16" else None)
+    assert out[:, :2].abs().max().item() == 0
+    assert plan.tensor(y32).dtype == torch.float32
+    _check(_nchw(plan.tensor(y32)), ref, precision, 2e-3 if precision == "bf16" else None)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_stem_maxpool_upadd_ops(precision):
+    B = 2
+    g = torch.Generator().manual_seed(2)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    # stem 7x7 3->16 on NCHW fp32 input
+    x = torch.randn(B, 3, 32, 40, generator=g)
+    w = torch.randn(16, 3, 7, 7, generator=g) * 0.1; b = torch.randn(16, generator=g)
+    pb = _builder(B, precision); pb.H, pb.W = 32, 40
+    xin = pb.input(3)
+    y = pb.stem(xin, w.to(DEV), b.to(DEV), 7, 1, 3, relu=True)
+    plan = pb.build(); plan.bind(x.to(DEV), {}); plan.run(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    _check(_nchw(plan.tensor(y)), F.relu(F.conv2d(x, w, b, padding=3)), precision)
+    # maxpool 2x2/s2 and 3x3/s2/p1
+    t = torch.randn(B, 32, 16, 20, generator=g).bfloat16().float()
+    for (k, s, p) in ((2, 2, 0), (3, 2, 1)):
+        pb = _builder(B, precision)
+        y = pb.maxpool(pb.external(_nhwc(t, dt)), k, s, p)
+        assert torch.equal(_nchw(_run(pb, y)), F.max_pool2d(t, k, s, p))
+    # depthwise deconv (f = 2 and f = 4) + skip
+    for f in (2, 4):
+        C = 32
+        xx = torch.randn(B, C, 6, 7, generator=g).bfloat16().float()
+        ww = torch.rand(C, 1, 2 * f, 2 * f, generator=g)
+        ref_up = F.conv_transpose2d(xx, ww, None, stride=f, padding=f // 2, groups=C)
+        skip = torch.randn(ref_up.shape, generator=g).bfloat16().float()
+        pb = _builder(B, precision)
+        y = pb.up_add(pb.external(_nhwc(xx, dt)), pb.external(_nhwc(skip, dt)), ww.to(DEV))
+        _check(_nchw(_run(pb, y)), ref_up + skip, precision)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("ci,co,H,W", [(64, 64, 12, 14), (128, 64, 8, 8), (32, 48, 9, 11)])
+def test_dcn_op_matches_oracle(precision, ci, co, H, W):
+    from oracle import dcn_ref
+    B = 2
+    g = torch.Generator().manual_seed(ci + co)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    x = torch.randn(B, ci, H, W, generator=g).bfloat16().float()
+    w = torch.randn(co, ci, 3, 3, generator=g) / (ci * 9) ** 0.5; b = torch.randn(co, generator=g)
+    ow = torch.randn(27, ci, 3, 3, generator=g) * (1.5 / (ci * 9) ** 0.5); ob = torch.randn(27, generator=g)
+    ref = F.relu(dcn_ref.dcn_module_forward(x, w, b, ow, ob))
+    pb = _builder(B, precision)
+    y = pb.dcn(pb.external(_nhwc(x, dt)), w.to(DEV), b.to(DEV), ow.to(DEV), ob.to(DEV), relu=True)
+    # bf16: offsets come from a bf16-input conv -> sampling positions differ slightly
+    _check(_nchw(_run(pb, y)), ref, precision, 2e-2 if precision == "bf16" else 5e-4)
+
+
+def test_dcn_zero_offset_identity():
+    """DCNv2/test.py:31-66 check_zero_offset on the CUDA op: 2 * out == in."""
+    B, C, H, W = 2, 16, 10, 12
+    x = torch.randn(B, C, H, W, generator=torch.Generator().manual_seed(0))
+    w = torch.zeros(C, C, 3, 3)
+    for c in range(C):
+        w[c, c, 1, 1] = 1.0
+    pb = _builder(B, "fp32")
+    y = pb.dcn(pb.external(_nhwc(x, torch.float32)), w.to(DEV), torch.zeros(C, device=DEV),
+               torch.zeros(27, C, 3, 3, device=DEV), torch.zeros(27, device=DEV), relu=False)
+    out = _nchw(_run(pb, y))
+    assert (2 * out - x).abs().max().item() < 1e-6
+
+
+def _model(precision):
+    from centerpose_b200.config import default_cfg
+    from centerpose_b200.model import create_model
+    from oracle.init_recipe import conditioned_state_dict
+    cfg = default_cfg("dla_34")
+    m = create_model(cfg.MODEL.NAME, cfg.MODEL.HEAD_CONV, cfg)
+    sd = conditioned_state_dict(m.state_dict(), 317)
+    m.load_state_dict(sd)
+    return m.to(DEV).set_precision(precision), sd
+
+
+@pytest.mark.parametrize("tag", ["128", "96x160"])
+def test_dla34_fp32_matches_reference_golden(tag):
+    from oracle.init_recipe import synth_images
+    g = np.load(os.path.join(GOLD, f"dla34_{tag}.npz"))
+    B, H, W = [int(v) for v in g["shape"]]
+    m, _ = _model("fp32")
+    maps = torch.cat(m(synth_images(B, H, W, 317).to(DEV)), dim=1).cpu().numpy()
+    ref = g["maps"]
+    assert maps.shape == ref.shape
+    assert np.abs(maps - ref).max() <= 5e-4 * np.abs(ref).max()
+
+
+def test_dla34_forward_vs_oracle_both_precisions():
+    from oracle import dla_ref
+    from oracle.init_recipe import synth_images
+    x = synth_images(2, 128, 160, seed=5)
+    m, sd = _model("fp32")
+    ref = torch.cat(dla_ref.forward(sd, x), dim=1)
+    got = torch.cat(m(x.to(DEV)), dim=1).cpu()
+    assert (got - ref).abs().max().item() <= 5e-4 * ref.abs().max().item()
+    m.set_precision("bf16")
+    got16 = torch.cat(m(x.to(DEV)), dim=1).cpu()
+    rel = ((got16 - ref).norm() / ref.norm()).item()
+    assert rel <= 3e-2, rel
+
+
+def test_dla34_512_end_to_end_vs_reference_golden():
+    """Full-size config image: head maps (stride-4 subsample) and decoded detections against the
+    reference's own outputs; detections compared tie-/discontinuity-aware (top-K is
+    discontinuous: rows are matched on bbox+score, then compared element-wise)."""
+    from centerpose_b200 import multi_pose_decode
+    from oracle.init_recipe import synth_images
+    from tests.util import match_rows
+    g = np.load(os.path.join(GOLD, "dla34_512.npz"))
+    m, _ = _model("fp32")
+    outs = m(synth_images(1, 512, 512, 317).to(DEV))
+    maps = torch.cat(outs, dim=1).cpu().numpy()[:, :, ::4, ::4]
+    assert np.abs(maps - g["maps"]).max() <= 5e-4 * np.abs(g["maps"]).max()
+    hm, wh, hps, reg, hm_hp, hp_off = outs
+    dets = multi_pose_decode(hm, wh, hps, reg=reg, hm_hp=hm_hp, hp_offset=hp_off, K=100, apply_sigmoid=True)
+    rows, elems = match_rows(dets[0].cpu().numpy(), g["dets"][0], tol=1e-3, box_tol=2e-2)
+    assert rows >= 0.9 and elems >= 0.97, (rows, elems)
+
+
+def test_forward_rejects_cpu_and_training():
+    m, _ = _model("bf16")
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64))
+    m.train()
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64, device=DEV))

@@ -101,7 +101,7 @@ def test_post_process_matches_golden():
 def test_dla34_oracle_matches_golden(tag):
     g = np.load(os.path.join(GOLD, f"dla34_{tag}.npz"))
     B, H, W = [int(v) for v in g["shape"]]
-    from centerpose_b200.models import create_model
+    from centerpose_b200.model import create_model
     from centerpose_b200.config import default_cfg
     cfg = default_cfg("dla_34")
     tmpl = create_model(cfg.MODEL.NAME, cfg.MODEL.HEAD_CONV, cfg).state_dict()
