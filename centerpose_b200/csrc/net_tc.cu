@@ -1,7 +1,420 @@
-// tcgen05 / TMA tensor-core path (placeholder until the kernels land).
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (bf16 NHWC activations, fp32
+// accumulate in tensor memory).
+//
+//   M tile  = 128 output pixels = a TH x TW rectangle of one image (8x16, or 16x8 for narrow maps)
+//   N tile  = BN output channels (16..256), one tcgen05.mma.cta_group::1.kind::f16 of shape 128 x BN x 16
+//   K loop  = filter taps x concatenated inputs x channel slabs of BK (64/32/16 = one swizzle atom)
+//
+// A operand: for tap (r,s) the 128 x BK slab is the input window
+//   x[n, h0*stride + r - pad : .. : stride, w0*stride + s - pad : .. : stride, c0 : c0+BK]
+// fetched by ONE 4-D TMA tiled load (box {BK, TW, TH, 1}, element strides {1,stride,stride,1});
+// TMA zero-fills out-of-bounds coordinates, which IS the convolution's zero padding, and lands the
+// box in shared memory as 128 rows of BK bf16 in the 128B/64B/32B-swizzled K-major layout the UMMA
+// shared-memory descriptor expects — no im2col buffer exists anywhere.
+// B operand: weights packed [tap][Cout_pad][Cin_total] bf16 (K-major), 3-D TMA box {BK, BN, 1}.
+// `Root` concatenations are K-slabs from up to four tensor maps (no torch.cat copy).
+//
+// Warp roles (192 threads, persistent CTAs, one per SM): warp 0 = TMA producer, warp 1 = MMA
+// issuer + TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> +bias (+residual) -> ReLU -> bf16 ->
+// global).  Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1;
+// a STAGES-deep smem ring with full/empty mbarriers feeds the tensor core.
 #include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int TILE_M = 128;
+
+struct alignas(64) TcArgs {
+  CUtensorMap amap[4];
+  CUtensorMap bmap;
+  int cin[4];
+  int nsrc;
+  int kh, kw, stride, pad_h, pad_w;
+  int B, Ho, Wo;
+  int TH, TW, tiles_h, tiles_w, n_tiles;
+  int cout, cout_store;       // cout_store: channel pitch of dst/res
+  int BK, stages, total_tiles;
+  void *dst;
+  const void *res;
+  const float *bias;
+  unsigned flags;
+  unsigned swizzle_bits;      // UMMA layout_type for the chosen BK
+};
+
+// ------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmap_prefetch(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, rows of `row_bytes` (= swizzle span), 8-row
+// core-matrix groups packed back to back (what a TMA box with inner extent = swizzle span writes).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                 // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                                  // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)((8u * row_bytes) >> 4) << 32;            // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                                  // descriptor version 1 (sm_100)
+  d |= (uint64_t)layout_type << 61;                        // 2 = SW128, 4 = SW64, 6 = SW32
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A | B)] then barriers
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_bytes = TILE_M * a.BK * 2, b_bytes = BN * a.BK * 2;
+  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
+  __shared__ __align__(8) uint64_t bars[2 * 8 + 4];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_bias[2][BN];
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
+  const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[18]);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < a.nsrc; ++s) tmap_prefetch(&a.amap[s]);
+    tmap_prefetch(&a.bmap);
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  const int taps = a.kh * a.kw;
+  int kblocks_per_tap = 0;
+  for (int s = 0; s < a.nsrc; ++s) kblocks_per_tap += a.cin[s] / a.BK;
+  const int kblocks = taps * kblocks_per_tap;
+
+  auto decode_tile = [&](int t, int &n, int &h0, int &w0, int &nt) {
+    nt = t % a.n_tiles; t /= a.n_tiles;
+    const int tw = t % a.tiles_w; t /= a.tiles_w;
+    const int th = t % a.tiles_h; n = t / a.tiles_h;
+    h0 = th * a.TH; w0 = tw * a.TW;
+  };
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
+        for (int tap = 0; tap < taps; ++tap) {
+          const int r = tap / a.kw, s_ = tap % a.kw;
+          const int hi = h0 * a.stride + r - a.pad_h, wi = w0 * a.stride + s_ - a.pad_w;
+          int cb = 0;
+          for (int s = 0; s < a.nsrc; ++s) {
+            for (int c0 = 0; c0 < a.cin[s]; c0 += a.BK) {
+              mbar_wait(empty0 + 8 * stage, phase ^ 1);
+              const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
+              mbar_expect_tx(full0 + 8 * stage, a_bytes + b_bytes);
+              tma_load_4d(sa, &a.amap[s], full0 + 8 * stage, c0, wi, hi, n);
+              tma_load_3d(sb, &a.bmap, full0 + 8 * stage, cb + c0, nt * BN, tap);
+              if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
+            cb += a.cin[s];
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t accphase = 0;
+    const uint32_t row_bytes = a.BK * 2;
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
+          const uint64_t ad = make_desc(sa, row_bytes, a.swizzle_bits), bd = make_desc(sb, row_bytes, a.swizzle_bits);
+          for (int k = 0; k < a.BK / 16; ++k)
+            umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty0 + 8 * stage);              // frees the smem slot when these MMAs retire
+          if (kb == kblocks - 1) umma_commit(tfull0 + 8 * acc);
+        }
+        __syncwarp();
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; accphase ^= 1; }
+    }
+  } else {
+    // =============================== epilogue (warps 2..5) ===============================
+    const int q = warp & 3;                              // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;                     // 0..127
+    const bool relu = a.flags & CPB200_FLAG_RELU;
+    const bool out_f32 = a.flags & CPB200_FLAG_OUT_F32;
+    int acc = 0; uint32_t accphase = 0;
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
+      const int n0 = nt * BN;
+      for (int i = et; i < BN; i += 128) s_bias[acc][i] = (a.bias && n0 + i < a.cout) ? __ldg(a.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tfull0 + 8 * acc, accphase);
+      tc_fence_after();
+      const int th = row / a.TW, tw = row % a.TW;
+      const int ho = h0 + th, wo = w0 + tw;
+      const bool ok = ho < a.Ho && wo < a.Wo;
+      const size_t pix = ((size_t)n * a.Ho + ho) * a.Wo + wo;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c * 16, v);
+        tmem_ld_wait();
+        const int nb = n0 + c * 16;
+        if (ok && nb < a.cout) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[acc][c * 16 + j];
+          if (out_f32) {
+            float *o = static_cast<float *>(a.dst) + pix * a.cout_store + nb;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nb + j < a.cout) o[j] = relu ? fmaxf(f[j], 0.f) : f[j];
+          } else {
+            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(a.dst) + pix * a.cout_store + nb;
+            if (a.res) {
+              const uint4 *rp = reinterpret_cast<const uint4 *>(static_cast<const __nv_bfloat16 *>(a.res) + pix * a.cout_store + nb);
+              uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+              const __nv_bfloat162 *rb0 = reinterpret_cast<const __nv_bfloat162 *>(&r0);
+              const __nv_bfloat162 *rb1 = reinterpret_cast<const __nv_bfloat162 *>(&r1);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 x0 = __bfloat1622float2(rb0[j]), x1 = __bfloat1622float2(rb1[j]);
+                f[2 * j] += x0.x; f[2 * j + 1] += x0.y; f[8 + 2 * j] += x1.x; f[8 + 2 * j + 1] += x1.y;
+              }
+            }
+            if (relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint4 o0, o1;
+            __nv_bfloat162 *ob0 = reinterpret_cast<__nv_bfloat162 *>(&o0), *ob1 = reinterpret_cast<__nv_bfloat162 *>(&o1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              ob0[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              ob1[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+            }
+            reinterpret_cast<uint4 *>(o)[0] = o0;
+            reinterpret_cast<uint4 *>(o)[1] = o1;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (++acc == 2) { acc = 0; accphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct TcOp {
+  TcArgs args;
+  int BN;
+  int grid;
+  size_t smem;
+};
+
+int g_num_sms = 0;
+
+template <int BN>
+int launch_tc(const TcOp &t, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CPB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+    attr_set = true;
+  }
+  conv_tc_kernel<BN><<<t.grid, TC_THREADS, t.smem, st>>>(t.args);
+  return cpb::check_launch("conv_tc_kernel");
+}
+
+}  // namespace
+
 namespace cpb {
-int tc_prepare_op(cpb200_op &op) { return fail(CPB200_ERR_STATE, "tensor-core path not built"); }
-int tc_release_op(cpb200_op &op) { op.tc = nullptr; return CPB200_OK; }
-int tc_run_op(const cpb200_op &op, cudaStream_t st) { return fail(CPB200_ERR_STATE, "tensor-core path not built"); }
+
+int tc_prepare_op(cpb200_op &op) {
+  if (op.type != CPB200_OP_CONV) return fail(CPB200_ERR_ARG, "tc: only CONV ops run on the tensor-core path");
+  if (op.act_dtype != CPB200_BF16) return fail(CPB200_ERR_ARG, "tc: bf16 activations required");
+  if (op.flags & CPB200_FLAG_OUT_NCHW_F32) return fail(CPB200_ERR_ARG, "tc: NCHW output not supported");
+  if (op.stride < 1 || op.stride > 2) return fail(CPB200_ERR_ARG, "tc: stride %d", op.stride);
+  if (op.out_sy != 1 || op.out_sx != 1 || op.out_oy || op.out_ox || op.Hd != op.Ho || op.Wd != op.Wo)
+    return fail(CPB200_ERR_ARG, "tc: strided output not supported");
+  if (op.Wo < 8 || op.Ho < 1) return fail(CPB200_ERR_ARG, "tc: output too small");
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return fail(CPB200_ERR_STATE, "tc: cuTensorMapEncodeTiled unavailable");
+  if (!g_num_sms) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  TcOp *t = new TcOp();
+  TcArgs &a = t->args;
+  memset(&a, 0, sizeof(a));
+  int cin_total = 0, bk = 64;
+  for (int s = 0; s < op.nsrc; ++s) {
+    const int c = op.cin[s];
+    if (c % 16) { delete t; return fail(CPB200_ERR_ARG, "tc: cin %d not a multiple of 16", c); }
+    if (c % 64) bk = (c % 32 == 0) ? (bk < 32 ? bk : 32) : 16;
+    a.cin[s] = c; cin_total += c;
+  }
+  a.nsrc = op.nsrc; a.BK = bk;
+  const CUtensorMapSwizzle sw = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  a.swizzle_bits = bk == 64 ? 2u : bk == 32 ? 4u : 6u;
+  a.kh = op.kh; a.kw = op.kw; a.stride = op.stride; a.pad_h = op.pad_h; a.pad_w = op.pad_w;
+  a.B = op.B; a.Ho = op.Ho; a.Wo = op.Wo;
+  a.TW = op.Wo >= 16 ? 16 : 8; a.TH = TILE_M / a.TW;
+  a.tiles_h = (op.Ho + a.TH - 1) / a.TH; a.tiles_w = (op.Wo + a.TW - 1) / a.TW;
+  int BN = 16;
+  while (BN < op.cout && BN < 256) BN <<= 1;
+  t->BN = BN;
+  a.n_tiles = (op.cout + BN - 1) / BN;
+  a.cout = op.cout; a.cout_store = op.cout;
+  if (!(op.flags & CPB200_FLAG_OUT_F32) && (op.cout % 16)) { delete t; return fail(CPB200_ERR_ARG, "tc: bf16 output needs cout %% 16 == 0"); }
+  a.total_tiles = op.B * a.tiles_h * a.tiles_w * a.n_tiles;
+  a.dst = op.dst; a.res = op.res; a.bias = op.bias; a.flags = op.flags;
+  const size_t a_bytes = (size_t)TILE_M * bk * 2, b_bytes = ((size_t)BN * bk * 2 + 1023) / 1024 * 1024;
+  const size_t budget = 200 * 1024;
+  int stages = (int)(budget / (a_bytes + b_bytes));
+  if (stages > 8) stages = 8;
+  if (stages < 2) { delete t; return fail(CPB200_ERR_ARG, "tc: tile does not fit shared memory"); }
+  a.stages = stages;
+  t->smem = stages * (a_bytes + b_bytes) + 1024;
+  t->grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
+
+  for (int s = 0; s < op.nsrc; ++s) {
+    const cuuint64_t dims[4] = {(cuuint64_t)op.cin[s], (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)op.cin[s] * 2, (cuuint64_t)op.W * op.cin[s] * 2, (cuuint64_t)op.H * op.W * op.cin[s] * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(a.TW * op.stride), (cuuint32_t)(a.TH * op.stride), 1};
+    const cuuint32_t estr[4] = {1, (cuuint32_t)op.stride, (cuuint32_t)op.stride, 1};
+    CUresult r = enc(&a.amap[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(op.src[s]), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { delete t; return fail(CPB200_ERR_CUDA, "tc: cuTensorMapEncodeTiled(A[%d]) failed: %d", s, (int)r); }
+  }
+  {
+    const int cout_pad = (op.cout + 15) / 16 * 16;
+    const cuuint64_t dims[3] = {(cuuint64_t)cin_total, (cuuint64_t)cout_pad, (cuuint64_t)(op.kh * op.kw)};
+    const cuuint64_t strides[2] = {(cuuint64_t)cin_total * 2, (cuuint64_t)cout_pad * cin_total * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)BN, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&a.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(op.weight), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { delete t; return fail(CPB200_ERR_CUDA, "tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r); }
+  }
+  op.tc = t;
+  return CPB200_OK;
+}
+
+int tc_release_op(cpb200_op &op) {
+  delete static_cast<TcOp *>(op.tc);
+  op.tc = nullptr;
+  return CPB200_OK;
+}
+
+int tc_run_op(const cpb200_op &op, cudaStream_t st) {
+  const TcOp *t = static_cast<const TcOp *>(op.tc);
+  if (!t) return fail(CPB200_ERR_STATE, "tc: op not prepared");
+  switch (t->BN) {
+    case 16: return launch_tc<16>(*t, st);
+    case 32: return launch_tc<32>(*t, st);
+    case 64: return launch_tc<64>(*t, st);
+    case 128: return launch_tc<128>(*t, st);
+    case 256: return launch_tc<256>(*t, st);
+  }
+  return fail(CPB200_ERR_STATE, "tc: bad BN");
+}
+
 }  // namespace cpb

@@ -1,0 +1,250 @@
+"""Host-side mirror of the reference's detector classes (``lib/detectors/base_detector.py``,
+``lib/detectors/multi_pose.py``, ``lib/detectors/detector_factory.py``): same constructor,
+``run / pre_process / process / post_process / merge_outputs`` methods, result dictionary and the
+seven timing keys — with the network forward and the decode running as fused CUDA kernels.
+
+Differences that are additive only:
+  * ``process`` hands the head logits to the decode kernel, which applies the logistic itself
+    (``multi_pose.py:35-37`` folded into the kernel); the returned ``outputs`` still carry the
+    sigmoid'ed ``hm`` / ``hm_hp`` like the reference's in-place ``sigmoid_``;
+  * flip-test averaging (``multi_pose.py:45-53``) is done on the device — the reference's
+    ``flip_lr`` / ``flip_lr_off`` round-trip through numpy (``lib/models/utils.py:30-47``);
+  * ``run_batch`` (new): many pre-processed images per call — the reference API is single-image.
+"""
+from __future__ import annotations
+
+import time
+
+import cv2
+import numpy as np
+import torch
+
+from .decode import multi_pose_decode, sigmoid_
+from .image import get_affine_transform, multi_pose_post_process
+from .model import create_model, load_model
+from .soft_nms import soft_nms_39
+
+FLIP_IDX = [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]]   # multi_pose.py:27
+
+
+class BaseDetector(object):
+    def __init__(self, cfg):
+        print("Creating model...")
+        self.model = create_model(cfg.MODEL.NAME, cfg.MODEL.HEAD_CONV, cfg)
+        if getattr(cfg.TEST, "MODEL_PATH", ""):
+            self.model = load_model(self.model, cfg.TEST.MODEL_PATH)
+        if not torch.cuda.is_available():
+            raise RuntimeError("centerpose_b200 detectors need a CUDA device (no CPU path)")
+        self.model = self.model.to(torch.device("cuda"))
+        self.model.eval()
+        self.mean = np.array(cfg.DATASET.MEAN, dtype=np.float32).reshape(1, 1, 3)
+        self.std = np.array(cfg.DATASET.STD, dtype=np.float32).reshape(1, 1, 3)
+        self.max_per_image = 100
+        self.num_classes = cfg.MODEL.NUM_CLASSES
+        self.scales = cfg.TEST.TEST_SCALES
+        self.cfg = cfg
+        self.pause = True
+
+    def pre_process(self, image, scale, meta=None):
+        """base_detector.py:32-62 — resize, centre-crop affine warp to the network input, normalise,
+        HWC->CHW, optional mirrored copy; returns the (1 or 2,3,H,W) tensor and the c/s/out-size meta."""
+        height, width = image.shape[0:2]
+        new_height, new_width = int(height * scale), int(width * scale)
+        if self.cfg.TEST.FIX_RES:
+            inp_height, inp_width = self.cfg.MODEL.INPUT_H, self.cfg.MODEL.INPUT_W
+            c = np.array([new_width / 2., new_height / 2.], dtype=np.float32)
+            s = max(height, width) * 1.0
+        else:
+            inp_height = (new_height | self.cfg.MODEL.PAD) + 1
+            inp_width = (new_width | self.cfg.MODEL.PAD) + 1
+            c = np.array([new_width // 2, new_height // 2], dtype=np.float32)
+            s = np.array([inp_width, inp_height], dtype=np.float32)
+        trans_input = get_affine_transform(c, s, 0, [inp_width, inp_height])
+        resized = cv2.resize(image, (new_width, new_height))
+        inp = cv2.warpAffine(resized, trans_input, (inp_width, inp_height), flags=cv2.INTER_LINEAR)
+        inp = ((inp / 255. - self.mean) / self.std).astype(np.float32)
+        images = inp.transpose(2, 0, 1).reshape(1, 3, inp_height, inp_width)
+        if self.cfg.TEST.FLIP_TEST:
+            images = np.concatenate((images, images[:, :, :, ::-1]), axis=0)
+        images = torch.from_numpy(np.ascontiguousarray(images))
+        meta = {"c": c, "s": s, "out_height": inp_height // self.cfg.MODEL.DOWN_RATIO,
+                "out_width": inp_width // self.cfg.MODEL.DOWN_RATIO}
+        return images, meta
+
+    def process(self, images, return_time=False):
+        raise NotImplementedError
+
+    def post_process(self, dets, meta, scale=1):
+        raise NotImplementedError
+
+    def merge_outputs(self, detections):
+        raise NotImplementedError
+
+    def debug(self, debugger, images, dets, output, scale=1):
+        raise NotImplementedError
+
+    def show_results(self, debugger, image, results):
+        raise NotImplementedError
+
+    def run(self, image_or_path_or_tensor, meta=None):
+        """base_detector.py:79-140 — same inputs (ndarray / path / pre-processed dict), same result
+        dict: ``{'results': {1: rows}, 'tot','load','pre','net','dec','post','merge'}``."""
+        load_time = pre_time = net_time = dec_time = post_time = merge_time = tot_time = 0
+        start_time = time.time()
+        pre_processed = False
+        if isinstance(image_or_path_or_tensor, np.ndarray):
+            image = image_or_path_or_tensor
+        elif isinstance(image_or_path_or_tensor, str):
+            image = cv2.imread(image_or_path_or_tensor)
+            if image is None:
+                raise FileNotFoundError(image_or_path_or_tensor)
+        else:
+            image = image_or_path_or_tensor["image"][0].numpy()
+            pre_processed_images = image_or_path_or_tensor
+            pre_processed = True
+        loaded_time = time.time()
+        load_time += loaded_time - start_time
+        detections = []
+        for scale in self.scales:
+            scale_start_time = time.time()
+            if not pre_processed:
+                images, meta = self.pre_process(image, scale, meta)
+            else:
+                images = pre_processed_images["images"][scale][0]
+                meta = pre_processed_images["meta"][scale]
+                meta = {k: v.numpy()[0] for k, v in meta.items()}
+            images = images.to(torch.device("cuda"))
+            torch.cuda.synchronize()
+            pre_process_time = time.time()
+            pre_time += pre_process_time - scale_start_time
+            output, dets, forward_time = self.process(images, return_time=True)
+            torch.cuda.synchronize()
+            net_time += forward_time - pre_process_time
+            decode_time = time.time()
+            dec_time += decode_time - forward_time
+            if self.cfg.DEBUG >= 2:
+                self.debug(None, images, dets, output, scale)
+            dets = self.post_process(dets, meta, scale)
+            torch.cuda.synchronize()
+            post_process_time = time.time()
+            post_time += post_process_time - decode_time
+            detections.append(dets)
+        results = self.merge_outputs(detections)
+        torch.cuda.synchronize()
+        end_time = time.time()
+        merge_time += end_time - post_process_time
+        tot_time += end_time - start_time
+        if self.cfg.DEBUG >= 1:
+            self.show_results(None, image, results)
+        return {"results": {1: results}, "tot": tot_time, "load": load_time, "pre": pre_time,
+                "net": net_time, "dec": dec_time, "post": post_time, "merge": merge_time}
+
+
+def _swap_pairs(C, pairs, device):
+    idx = list(range(C))
+    for a, b in pairs:
+        idx[a], idx[b] = idx[b], idx[a]
+    return torch.tensor(idx, device=device, dtype=torch.long)
+
+
+class MultiPoseDetector(BaseDetector):
+    def __init__(self, cfg):
+        super(MultiPoseDetector, self).__init__(cfg)
+        self.flip_idx = FLIP_IDX
+
+    # -- device-side flip helpers (semantics of lib/models/utils.py:27-47 without the host round-trip)
+    def _flip_lr(self, x):
+        return torch.flip(x, [3]).index_select(1, _swap_pairs(x.shape[1], self.flip_idx, x.device))
+
+    def _flip_lr_off(self, x):
+        B, C, H, W = x.shape
+        t = torch.flip(x, [3]).view(B, C // 2, 2, H, W).clone()
+        t[:, :, 0] *= -1
+        t = t.index_select(1, _swap_pairs(C // 2, self.flip_idx, x.device))
+        return t.view(B, C, H, W)
+
+    def process(self, images, return_time=False):
+        """multi_pose.py:29-60."""
+        cfg = self.cfg
+        with torch.no_grad():
+            torch.cuda.synchronize()
+            outputs = self.model(images)
+            hm, wh, hps, reg, hm_hp, hp_offset = outputs
+            use_hm_hp = cfg.LOSS.HM_HP
+            sig_hp = use_hm_hp and not cfg.LOSS.MSE_LOSS
+            reg = reg if cfg.LOSS.REG_OFFSET else None
+            hm_hp = hm_hp if use_hm_hp else None
+            hp_offset = hp_offset if cfg.LOSS.REG_HP_OFFSET else None
+            if cfg.TEST.FLIP_TEST:
+                sigmoid_(hm)
+                if sig_hp:
+                    sigmoid_(hm_hp)
+                torch.cuda.synchronize()
+                forward_time = time.time()
+                hm = (hm[0:1] + torch.flip(hm[1:2], [3])) / 2
+                wh = (wh[0:1] + torch.flip(wh[1:2], [3])) / 2
+                hps = (hps[0:1] + self._flip_lr_off(hps[1:2])) / 2
+                hm_hp = (hm_hp[0:1] + self._flip_lr(hm_hp[1:2])) / 2 if hm_hp is not None else None
+                reg = reg[0:1] if reg is not None else None
+                hp_offset = hp_offset[0:1] if hp_offset is not None else None
+                dets = multi_pose_decode(hm, wh, hps, reg=reg, hm_hp=hm_hp, hp_offset=hp_offset, K=cfg.TEST.TOPK)
+            elif sig_hp or hm_hp is None:
+                # logits go straight into the decode kernel (fused logistic); `outputs` still get
+                # the reference's in-place sigmoid so callers (debug viz) see the same tensors
+                torch.cuda.synchronize()
+                forward_time = time.time()
+                dets = multi_pose_decode(hm, wh, hps, reg=reg, hm_hp=hm_hp, hp_offset=hp_offset,
+                                         K=cfg.TEST.TOPK, apply_sigmoid=True)
+                sigmoid_(hm)
+                if hm_hp is not None:
+                    sigmoid_(hm_hp)
+            else:                      # MSE_LOSS: hm_hp is used raw, hm is sigmoid'ed
+                sigmoid_(hm)
+                torch.cuda.synchronize()
+                forward_time = time.time()
+                dets = multi_pose_decode(hm, wh, hps, reg=reg, hm_hp=hm_hp, hp_offset=hp_offset, K=cfg.TEST.TOPK)
+        if return_time:
+            return outputs, dets, forward_time
+        return outputs, dets
+
+    def post_process(self, dets, meta, scale=1):
+        """multi_pose.py:62-71 (single image: a batch is flattened into one image's rows, as there)."""
+        dets = dets.detach().cpu().numpy().reshape(1, -1, dets.shape[2])
+        out = multi_pose_post_process(dets.copy(), [meta["c"]], [meta["s"]], meta["out_height"], meta["out_width"])
+        for j in range(1, self.num_classes + 1):
+            out[0][j] = np.array(out[0][j], dtype=np.float32).reshape(-1, 56)
+            out[0][j][:, :4] /= scale
+            out[0][j][:, 5:39] /= scale
+        return out[0]
+
+    def merge_outputs(self, detections):
+        """multi_pose.py:73-79."""
+        results = np.concatenate([d[1] for d in detections], axis=0).astype(np.float32)
+        if self.cfg.TEST.NMS or len(self.cfg.TEST.TEST_SCALES) > 1:
+            soft_nms_39(results, Nt=0.5, method=2)
+        return results.tolist()
+
+    def debug(self, debugger, images, dets, output, scale=1):
+        raise NotImplementedError("visual debugging (lib/utils/debugger.py) is outside the B200 hot path")
+
+    def show_results(self, debugger, image, results):
+        raise NotImplementedError("visualisation (lib/utils/debugger.py) is outside the B200 hot path")
+
+    # -- additive: batched throughput path ---------------------------------------------------
+    @torch.no_grad()
+    def run_batch(self, images: torch.Tensor, metas=None):
+        """images (B,3,H,W) pre-processed (host or device).  Returns the (B,K,56) detections in
+        output-grid units on the device, or per-image post-processed dicts when ``metas`` is given."""
+        images = images.to(torch.device("cuda"), non_blocking=True)
+        hm, wh, hps, reg, hm_hp, hp_offset = self.model(images)
+        cfg = self.cfg
+        dets = multi_pose_decode(hm, wh, hps, reg=reg if cfg.LOSS.REG_OFFSET else None, hm_hp=hm_hp,
+                                 hp_offset=hp_offset if cfg.LOSS.REG_HP_OFFSET else None,
+                                 K=cfg.TEST.TOPK, apply_sigmoid=True)
+        if metas is None:
+            return dets
+        host = dets.cpu().numpy()
+        return [self.post_process(torch.from_numpy(host[i:i + 1]), metas[i]) for i in range(host.shape[0])]
+
+
+detector_factory = {"multi_pose": MultiPoseDetector}     # detector_factory.py:5-7

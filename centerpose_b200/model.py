@@ -68,7 +68,7 @@ class BackBoneWithHead(nn.Module):
         b200 = cfg.get("B200", None) if hasattr(cfg, "get") else getattr(cfg, "B200", None)
         self.precision = (b200 or {}).get("PRECISION", "bf16") if isinstance(b200, dict) else "bf16"
         self._plans = {}
-        self._weights_version = 0
+        self.tc = None
         self.eval()
 
     # -- weight changes invalidate packed plans
@@ -85,18 +85,21 @@ class BackBoneWithHead(nn.Module):
     def invalidate(self):
         self._plans = {}
 
-    def set_precision(self, precision: str):
+    def set_precision(self, precision: str, tc=None):
+        """'fp32' (CUDA-core kernels, reference-precision) or 'bf16' (tcgen05 tensor-core kernels;
+        tc=False keeps bf16 activations but forces the CUDA-core kernels — debugging aid)."""
         if precision not in ("fp32", "bf16"):
             raise ValueError(precision)
         self.precision = precision
+        self.tc = tc
         self.invalidate()
         return self
 
     def _plan(self, B, H, W, device):
-        key = (B, H, W, self.precision, device.index)
+        key = (B, H, W, self.precision, self.tc, device.index)
         plan = self._plans.get(key)
         if plan is None:
-            pb = PlanBuilder(B, H, W, self.precision, device)
+            pb = PlanBuilder(B, H, W, self.precision, device, tc=self.tc)
             sd = self.state_dict()
             x = pb.input(3)
             feat = self._arch_mod.lower(pb, StateView(sd, "backbone_model.", device), x)

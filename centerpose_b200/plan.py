@@ -17,6 +17,7 @@ All torch usage here is plumbing (device memory, one-time weight re-layout).
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -77,7 +78,7 @@ def fold_bn(w: torch.Tensor, b: Optional[torch.Tensor], bn: Optional[dict]):
 
 
 class PlanBuilder:
-    def __init__(self, B: int, H: int, W: int, precision: str, device: torch.device):
+    def __init__(self, B: int, H: int, W: int, precision: str, device: torch.device, tc: Optional[bool] = None):
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         self.B, self.H, self.W = B, H, W
@@ -87,7 +88,10 @@ class PlanBuilder:
         self.ops: List[_PendingOp] = []
         self.keep: List[torch.Tensor] = []      # weights / biases kept alive
         self.syms: List[Sym] = []
-        self.use_tc = False
+        # tensor-core (tcgen05) path: bf16 only; CPB200_TC=0 forces the SIMT kernels (debugging)
+        if tc is None:
+            tc = os.environ.get("CPB200_TC", "1") != "0"
+        self.use_tc = bool(tc) and precision == "bf16"
 
     # ---- symbolic tensors -------------------------------------------------------------
     def _sym(self, C, H, W, kind="act", name=""):
@@ -138,6 +142,19 @@ class PlanBuilder:
         p[:, :, :co] = w.permute(2, 3, 1, 0).reshape(kh * kw, ci, co)
         return self._dev(p)
 
+    def _pack_conv_tc(self, w: torch.Tensor):
+        """(Co,Ci,kh,kw) fp32 -> tcgen05 layout [kh*kw][Co_pad16][Ci] bf16 (K-major B operand)."""
+        co, ci, kh, kw = w.shape
+        cop = (co + 15) // 16 * 16
+        p = torch.zeros(kh * kw, cop, ci, dtype=torch.float32, device=w.device)
+        p[:, :co, :] = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
+        return self._dev(p, torch.bfloat16)
+
+    def _tc_ok(self, srcs, co, kh, kw, stride, out, out_map, Wo):
+        return (self.use_tc and out != "nchw" and out_map is None and stride in (1, 2) and Wo >= 8
+                and all(s.C % 16 == 0 and s.kind == "act" for s in srcs)
+                and (co % 16 == 0 or out == "f32") and kh * kw <= 49)
+
     # ---- ops -------------------------------------------------------------------------------
     def stem(self, x: Sym, w, b, k, stride, pad, relu=True):
         co, ci = w.shape[0], w.shape[1]
@@ -173,8 +190,12 @@ class PlanBuilder:
             y = dst if dst is not None else self._sym(co, Hd, Wd, "f32")
         else:
             y = dst if dst is not None else self._sym(co, Hd, Wd)
+        tc = self._tc_ok(srcs, co, kh, kw, stride, out, out_map, Wo)
+        if tc:
+            flags |= FLAG_TC
         self._emit(_PendingOp(type=OP_CONV, flags=flags, k=(kh, kw), stride=stride, pad=(ph, pw),
-                              weight=self._pack_conv(w), bias=self._dev(b), cout=co, ch_off=ch_off,
+                              weight=self._pack_conv_tc(w) if tc else self._pack_conv(w),
+                              bias=self._dev(b), cout=co, ch_off=ch_off,
                               out_map=(Hd, Wd, sy, sx, oy, ox), HoWo=(Ho, Wo), w_raw=w), srcs, y, [res])
         return y
 

@@ -34,9 +34,53 @@ def _check(got, ref, precision, op_tol=None):
         assert rel <= (op_tol or 1e-2), rel
 
 
-def _builder(B, precision):
+def _builder(B, precision, tc=False):
     from centerpose_b200.plan import PlanBuilder
-    return PlanBuilder(B, 1, 1, precision, torch.device(DEV))
+    return PlanBuilder(B, 1, 1, precision, torch.device(DEV), tc=tc)
+
+
+TC_CASES = [
+    # cins, cout, k, stride, H, W, res, relu, out
+    ([64], 64, 3, 1, 16, 16, False, True, "act"),        # exactly one tile per image
+    ([64], 64, 3, 1, 40, 48, True, True, "act"),         # partial tiles, residual
+    ([16], 16, 3, 1, 64, 64, False, True, "act"),        # BK=16 (SW32)
+    ([16], 32, 3, 2, 64, 64, False, True, "act"),        # stride 2 (TMA element strides), BK=16
+    ([32], 64, 3, 2, 32, 32, False, True, "act"),        # stride 2, BK=32 (SW64)
+    ([32], 64, 1, 1, 16, 24, False, False, "act"),       # 1x1, BK=32
+    ([128], 256, 3, 2, 32, 32, False, True, "act"),      # stride 2, BN=256
+    ([256], 512, 3, 1, 16, 16, True, True, "act"),       # two N tiles
+    ([128, 128, 64, 128], 128, 1, 1, 16, 16, False, True, "act"),   # Root: 4 K-slabs
+    ([512, 512, 256], 512, 1, 1, 8, 8, False, True, "act"),         # TW=8 tiles
+    ([128], 27, 3, 1, 24, 24, False, False, "f32"),      # DCN offset/mask conv: fp32 out, cout 27
+    ([64], 256, 3, 1, 32, 32, False, True, "act"),       # head 3x3
+]
+
+
+@pytest.mark.parametrize("cins,cout,k,stride,H,W,res,relu,out", TC_CASES)
+def test_conv_tensor_core_path(cins, cout, k, stride, H, W, res, relu, out):
+    """tcgen05 implicit-GEMM conv vs torch fp32 on the same bf16-rounded inputs/weights.
+    Tolerance: |err| <= 1e-2 * max|ref| (bf16 output rounding 2^-9 + fp32 accumulation order)."""
+    B = 3
+    g = torch.Generator().manual_seed(sum(cins) * 7 + cout + k + stride)
+    xs = [torch.randn(B, c, H, W, generator=g).bfloat16().float() for c in cins]
+    w = (torch.randn(cout, sum(cins), k, k, generator=g) / (sum(cins) * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g)
+    pad = k // 2
+    ref = F.conv2d(torch.cat(xs, 1), w, b, stride=stride, padding=pad)
+    r = None
+    if res:
+        r = torch.randn(ref.shape, generator=g).bfloat16().float()
+        ref = ref + r
+    if relu:
+        ref = F.relu(ref)
+    pb = _builder(B, "bf16", tc=True)
+    sx = [pb.external(_nhwc(x, torch.bfloat16)) for x in xs]
+    sr = pb.external(_nhwc(r, torch.bfloat16)) if res else None
+    y = pb.conv(sx, w.to(DEV), b.to(DEV), stride=stride, pad=pad, relu=relu, res=sr, out=out)
+    assert pb.ops[-1].flags & 8, "op was not routed to the tensor-core path"
+    got = _nchw(_run(pb, y))
+    err = (got - ref).abs().max().item()
+    assert err <= 1e-2 * ref.abs().max().item(), (err, ref.abs().max().item())
 
 
 def _run(pb, y):
@@ -197,10 +241,11 @@ def test_dla34_forward_vs_oracle_both_precisions():
     ref = torch.cat(dla_ref.forward(sd, x), dim=1)
     got = torch.cat(m(x.to(DEV)), dim=1).cpu()
     assert (got - ref).abs().max().item() <= 5e-4 * ref.abs().max().item()
-    m.set_precision("bf16")
-    got16 = torch.cat(m(x.to(DEV)), dim=1).cpu()
-    rel = ((got16 - ref).norm() / ref.norm()).item()
-    assert rel <= 3e-2, rel
+    for tc in (False, True):            # bf16 activations: CUDA-core kernels, then tcgen05 kernels
+        m.set_precision("bf16", tc=tc)
+        got16 = torch.cat(m(x.to(DEV)), dim=1).cpu()
+        rel = ((got16 - ref).norm() / ref.norm()).item()
+        assert rel <= 3e-2, (tc, rel)
 
 
 def test_dla34_512_end_to_end_vs_reference_golden():
