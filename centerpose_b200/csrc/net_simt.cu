@@ -187,6 +187,13 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
           if (k < BK) *reinterpret_cast<float4 *>(&Bs[k][nq * 4]) = bv[l];
         }
         __syncthreads();
+        // blocked summation: each 16-deep chunk is reduced on its own, then added to the running
+        // sum — error grows with K/16 + 16 instead of K (matters for K = 9*512 in fp32 parity mode)
+        float part[TM][TN];
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) part[i][j] = 0.f;
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
           const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * TM]);
@@ -195,8 +202,12 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
 #pragma unroll
           for (int i = 0; i < TM; ++i)
 #pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+            for (int j = 0; j < TN; ++j) part[i][j] = fmaf(ar[i], br[j], part[i][j]);
         }
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] += part[i][j];
       }
       cbase += cs;
     }
