@@ -14,10 +14,12 @@
 //   phase 1  each CTA scans its H*W map: thread = (row strip, 4-column group), rolling
 //            3-row window in registers, horizontal neighbours by warp shuffle; local maxima
 //            above the channel's floor are compacted into shared memory (warp-ballot).
-//   phase 2  exact top-K of the candidates: radix-select on the float bits when there are
-//            more than 256, then a shared-memory bitonic sort of 64-bit (value,~index) keys.
-//            Degenerate inputs (candidate overflow, massive ties, negative maps) take an
-//            exact but slow K-round arg-max path so results stay defined everywhere.
+//   phase 2  exact top-K SET of the candidates by adaptive bucket select (256 linear buckets over
+//            the candidates' float-bit range; the boundary bucket is resolved by rank counting on
+//            64-bit (value,~index) keys); only the centre channel orders its K rows (rank
+//            counting) — keypoint-candidate order never reaches the output.  Degenerate inputs
+//            (candidate overflow, massive ties, negative maps) take an exact but slow K-round
+//            arg-max path so results stay defined everywhere.
 //   phase 3  keypoint grouping for joint j is done by whichever of {centre CTA, joint-j CTA}
 //            finishes second (one atomic per pair; deadlock-free, no second launch).
 #include "common.cuh"
@@ -26,7 +28,7 @@ namespace {
 
 constexpr int TPB = 256;
 constexpr int CAP = 4096;      // candidate capacity per channel map (32 KB of smem)
-constexpr int SORT_N = 256;    // bitonic sort capacity
+constexpr int BND = 64;        // boundary-bucket capacity resolved by rank counting
 constexpr int MAXK = CPB200_DECODE_MAX_K;
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -44,16 +46,21 @@ struct DecodeParams {
 struct Smem {
   float cval[CAP];
   int cidx[CAP];
-  unsigned long long skey[SORT_N];
+  unsigned long long bkey[BND];
   int hist[256];
   int warp_tot[8];
-  float topv[MAXK];
+  float selv[MAXK];            // selected (unordered) top-K
+  int seli[MAXK];
+  float topv[MAXK];            // final per-channel list
   int topi[MAXK];
-  float gx[MAXK], gy[MAXK], gs[MAXK];
+  float2 gxy[MAXK];
+  float gs[MAXK];
+  int gi[MAXK];
   float hd[MAXK];
   int hc[MAXK];
   unsigned long long red[8];
-  int count, nsel, digit, krem, flags;
+  unsigned kmin, kmax;
+  int count, nsel, nbnd, digit, need, flags;
   unsigned todo_mask;
 };
 
@@ -63,22 +70,11 @@ __device__ __forceinline__ float act(float v, bool sig) {
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
-__device__ __forceinline__ void push(Smem &s, bool pred, float val, int idx, int lane) {
-  unsigned m = __ballot_sync(FULL, pred);
-  if (m == 0) return;
-  int leader = __ffs(m) - 1;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(&s.count, __popc(m));
-  base = __shfl_sync(FULL, base, leader);
-  if (pred) {
-    int pos = base + __popc(m & ((1u << lane) - 1u));
-    if (pos < CAP) { s.cval[pos] = val; s.cidx[pos] = idx; }
-  }
-}
-
 // ---- phase 1, vector path (W % 4 == 0, 16-byte aligned map) -----------------------------
-__device__ void scan_vec(Smem &s, const float *__restrict__ map, int H, int W, bool sig,
-                         float floorv) {
+// Each thread owns a 4-column group and walks down a strip of rows with a rolling 3-row window.
+// Per row it only sets bits (peak && value > floor) in a 64-bit mask (16 rows x 4 columns); the
+// rare set bits are turned into (value, index) candidates afterwards with warp-aggregated atomics.
+__device__ void scan_vec(Smem &s, const float *__restrict__ map, int H, int W, bool sig, float floorv) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int XG = W >> 2;
   int S = TPB / XG; if (S < 1) S = 1; if (S > H) S = H;
@@ -104,43 +100,61 @@ __device__ void scan_vec(Smem &s, const float *__restrict__ map, int H, int W, b
       } else {
         v = make_float4(NINF, NINF, NINF, NINF);
       }
-      float lv = __shfl_up_sync(FULL, v.w, 1);
-      float rv = __shfl_down_sync(FULL, v.x, 1);
-      float l = NINF, r = NINF;
-      if (ok) {
-        if (!lpad) l = lsh ? lv : act(__ldg(base + (size_t)y * W - 1), sig);
-        if (!rpad) r = rsh ? rv : act(__ldg(base + (size_t)y * W + 4), sig);
-      }
-      h.x = max3(l, v.x, v.y); h.y = max3(v.x, v.y, v.z);
-      h.z = max3(v.y, v.z, v.w); h.w = max3(v.z, v.w, r);
+      float l = __shfl_up_sync(FULL, v.w, 1);
+      float r = __shfl_down_sync(FULL, v.x, 1);
+      if (!lsh) l = (ok && !lpad) ? act(__ldg(base + (size_t)y * W - 1), sig) : NINF;
+      if (!rsh) r = (ok && !rpad) ? act(__ldg(base + (size_t)y * W + 4), sig) : NINF;
+      const float m01 = fmaxf(v.x, v.y), m23 = fmaxf(v.z, v.w);
+      h.x = fmaxf(l, m01); h.y = fmaxf(m01, v.z); h.z = fmaxf(v.y, m23); h.w = fmaxf(m23, r);
     };
 
     float4 vcur, hprev, hcur, tmp;
     load_row(r0 - 1, tmp, hprev);
     load_row(r0, vcur, hcur);
-    for (int i0 = 0; i0 < RS; i0 += 4) {
-      float4 nv[4], nh[4];
+    for (int i0 = 0; i0 < RS; i0 += 16) {
+      unsigned long long bits = 0ull;
+#pragma unroll 1
+      for (int i1 = 0; i1 < 16; i1 += 4) {
+        float4 nv[4], nh[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        int y = r0 + i0 + q + 1;
-        load_row((y <= r1) ? y : -1, nv[q], nh[q]);   // row r1 is the strip's lower halo
+        for (int q = 0; q < 4; ++q) {
+          const int y = r0 + i0 + i1 + q + 1;
+          load_row((y <= r1) ? y : -1, nv[q], nh[q]);          // row r1 is the strip's lower halo
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int y = r0 + i0 + i1 + q;
+          const float mx = max3(hprev.x, hcur.x, nh[q].x), my = max3(hprev.y, hcur.y, nh[q].y);
+          const float mz = max3(hprev.z, hcur.z, nh[q].z), mw = max3(hprev.w, hcur.w, nh[q].w);
+          unsigned b = 0;
+          b |= (vcur.x == mx && vcur.x > floorv) ? 1u : 0u;
+          b |= (vcur.y == my && vcur.y > floorv) ? 2u : 0u;
+          b |= (vcur.z == mz && vcur.z > floorv) ? 4u : 0u;
+          b |= (vcur.w == mw && vcur.w > floorv) ? 8u : 0u;
+          if (!(on && y < r1)) b = 0;
+          bits |= (unsigned long long)b << (4 * (i1 + q));
+          hprev = hcur; hcur = nh[q]; vcur = nv[q];
+        }
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int y = r0 + i0 + q;
-        const bool rowok = on && (y < r1);
-        float mx = max3(hprev.x, hcur.x, nh[q].x), my = max3(hprev.y, hcur.y, nh[q].y);
-        float mz = max3(hprev.z, hcur.z, nh[q].z), mw = max3(hprev.w, hcur.w, nh[q].w);
-        const int idx = y * W + x0;
-        bool px = rowok && (vcur.x == mx), py = rowok && (vcur.y == my);
-        bool pz = rowok && (vcur.z == mz), pw = rowok && (vcur.w == mw);
-        if ((px && vcur.x < 0.f) || (py && vcur.y < 0.f) || (pz && vcur.z < 0.f) || (pw && vcur.w < 0.f))
-          s.flags = 1;   // benign race: negative peak seen (only matters when count < K)
-        push(s, px && vcur.x > floorv, vcur.x, idx, lane);
-        push(s, py && vcur.y > floorv, vcur.y, idx + 1, lane);
-        push(s, pz && vcur.z > floorv, vcur.z, idx + 2, lane);
-        push(s, pw && vcur.w > floorv, vcur.w, idx + 3, lane);
-        hprev = hcur; hcur = nh[q]; vcur = nv[q];
+      // deferred extraction of this 16-row batch (warp-uniform loop, aggregated atomics)
+      while (__any_sync(FULL, bits != 0ull)) {
+        const bool has = bits != 0ull;
+        int idx = 0; float val = 0.f;
+        if (has) {
+          const int bit = __ffsll((long long)bits) - 1;
+          bits &= bits - 1ull;
+          idx = (r0 + i0 + (bit >> 2)) * W + x0 + (bit & 3);
+          val = act(__ldg(map + idx), sig);
+        }
+        const unsigned m = __ballot_sync(FULL, has);
+        const int leader = __ffs(m) - 1;
+        int basep = 0;
+        if (lane == leader) basep = atomicAdd(&s.count, __popc(m));
+        basep = __shfl_sync(FULL, basep, leader);
+        if (has) {
+          const int pos = basep + __popc(m & ((1u << lane) - 1u));
+          if (pos < CAP) { s.cval[pos] = val; s.cidx[pos] = idx; }
+        }
       }
     }
   }
@@ -167,16 +181,24 @@ __device__ __forceinline__ float nms_value(const float *__restrict__ map, int H,
 }
 
 // ---- phase 1, scalar path (any W / alignment) -------------------------------------------
-__device__ void scan_scalar(Smem &s, const float *__restrict__ map, int H, int W, bool sig,
-                            float floorv) {
+__device__ void scan_scalar(Smem &s, const float *__restrict__ map, int H, int W, bool sig, float floorv) {
   const int N = H * W, lane = threadIdx.x & 31;
   const int iters = cpb::ceil_div(N, TPB);
   for (int it = 0; it < iters; ++it) {
     const int cell = it * TPB + threadIdx.x;
     bool pk = false; float v = 0.f;
     if (cell < N) v = nms_value(map, H, W, cell / W, cell % W, sig, &pk);
-    if (pk && v < 0.f) s.flags = 1;
-    push(s, pk && v > floorv, v, cell, lane);
+    const bool has = pk && v > floorv;
+    const unsigned m = __ballot_sync(FULL, has);
+    if (m == 0) continue;
+    const int leader = __ffs(m) - 1;
+    int basep = 0;
+    if (lane == leader) basep = atomicAdd(&s.count, __popc(m));
+    basep = __shfl_sync(FULL, basep, leader);
+    if (has) {
+      const int pos = basep + __popc(m & ((1u << lane) - 1u));
+      if (pos < CAP) { s.cval[pos] = v; s.cidx[pos] = cell; }
+    }
   }
 }
 
@@ -194,23 +216,7 @@ __device__ __forceinline__ int key_idx(unsigned long long k) {
   return (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
 }
 
-__device__ void bitonic_desc(unsigned long long *key, int P) {
-  for (int k = 2; k <= P; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < P; t += TPB) {
-        const int o = t ^ j;
-        if (o > t) {
-          const bool desc = ((t & k) == 0);
-          unsigned long long a = key[t], b = key[o];
-          if ((a < b) == desc) { key[t] = b; key[o] = a; }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// exact, general, slow: K rounds of block-wide arg-max over the post-NMS map
+// exact, general, slow: K rounds of block-wide arg-max over the post-NMS map (degenerate inputs)
 __device__ void select_slow(Smem &s, const float *__restrict__ map, int H, int W, bool sig, int K) {
   const int N = H * W, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   unsigned long long bound = ~0ull;
@@ -238,84 +244,145 @@ __device__ void select_slow(Smem &s, const float *__restrict__ map, int H, int W
   }
 }
 
-// ---- phase 2: exact top-K of the compacted candidates ----------------------------------
-// returns false when the fast path cannot decide (caller falls back to select_slow)
-__device__ bool select_fast(Smem &s, int K, bool is_centre, int N) {
+// ---- phase 2: exact top-K SET of the n candidates -> s.selv/s.seli[0..nsel) --------------
+// Adaptive bucket select: histogram the candidates' float bits over their actual [min,max] range
+// (256 linear buckets), everything above the boundary bucket is in, the boundary bucket is resolved
+// by rank counting on 64-bit (value, ~index) keys, or refined with a narrower range.
+// Returns false when the input is too degenerate (massive exact ties) -> caller uses select_slow.
+__device__ bool select_set(Smem &s, int n, int K) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int n = s.count;                         // caller guarantees n <= CAP
-  int nsort;
-  if (n <= SORT_N) {
-    for (int i = tid; i < SORT_N; i += TPB)
-      s.skey[i] = (i < n) ? make_key(s.cval[i], s.cidx[i]) : 0ull;
-    nsort = n;
+  if (n <= K) {
+    for (int i = tid; i < n; i += TPB) { s.selv[i] = s.cval[i]; s.seli[i] = s.cidx[i]; }
+    if (tid == 0) s.nsel = n;
     __syncthreads();
-  } else {
-    // radix select (8-bit digits, MSB first) for the K-th largest value; candidates are > 0
-    unsigned prefix = 0u, mask = 0u;
-    int krem = K;
-    for (int d = 3; d >= 0; --d) {
-      const int shift = 8 * d;
-      s.hist[tid] = 0;
-      __syncthreads();
-      for (int i = tid; i < n; i += TPB) {
-        unsigned u = __float_as_uint(s.cval[i]);
-        if ((u & mask) == prefix) atomicAdd(&s.hist[(u >> shift) & 255u], 1);
-      }
-      __syncthreads();
-      const int h = s.hist[tid];
-      int suf = h;                                // inclusive suffix sum within the warp
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_down_sync(FULL, suf, o);
-        if (lane + o < 32) suf += t;
-      }
-      if (lane == 0) s.warp_tot[wid] = suf;
-      __syncthreads();
-      for (int w = wid + 1; w < TPB / 32; ++w) suf += s.warp_tot[w];
-      const int excl = suf - h;
-      if (excl < krem && krem <= suf) { s.digit = tid; s.krem = krem - excl; }
-      __syncthreads();
-      prefix |= ((unsigned)s.digit) << shift;
-      mask |= 255u << shift;
-      krem = s.krem;
-      __syncthreads();
-    }
-    if (tid == 0) s.nsel = 0;
-    for (int i = tid; i < SORT_N; i += TPB) s.skey[i] = 0ull;
+    return true;
+  }
+  // value-bit range of the candidates (all > 0, so float bits order like unsigned ints)
+  unsigned lo_ = 0xFFFFFFFFu, hi_ = 0u;
+  for (int i = tid; i < n; i += TPB) {
+    const unsigned u = __float_as_uint(s.cval[i]);
+    lo_ = min(lo_, u); hi_ = max(hi_, u);
+  }
+  lo_ = __reduce_min_sync(FULL, lo_); hi_ = __reduce_max_sync(FULL, hi_);
+  if (tid == 0) { s.kmin = 0xFFFFFFFFu; s.kmax = 0u; s.nsel = 0; }
+  __syncthreads();
+  if (lane == 0) { atomicMin(&s.kmin, lo_); atomicMax(&s.kmax, hi_); }
+  __syncthreads();
+  unsigned lo = s.kmin, hi = s.kmax;
+  int need = K;
+  for (int round = 0; round < 5; ++round) {
+    const unsigned range = hi - lo;
+    const int shift = range ? max(0, 32 - __clz(range) - 8) : 0;
+    s.hist[tid] = 0;
+    if (tid == 0) s.nbnd = 0;
     __syncthreads();
     for (int i = tid; i < n; i += TPB) {
-      if (__float_as_uint(s.cval[i]) >= prefix) {
-        int pos = atomicAdd(&s.nsel, 1);
-        if (pos < SORT_N) s.skey[pos] = make_key(s.cval[i], s.cidx[i]);
+      const unsigned u = __float_as_uint(s.cval[i]);
+      if (u >= lo && u <= hi) atomicAdd(&s.hist[(u - lo) >> shift], 1);
+    }
+    __syncthreads();
+    const int h = s.hist[tid];
+    int suf = h;                                  // inclusive suffix sum (buckets >= tid)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_down_sync(FULL, suf, o);
+      if (lane + o < 32) suf += t;
+    }
+    if (lane == 0) s.warp_tot[wid] = suf;
+    __syncthreads();
+    for (int w = wid + 1; w < TPB / 32; ++w) suf += s.warp_tot[w];
+    const int excl = suf - h;
+    if (excl < need && need <= suf) { s.digit = tid; s.need = need - excl; }
+    __syncthreads();
+    const int tb = s.digit;
+    const int need_b = s.need;                    // how many of the boundary bucket are still needed
+    const int nb = s.hist[tb];
+    const bool take_all = (nb == need_b);
+    const bool resolve = !take_all && (nb <= BND);
+    if (!take_all && !resolve && shift == 0) return false;      // > BND exact ties at the K-th value
+    // everything above the boundary bucket is selected; the boundary bucket is taken whole,
+    // parked for rank counting, or refined in the next round
+    for (int i = tid; i < n; i += TPB) {
+      const unsigned u = __float_as_uint(s.cval[i]);
+      if (u < lo || u > hi) continue;
+      const int b = (int)((u - lo) >> shift);
+      if (b > tb || (b == tb && take_all)) {
+        const int pos = atomicAdd(&s.nsel, 1);
+        if (pos < MAXK) { s.selv[pos] = s.cval[i]; s.seli[pos] = s.cidx[i]; }
+      } else if (b == tb && resolve) {
+        const int pos = atomicAdd(&s.nbnd, 1);
+        if (pos < BND) s.bkey[pos] = make_key(s.cval[i], s.cidx[i]);
       }
     }
     __syncthreads();
-    nsort = s.nsel;
-    if (nsort > SORT_N) return false;             // massive ties at the K-th value
-  }
-  int P = 2;
-  while (P < nsort) P <<= 1;
-  bitonic_desc(s.skey, P);
-  const int take = min(K, nsort);
-  for (int i = tid; i < K; i += TPB) {
-    if (i < take) { s.topv[i] = key_val(s.skey[i]); s.topi[i] = key_idx(s.skey[i]); }
-    else if (!is_centre) { s.topv[i] = -1.0f; s.topi[i] = 0; }   // masked placeholder
-  }
-  __syncthreads();
-  if (is_centre && take < K) {
-    // fewer than K positive peaks: the reference's topk then returns zero-valued cells.
-    // Canonical choice: the lowest flat indices that are not among the selected peaks.
-    if (s.flags) return false;                    // negative peaks present: let the slow path rank
-    const int need = K - take;
-    int cand = tid;                               // 2K <= 256 candidates, one per thread
-    bool free_cell = (cand < N) && (cand < 2 * K);
-    if (free_cell) for (int i = 0; i < take; ++i) if (s.topi[i] == cand) { free_cell = false; break; }
-    unsigned m = __ballot_sync(FULL, free_cell);
-    if (lane == 0) s.warp_tot[wid] = __popc(m);
+    if (take_all) return true;
+    if (resolve) {
+      const int m = s.nbnd;
+      if (tid < m) {
+        const unsigned long long me = s.bkey[tid];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) rank += (s.bkey[j] > me) ? 1 : 0;
+        if (rank < need_b) {
+          const int pos = atomicAdd(&s.nsel, 1);
+          if (pos < MAXK) { s.selv[pos] = key_val(me); s.seli[pos] = key_idx(me); }
+        }
+      }
+      __syncthreads();
+      return true;
+    }
+    need = need_b;
+    const unsigned nlo = lo + ((unsigned)tb << shift);
+    const unsigned nhi = nlo + ((1u << shift) - 1u);
+    lo = nlo; hi = min(hi, nhi);
     __syncthreads();
-    int rank = __popc(m & ((1u << lane) - 1u));
-    for (int w = 0; w < wid; ++w) rank += s.warp_tot[w];
-    if (free_cell && rank < need) { s.topv[take + rank] = 0.0f; s.topi[take + rank] = cand; }
+  }
+  return false;
+}
+
+// ---- phase 2b: order the selected set (centre channel) / fill placeholders ------------------
+__device__ bool finalize_list(Smem &s, const float *__restrict__ map, int H, int W, bool sig, int K,
+                              bool is_centre) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int N = H * W;
+  const int take = min(s.nsel, K);
+  if (is_centre) {
+    // rows must come out sorted (score desc, index asc): rank counting over <= 128 keys
+    if (tid < take) {
+      const unsigned long long me = make_key(s.selv[tid], s.seli[tid]);
+      int rank = 0;
+      for (int j = 0; j < take; ++j) rank += (make_key(s.selv[j], s.seli[j]) > me) ? 1 : 0;
+      s.topv[rank] = s.selv[tid]; s.topi[rank] = s.seli[tid];
+    }
+    __syncthreads();
+    if (take < K) {
+      // fewer than K positive peaks: the reference's topk then returns zero-valued cells; canonical
+      // choice = lowest flat indices that are not selected peaks.  If a NEGATIVE peak exists the
+      // zero cells no longer rank last among the rest -> exact slow path decides.
+      int neg = 0;
+      for (int cell = tid; cell < N; cell += TPB) {
+        bool pk; const float v = nms_value(map, H, W, cell / W, cell % W, sig, &pk);
+        neg |= (pk && v < 0.f) ? 1 : 0;
+      }
+      if (__syncthreads_or(neg)) return false;
+      const int need = K - take;
+      const int cand = tid;                         // 2K <= 256 candidates, one per thread
+      bool free_cell = (cand < N) && (cand < 2 * K);
+      if (free_cell) for (int i = 0; i < take; ++i) if (s.topi[i] == cand) { free_cell = false; break; }
+      const unsigned m = __ballot_sync(FULL, free_cell);
+      if (lane == 0) s.warp_tot[wid] = __popc(m);
+      __syncthreads();
+      int rank = __popc(m & ((1u << lane) - 1u));
+      for (int w = 0; w < wid; ++w) rank += s.warp_tot[w];
+      if (free_cell && rank < need) { s.topv[take + rank] = 0.0f; s.topi[take + rank] = cand; }
+      __syncthreads();
+    }
+  } else {
+    // keypoint channels: only the SET matters (order never reaches the output); entries below the
+    // score threshold are interchangeable "masked" candidates (decode.py:282-285)
+    for (int i = tid; i < K; i += TPB) {
+      if (i < take) { s.topv[i] = s.selv[i]; s.topi[i] = s.seli[i]; }
+      else { s.topv[i] = -1.0f; s.topi[i] = 0; }
+    }
     __syncthreads();
   }
   return true;
@@ -341,9 +408,9 @@ __device__ void group_joint(Smem &s, const DecodeParams &p, int b, int j) {
         ox = __ldg(p.hp_offset + ((size_t)b * 2 + 0) * N + idx);
         oy = __ldg(p.hp_offset + ((size_t)b * 2 + 1) * N + idx);
       }
-      s.gx[tid] = __fadd_rn(fx, ox); s.gy[tid] = __fadd_rn(fy, oy); s.gs[tid] = v;
+      s.gxy[tid] = make_float2(__fadd_rn(fx, ox), __fadd_rn(fy, oy)); s.gs[tid] = v; s.gi[tid] = idx;
     } else {
-      s.gx[tid] = -10000.0f; s.gy[tid] = -10000.0f; s.gs[tid] = -1.0f;
+      s.gxy[tid] = make_float2(-10000.0f, -10000.0f); s.gs[tid] = -1.0f; s.gi[tid] = 0x7fffffff;
     }
   }
   __syncthreads();
@@ -366,19 +433,35 @@ __device__ void group_joint(Smem &s, const DecodeParams &p, int b, int j) {
     l = __fsub_rn(cx, hw); t = __fsub_rn(cy, hh); r = __fadd_rn(cx, hw); bt = __fadd_rn(cy, hh);
     const int hk = (K + 1) >> 1;
     const int c0 = half ? hk : 0, c1 = half ? K : hk;
+    // nearest candidate on SQUARED distance (monotone in the reference's sqrt); exact ties ->
+    // the reference's first-minimum over its score-sorted list = higher score, then lower index
     for (int c = c0; c < c1; ++c) {                                                 // :286-289
-      const float dx = __fsub_rn(kx, s.gx[c]), dy = __fsub_rn(ky, s.gy[c]);
-      const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+      const float2 g = s.gxy[c];
+      const float dx = __fsub_rn(kx, g.x), dy = __fsub_rn(ky, g.y);
+      const float d = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
       if (d < best_d) { best_d = d; best_c = c; }
+      else if (d == best_d) {
+        const float sc = s.gs[c], sb = s.gs[best_c];
+        if (sc > sb || (sc == sb && s.gi[c] < s.gi[best_c])) best_c = c;
+      }
     }
     if (half) { s.hd[pidx] = best_d; s.hc[pidx] = best_c; }
   }
   __syncthreads();
   if (half == 0 && pidx < K) {
-    if (s.hd[pidx] < best_d) { best_d = s.hd[pidx]; best_c = s.hc[pidx]; }
-    const float sx = s.gx[best_c], sy = s.gy[best_c], ss = s.gs[best_c];
+    const float od = s.hd[pidx]; const int oc = s.hc[pidx];
+    if (K > 1) {
+      if (od < best_d) { best_d = od; best_c = oc; }
+      else if (od == best_d) {
+        const float sc = s.gs[oc], sb = s.gs[best_c];
+        if (sc > sb || (sc == sb && s.gi[oc] < s.gi[best_c])) best_c = oc;
+      }
+    }
+    const float min_dist = __fsqrt_rn(best_d);
+    const float2 g = s.gxy[best_c];
+    const float sx = g.x, sy = g.y, ss = s.gs[best_c];
     const bool rej = (sx < l) || (sx > r) || (sy < t) || (sy > bt) || (ss < p.thresh) ||
-                     (best_d > __fmul_rn(fmaxf(__fsub_rn(bt, t), __fsub_rn(r, l)), 0.3f));   // :300-302
+                     (min_dist > __fmul_rn(fmaxf(__fsub_rn(bt, t), __fsub_rn(r, l)), 0.3f));   // :300-302
     const int row = 5 + 3 * J;
     float *o = p.out + ((size_t)b * K + pidx) * row;
     o[5 + 2 * j] = rej ? kx : sx;
@@ -394,9 +477,8 @@ __global__ void __launch_bounds__(TPB) decode_kernel(const DecodeParams p) {
   const int C1 = 1 + p.J;
   const int b = blockIdx.x / C1, ch = blockIdx.x % C1;
   const int tid = threadIdx.x;
-  const int N = p.H * p.W;
   const bool is_centre = (ch == 0);
-  const float *map = is_centre ? (p.heat + (size_t)b * N) : (p.hm_hp + ((size_t)b * p.J + (ch - 1)) * N);
+  const float *map = is_centre ? (p.heat + (size_t)b * p.H * p.W) : (p.hm_hp + ((size_t)b * p.J + (ch - 1)) * p.H * p.W);
   const bool sig = p.apply_sigmoid != 0;
   const float floorv = is_centre ? 0.0f : p.thresh;
   if (tid == 0) { s.count = 0; s.flags = 0; s.nsel = 0; s.todo_mask = 0; }
@@ -408,7 +490,10 @@ __global__ void __launch_bounds__(TPB) decode_kernel(const DecodeParams p) {
   __syncthreads();
 
   bool done = false;
-  if (s.count <= CAP) done = select_fast(s, p.K, is_centre, N);
+  if (s.count <= CAP) {
+    done = select_set(s, s.count, p.K);
+    if (done) done = finalize_list(s, map, p.H, p.W, sig, p.K, is_centre);
+  }
   if (!done) {
     __syncthreads();
     select_slow(s, map, p.H, p.W, sig, p.K);
