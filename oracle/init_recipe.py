@@ -12,7 +12,15 @@ exercised.  This recipe keeps the architecture and shapes and only changes the V
 
   * every 4-D conv weight        ~ N(0, gain/sqrt(fan_in)), gain sqrt(2) (ReLU-preserving)
   * depthwise deconv ``up_*``    bilinear kernel (``pose_dla_dcn.py:324-333`` formula) x U(0.8,1.2)
-  * ``conv_offset_mask``         weight ~ N(0, 0.7/sqrt(fan_in)), bias ~ N(0, 0.5) -> offsets O(1) px
+  * ``conv_offset_mask``         weight ~ N(0, 0.05/sqrt(fan_in)), bias ~ N(0, 0.5): every tap samples at a
+                                 fractional position (|offset| ~ 0.5 px from the bias, mask != 0.5) with a small
+                                 data-dependent part.  Measured (float64 oracle): with weight gain 0.7 the
+                                 16 chained DCNs on spatially white random features amplify a 1e-7 input
+                                 perturbation x150 and merely rounding the INPUT to bf16 moves the heads by
+                                 28 % — any bf16 parity statement would be meaningless; with 0.05 the
+                                 amplification is 1.7 and fp32-vs-fp64 noise is 2e-6.  Large data-dependent
+                                 offsets (gain 1.5, many samples out of bounds) are covered at op level
+                                 (tests/test_net_gpu.py::test_dcn_op_matches_oracle).
   * BatchNorm                    weight ~ U(0.5,1.5), bias ~ N(0,0.1), mean ~ N(0,0.1), var ~ U(0.5,1.5)
   * conv / DCN biases            ~ N(0, 0.1)
   * head final 1x1 (``.2``)      per-head gain so logits/regressions have realistic spread;
@@ -28,7 +36,8 @@ from collections import OrderedDict
 
 import torch
 
-HEAD_GAIN = {"hm": 0.8, "hm_hp": 0.5, "wh": 6.0, "hps": 8.0, "reg": 0.25, "hp_offset": 0.25}
+OFFSET_GAIN = 0.05
+HEAD_GAIN = {"hm": 0.09, "hm_hp": 0.055, "wh": 0.5, "hps": 0.65, "reg": 0.027, "hp_offset": 0.013}
 HEAD_BIAS = {"hm": -2.19, "hm_hp": -2.19, "wh": 12.0, "hps": 0.0, "reg": 0.5, "hp_offset": 0.5}
 
 
@@ -76,7 +85,7 @@ def conditioned_state_dict(template: "OrderedDict[str, torch.Tensor]", seed: int
             else:
                 fan_in = shape[1] * shape[2] * shape[3]
             if "conv_offset_mask" in k:
-                new[k] = randn(shape) * (0.7 / math.sqrt(fan_in))
+                new[k] = randn(shape) * (OFFSET_GAIN / math.sqrt(fan_in))
             elif k.startswith("head_model.") and k.endswith(".2.weight"):
                 head = k.split(".")[1]
                 new[k] = randn(shape) * (HEAD_GAIN[head] / math.sqrt(fan_in))

@@ -3,10 +3,9 @@ program) against torch-CPU fp32 references / the oracle / the reference-generate
 
 Tolerances (floating point, stated here as the task requires):
   fp32 activations, one op   : |err| <= 2e-4 * max|ref|  (fp32 accumulate, different summation order)
-  fp32 activations, network  : |err| <= 5e-3 * max|ref| and relative L2 <= 3e-3.  Measured on the CPU: this
-                               (conditioned random) DLA-34 amplifies a 1e-7 input perturbation to 2e-5 at the
-                               heads (x200), and the reference's own fp32 CPU result is 5.8e-4 (relative L2)
-                               away from a float64 evaluation — fp32 rounding noise alone is ~1e-3 here
+  fp32 activations, network  : |err| <= 5e-4 * max|ref| and relative L2 <= 2e-4 (the conditioned-init network
+                               amplifies perturbations x1.7; fp32-vs-float64 noise of the reference's own CPU
+                               path is 2e-6 — see oracle/init_recipe.py for why the DCN offset gain matters)
   bf16 activations           : relative L2 error <= 3e-2 end to end, <= 1e-2 per op
 """
 import os
@@ -240,7 +239,7 @@ def test_dla34_fp32_matches_reference_golden(tag):
 def _net_close(got, ref):
     got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
     err = np.abs(got - ref).max(); rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
-    assert err <= 5e-3 * np.abs(ref).max() and rel <= 3e-3, (err, np.abs(ref).max(), rel)
+    assert err <= 5e-4 * np.abs(ref).max() and rel <= 2e-4, (err, np.abs(ref).max(), rel)
 
 
 def test_dla34_forward_vs_oracle_both_precisions():
