@@ -42,6 +42,10 @@ struct alignas(64) TcArgs {
   const float *bias;
   unsigned flags;
   unsigned swizzle_bits;      // UMMA layout_type for the chosen BK
+  // deformable conv (DCN) only: A tiles are gathered by producer warps instead of TMA
+  const __nv_bfloat16 *dcn_src;   // (B,H,W,Cin) bf16
+  const float *dcn_om;            // (B,H,W,27) fp32: 18 offsets (dy,dx per tap) | 9 mask logits
+  int H, W;
 };
 
 // ------------------------------------------------------------------------------- PTX wrappers
@@ -111,8 +115,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes
   return d;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+constexpr int DCN_THREADS = 320;   // + 4 gather-producer warps
+
+struct __align__(16) DcnPrm { int off[4]; float wt[4]; };
+
+template <int BN, bool DCN>
+__global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A | B)] then barriers
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -121,6 +129,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   __shared__ __align__(8) uint64_t bars[2 * 8 + 4];
   __shared__ uint32_t s_tmem;
   __shared__ float s_bias[2][BN];
+  __shared__ DcnPrm s_prm[DCN ? 4 : 1][DCN ? 32 : 1];
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
   const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[18]);
 
@@ -128,9 +137,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < a.nsrc; ++s) tmap_prefetch(&a.amap[s]);
+    if (!DCN) for (int s = 0; s < a.nsrc; ++s) tmap_prefetch(&a.amap[s]);
     tmap_prefetch(&a.bmap);
-    for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, DCN ? 1 + 128 : 1); mbar_init(empty0 + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -169,8 +178,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int c0 = 0; c0 < a.cin[s]; c0 += a.BK) {
               mbar_wait(empty0 + 8 * stage, phase ^ 1);
               const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
-              mbar_expect_tx(full0 + 8 * stage, a_bytes + b_bytes);
-              tma_load_4d(sa, &a.amap[s], full0 + 8 * stage, c0, wi, hi, n);
+              if (DCN) {
+                mbar_expect_tx(full0 + 8 * stage, b_bytes);
+              } else {
+                mbar_expect_tx(full0 + 8 * stage, a_bytes + b_bytes);
+                tma_load_4d(sa, &a.amap[s], full0 + 8 * stage, c0, wi, hi, n);
+              }
               tma_load_3d(sb, &a.bmap, full0 + 8 * stage, cb + c0, nt * BN, tap);
               if (++stage == a.stages) { stage = 0; phase ^= 1; }
             }
@@ -204,6 +217,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; accphase ^= 1; }
+    }
+  } else if (DCN && warp >= 6) {
+    // =============================== DCN gather producers (warps 6..9) ===============================
+    // A[row = pixel][k = channel] of tap t is  sigmoid(mask_t) * bilinear(x, p + tap_t + offset_t)
+    // (dcn_v2_im2col_cuda.cu:25-54,125-195), blended in fp32, rounded once to bf16 and stored straight
+    // into the 128B-swizzled K-major tile the UMMA descriptor reads (16-byte chunk j of row r lives at
+    // chunk j ^ (r & 7)).  Lane = (row-in-group-of-4, 16-byte chunk): a warp reads 4 full 128-byte lines
+    // per corner load.
+    const int gw = warp - 6;
+    int stage = 0; uint32_t phase = 0;
+    const int Cin = a.cin[0];
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
+      const int rp = gw * 32 + lane;                       // the pixel whose sampling parameters I compute
+      const int ho = h0 + rp / a.TW, wo = w0 + rp % a.TW;
+      const bool okp = ho < a.Ho && wo < a.Wo;
+      const float *om = a.dcn_om + (((size_t)n * a.H + ho) * a.W + wo) * 27;
+      for (int tap = 0; tap < 9; ++tap) {
+        DcnPrm pr;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { pr.off[c] = 0; pr.wt[c] = 0.f; }
+        if (okp) {
+          const float oh = __ldg(om + 2 * tap), ow = __ldg(om + 2 * tap + 1);
+          const float mk = 1.0f / (1.0f + __expf(-__ldg(om + 18 + tap)));
+          const float h_im = (float)(ho - 1 + tap / 3) + oh, w_im = (float)(wo - 1 + tap % 3) + ow;
+          if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {
+            const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+            const int h_high = h_low + 1, w_high = w_low + 1;
+            const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+            const int rowb = n * a.H;
+            if (h_low >= 0 && w_low >= 0) { pr.off[0] = (rowb + h_low) * a.W + w_low; pr.wt[0] = hh * hw * mk; }
+            if (h_low >= 0 && w_high <= a.W - 1) { pr.off[1] = (rowb + h_low) * a.W + w_high; pr.wt[1] = hh * lw * mk; }
+            if (h_high <= a.H - 1 && w_low >= 0) { pr.off[2] = (rowb + h_high) * a.W + w_low; pr.wt[2] = lh * hw * mk; }
+            if (h_high <= a.H - 1 && w_high <= a.W - 1) { pr.off[3] = (rowb + h_high) * a.W + w_high; pr.wt[3] = lh * lw * mk; }
+          }
+        }
+        __syncwarp();
+        s_prm[gw][lane] = pr;
+        __syncwarp();
+        for (int c0 = 0; c0 < Cin; c0 += 64) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+#pragma unroll 2
+          for (int it = 0; it < 8; ++it) {
+            const int rl = it * 4 + (lane >> 3), chunk = lane & 7;
+            const DcnPrm q = s_prm[gw][rl];
+            float acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (q.wt[c] != 0.f) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.dcn_src + (size_t)q.off[c] * Cin + c0 + chunk * 8));
+                const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  acc[2 * j] = fmaf(q.wt[c], __uint_as_float(u[j] << 16), acc[2 * j]);
+                  acc[2 * j + 1] = fmaf(q.wt[c], __uint_as_float(u[j] & 0xFFFF0000u), acc[2 * j + 1]);
+                }
+              }
+            }
+            uint4 o;
+            __nv_bfloat162 *ob = reinterpret_cast<__nv_bfloat162 *>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+            const int row = gw * 32 + rl;
+            const uint32_t dst = sa + row * 128 + ((chunk ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(full0 + 8 * stage);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
     }
   } else {
     // =============================== epilogue (warps 2..5) ===============================
@@ -305,21 +392,22 @@ EncodeTiledFn get_encode() {
 struct TcOp {
   TcArgs args;
   int BN;
+  bool dcn;
   int grid;
   size_t smem;
 };
 
 int g_num_sms = 0;
 
-template <int BN>
+template <int BN, bool DCN>
 int launch_tc(const TcOp &t, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    CPB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
+    CPB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, DCN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192));
     attr_set = true;
   }
-  conv_tc_kernel<BN><<<t.grid, TC_THREADS, t.smem, st>>>(t.args);
-  return cpb::check_launch("conv_tc_kernel");
+  conv_tc_kernel<BN, DCN><<<t.grid, DCN ? DCN_THREADS : TC_THREADS, t.smem, st>>>(t.args);
+  return cpb::check_launch(DCN ? "dcn_tc_kernel" : "conv_tc_kernel");
 }
 
 }  // namespace
@@ -327,7 +415,11 @@ int launch_tc(const TcOp &t, cudaStream_t st) {
 namespace cpb {
 
 int tc_prepare_op(cpb200_op &op) {
-  if (op.type != CPB200_OP_CONV) return fail(CPB200_ERR_ARG, "tc: only CONV ops run on the tensor-core path");
+  const bool dcn = op.type == CPB200_OP_DCN;
+  if (op.type != CPB200_OP_CONV && !dcn) return fail(CPB200_ERR_ARG, "tc: only CONV / DCN ops run on the tensor-core path");
+  if (dcn && (op.kh != 3 || op.kw != 3 || op.stride != 1 || op.pad_h != 1 || op.pad_w != 1 || op.nsrc != 1 ||
+              op.cin[0] % 64 || !op.aux || op.H != op.Ho || op.W != op.Wo))
+    return fail(CPB200_ERR_ARG, "tc: DCN needs 3x3/s1/p1, one input with C %% 64 == 0 and the offset/mask tensor");
   if (op.act_dtype != CPB200_BF16) return fail(CPB200_ERR_ARG, "tc: bf16 activations required");
   if (op.flags & CPB200_FLAG_OUT_NCHW_F32) return fail(CPB200_ERR_ARG, "tc: NCHW output not supported");
   if (op.stride < 1 || op.stride > 2) return fail(CPB200_ERR_ARG, "tc: stride %d", op.stride);
@@ -360,7 +452,9 @@ int tc_prepare_op(cpb200_op &op) {
   a.tiles_h = (op.Ho + a.TH - 1) / a.TH; a.tiles_w = (op.Wo + a.TW - 1) / a.TW;
   int BN = 16;
   while (BN < op.cout && BN < 256) BN <<= 1;
-  t->BN = BN;
+  t->BN = BN; t->dcn = dcn;
+  a.dcn_src = static_cast<const __nv_bfloat16 *>(op.src[0]); a.dcn_om = static_cast<const float *>(op.aux);
+  a.H = op.H; a.W = op.W;
   a.n_tiles = (op.cout + BN - 1) / BN;
   a.cout = op.cout; a.cout_store = op.cout;
   if (!(op.flags & CPB200_FLAG_OUT_F32) && (op.cout % 16)) { delete t; return fail(CPB200_ERR_ARG, "tc: bf16 output needs cout %% 16 == 0"); }
@@ -375,7 +469,7 @@ int tc_prepare_op(cpb200_op &op) {
   t->smem = stages * (a_bytes + b_bytes) + 1024;
   t->grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
 
-  for (int s = 0; s < op.nsrc; ++s) {
+  for (int s = 0; s < op.nsrc && !dcn; ++s) {
     const cuuint64_t dims[4] = {(cuuint64_t)op.cin[s], (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.B};
     const cuuint64_t strides[3] = {(cuuint64_t)op.cin[s] * 2, (cuuint64_t)op.W * op.cin[s] * 2, (cuuint64_t)op.H * op.W * op.cin[s] * 2};
     const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(a.TW * op.stride), (cuuint32_t)(a.TH * op.stride), 1};
@@ -407,12 +501,20 @@ int tc_release_op(cpb200_op &op) {
 int tc_run_op(const cpb200_op &op, cudaStream_t st) {
   const TcOp *t = static_cast<const TcOp *>(op.tc);
   if (!t) return fail(CPB200_ERR_STATE, "tc: op not prepared");
+  if (t->dcn) {
+    switch (t->BN) {
+      case 64: return launch_tc<64, true>(*t, st);
+      case 128: return launch_tc<128, true>(*t, st);
+      case 256: return launch_tc<256, true>(*t, st);
+    }
+    return fail(CPB200_ERR_STATE, "tc: DCN supports cout 64/128/256 tiles only");
+  }
   switch (t->BN) {
-    case 16: return launch_tc<16>(*t, st);
-    case 32: return launch_tc<32>(*t, st);
-    case 64: return launch_tc<64>(*t, st);
-    case 128: return launch_tc<128>(*t, st);
-    case 256: return launch_tc<256>(*t, st);
+    case 16: return launch_tc<16, false>(*t, st);
+    case 32: return launch_tc<32, false>(*t, st);
+    case 64: return launch_tc<64, false>(*t, st);
+    case 128: return launch_tc<128, false>(*t, st);
+    case 256: return launch_tc<256, false>(*t, st);
   }
   return fail(CPB200_ERR_STATE, "tc: bad BN");
 }

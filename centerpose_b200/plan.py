@@ -222,8 +222,11 @@ class PlanBuilder:
         om = self.conv([x], om_w.float(), om_b.float(), stride=1, pad=1, relu=False, out="f32")
         co = w.shape[0]
         y = self._sym(co, x.H, x.W)
-        self._emit(_PendingOp(type=OP_DCN, flags=FLAG_RELU if relu else 0, k=(3, 3), stride=1, pad=(1, 1),
-                              weight=self._pack_conv(w), bias=self._dev(b), cout=co, w_raw=w), [x], y, [om])
+        tc = (self.use_tc and x.kind == "act" and x.C % 64 == 0 and co % 16 == 0 and 64 <= co and x.W >= 8
+              and os.environ.get("CPB200_TC_DCN", "1") != "0")
+        self._emit(_PendingOp(type=OP_DCN, flags=(FLAG_RELU if relu else 0) | (FLAG_TC if tc else 0), k=(3, 3),
+                              stride=1, pad=(1, 1), weight=self._pack_conv_tc(w) if tc else self._pack_conv(w),
+                              bias=self._dev(b), cout=co, w_raw=w), [x], y, [om])
         return y
 
     # ---- finalisation -----------------------------------------------------------------------

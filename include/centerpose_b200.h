@@ -143,6 +143,12 @@ int cpb200_run_ops(const cpb200_op *ops, int n, void *stream);
 /* sizeof(cpb200_op) as compiled, so the host binding can verify its struct layout. */
 size_t cpb200_sizeof_op(void);
 
+/* Hardware probe (diagnostics only, not on the product path): one smem halo tile serving all nine
+ * taps of a 3x3 conv through shifted UMMA descriptors.  x (1,18,10,64) bf16 NHWC, w (9,64,64) bf16
+ * [tap][cout][cin], out (128,64) fp32 with row = th*8 + tw.  variant 0/1 = descriptor base_offset 0 /
+ * (start>>7)&7.  See centerpose_b200/csrc/probe.cu and tools/halo_probe.py. */
+int cpb200_probe_halo(const void *x, const void *w, float *out, int variant, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

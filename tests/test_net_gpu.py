@@ -199,6 +199,43 @@ def test_dcn_op_matches_oracle(precision, ci, co, H, W):
     _check(_nchw(_run(pb, y)), ref, precision, 2e-2 if precision == "bf16" else 5e-4)
 
 
+@pytest.mark.parametrize("ci,co,H,W", [(64, 64, 16, 16), (128, 64, 24, 40), (256, 256, 16, 16), (512, 256, 8, 8), (64, 128, 33, 20)])
+def test_dcn_tensor_core_path(ci, co, H, W):
+    """tcgen05 DCN (gather producers write the swizzled A tile) vs the oracle on bf16-rounded data.
+    Offsets are large (gain 1.5: many samples out of bounds).  Tolerance: relative L2 <= 1e-2 and
+    |err| <= 3e-2 max|ref| (bf16 A-operand rounding after the fp32 bilinear blend, bf16 output)."""
+    from oracle import dcn_ref
+    B = 2
+    g = torch.Generator().manual_seed(ci * 3 + co)
+    x = torch.randn(B, ci, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(co, ci, 3, 3, generator=g) / (ci * 9) ** 0.5).bfloat16().float(); b = torch.randn(co, generator=g)
+    ow = (torch.randn(27, ci, 3, 3, generator=g) * (1.5 / (ci * 9) ** 0.5)).bfloat16().float(); ob = torch.randn(27, generator=g)
+    ref = F.relu(dcn_ref.dcn_module_forward(x, w, b, ow, ob))
+    pb = _builder(B, "bf16", tc=True)
+    y = pb.dcn(pb.external(_nhwc(x, torch.bfloat16)), w.to(DEV), b.to(DEV), ow.to(DEV), ob.to(DEV), relu=True)
+    assert pb.ops[-1].type == 5 and pb.ops[-1].flags & 8, "DCN op was not routed to the tensor-core path"
+    got = _nchw(_run(pb, y))
+    rel = ((got - ref).norm() / ref.norm()).item()
+    err = (got - ref).abs().max().item()
+    assert rel <= 1e-2 and err <= 3e-2 * ref.abs().max().item(), (rel, err, ref.abs().max().item())
+
+
+def test_dcn_tensor_core_zero_offset_identity():
+    """DCNv2/test.py:31-66 on the tcgen05 DCN: zero offsets, mask 0.5, identity weights => 2*out == in
+    (exact: 0.5*x is representable in bf16)."""
+    B, C, H, W = 2, 64, 24, 16
+    x = torch.randint(-8, 9, (B, C, H, W), generator=torch.Generator().manual_seed(0)).float()
+    w = torch.zeros(C, C, 3, 3)
+    for c in range(C):
+        w[c, c, 1, 1] = 1.0
+    pb = _builder(B, "bf16", tc=True)
+    y = pb.dcn(pb.external(_nhwc(x, torch.bfloat16)), w.to(DEV), torch.zeros(C, device=DEV),
+               torch.zeros(27, C, 3, 3, device=DEV), torch.zeros(27, device=DEV), relu=False)
+    assert pb.ops[-1].flags & 8
+    out = _nchw(_run(pb, y))
+    assert torch.equal(2 * out, x)
+
+
 def test_dcn_zero_offset_identity():
     """DCNv2/test.py:31-66 check_zero_offset on the CUDA op: 2 * out == in."""
     B, C, H, W = 2, 16, 10, 12
