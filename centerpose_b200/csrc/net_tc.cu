@@ -18,9 +18,9 @@
 // issuer + TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> +bias (+residual) -> ReLU -> bf16 ->
 // global).  Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1;
 // a STAGES-deep smem ring with full/empty mbarriers feeds the tensor core.
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
 #include <mutex>
+#include <cstdlib>
 
 namespace {
 
@@ -48,74 +48,9 @@ struct alignas(64) TcArgs {
   int H, W;
 };
 
-// ------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace tc;
 
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tmap_prefetch(const CUtensorMap *map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, K-major operand, rows of `row_bytes` (= swizzle span), 8-row
-// core-matrix groups packed back to back (what a TMA box with inner extent = swizzle span writes).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes, uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                 // start address, bits [0,14)
-  d |= (uint64_t)1 << 16;                                  // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)((8u * row_bytes) >> 4) << 32;            // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                                  // descriptor version 1 (sm_100)
-  d |= (uint64_t)layout_type << 61;                        // 2 = SW128, 4 = SW64, 6 = SW32
-  return d;
-}
-
-constexpr int DCN_THREADS = 320;   // + 4 gather-producer warps
+constexpr int DCN_THREADS = 448;   // + 8 gather-producer warps
 
 struct __align__(16) DcnPrm { int off[4]; float wt[4]; };
 
@@ -129,7 +64,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
   __shared__ __align__(8) uint64_t bars[2 * 8 + 4];
   __shared__ uint32_t s_tmem;
   __shared__ float s_bias[2][BN];
-  __shared__ DcnPrm s_prm[DCN ? 4 : 1][DCN ? 32 : 1];
+  __shared__ DcnPrm s_prm[DCN ? 8 : 1][DCN ? 16 : 1];
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
   const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[18]);
 
@@ -139,7 +74,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
   if (warp == 0 && lane == 0) {
     if (!DCN) for (int s = 0; s < a.nsrc; ++s) tmap_prefetch(&a.amap[s]);
     tmap_prefetch(&a.bmap);
-    for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, DCN ? 1 + 128 : 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, DCN ? 1 + 256 : 1); mbar_init(empty0 + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -219,18 +154,19 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
       if (++acc == 2) { acc = 0; accphase ^= 1; }
     }
   } else if (DCN && warp >= 6) {
-    // =============================== DCN gather producers (warps 6..9) ===============================
+    // =============================== DCN gather producers (warps 6..13) ===============================
     // A[row = pixel][k = channel] of tap t is  sigmoid(mask_t) * bilinear(x, p + tap_t + offset_t)
     // (dcn_v2_im2col_cuda.cu:25-54,125-195), blended in fp32, rounded once to bf16 and stored straight
     // into the 128B-swizzled K-major tile the UMMA descriptor reads (16-byte chunk j of row r lives at
-    // chunk j ^ (r & 7)).  Lane = (row-in-group-of-4, 16-byte chunk): a warp reads 4 full 128-byte lines
-    // per corner load.
-    const int gw = warp - 6;
+    // chunk j ^ (r & 7)).  8 warps x 16 rows; lane = (row-in-group-of-4, 16-byte chunk) so a warp reads 4
+    // full 128-byte lines per corner load; all 16 corner loads of a stage are issued before the first
+    // use (64 KB in flight per SM) — the gather is latency-bound otherwise.
+    const int gw = warp - 6;                               // 0..7, rows [16*gw, 16*gw+16)
     int stage = 0; uint32_t phase = 0;
     const int Cin = a.cin[0];
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
-      const int rp = gw * 32 + lane;                       // the pixel whose sampling parameters I compute
+      const int rp = gw * 16 + (lane & 15);                // the pixel whose sampling parameters I compute
       const int ho = h0 + rp / a.TW, wo = w0 + rp % a.TW;
       const bool okp = ho < a.Ho && wo < a.Wo;
       const float *om = a.dcn_om + (((size_t)n * a.H + ho) * a.W + wo) * 27;
@@ -254,35 +190,41 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
           }
         }
         __syncwarp();
-        s_prm[gw][lane] = pr;
+        if (lane < 16) s_prm[gw][lane] = pr;
         __syncwarp();
+        const int chunk = lane & 7;
+        DcnPrm q[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) q[it] = s_prm[gw][it * 4 + (lane >> 3)];
         for (int c0 = 0; c0 < Cin; c0 += 64) {
+          uint4 v[4][4];
+#pragma unroll
+          for (int it = 0; it < 4; ++it)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)       // invalid corners have weight 0 and offset 0 (a safe address)
+              v[it][c] = __ldg(reinterpret_cast<const uint4 *>(a.dcn_src + (size_t)q[it].off[c] * Cin + c0 + chunk * 8));
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_base + stage * stage_bytes;
-#pragma unroll 2
-          for (int it = 0; it < 8; ++it) {
-            const int rl = it * 4 + (lane >> 3), chunk = lane & 7;
-            const DcnPrm q = s_prm[gw][rl];
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
             float acc[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[j] = 0.f;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              if (q.wt[c] != 0.f) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.dcn_src + (size_t)q.off[c] * Cin + c0 + chunk * 8));
-                const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+              const uint32_t u[4] = {v[it][c].x, v[it][c].y, v[it][c].z, v[it][c].w};
+              const float wgt = q[it].wt[c];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  acc[2 * j] = fmaf(q.wt[c], __uint_as_float(u[j] << 16), acc[2 * j]);
-                  acc[2 * j + 1] = fmaf(q.wt[c], __uint_as_float(u[j] & 0xFFFF0000u), acc[2 * j + 1]);
-                }
+              for (int j = 0; j < 4; ++j) {
+                acc[2 * j] = fmaf(wgt, __uint_as_float(u[j] << 16), acc[2 * j]);
+                acc[2 * j + 1] = fmaf(wgt, __uint_as_float(u[j] & 0xFFFF0000u), acc[2 * j + 1]);
               }
             }
             uint4 o;
             __nv_bfloat162 *ob = reinterpret_cast<__nv_bfloat162 *>(&o);
 #pragma unroll
             for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
-            const int row = gw * 32 + rl;
+            const int row = gw * 16 + it * 4 + (lane >> 3);
             const uint32_t dst = sa + row * 128 + ((chunk ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
           }
@@ -372,32 +314,15 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
 }
 
 // ------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
 struct TcOp {
   TcArgs args;
   int BN;
   bool dcn;
+  void *c3 = nullptr;      // halo-reuse 3x3 kernel handle (net_tc3.cu) when that path was chosen
   int grid;
   size_t smem;
 };
 
-int g_num_sms = 0;
 
 template <int BN, bool DCN>
 int launch_tc(const TcOp &t, cudaStream_t st) {
@@ -412,9 +337,52 @@ int launch_tc(const TcOp &t, cudaStream_t st) {
 
 }  // namespace
 
+namespace tc {
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+}  // namespace tc
+
 namespace cpb {
 
+bool c3_eligible(const cpb200_op &op);
+void *c3_prepare(const cpb200_op &op, int *rc);
+void c3_release(void *h);
+int c3_run(const void *h, cudaStream_t st);
+
+static bool halo_enabled() {
+  const char *e = getenv("CPB200_TC_HALO");
+  return !(e && e[0] == '0');
+}
+
 int tc_prepare_op(cpb200_op &op) {
+  if (halo_enabled() && c3_eligible(op)) {
+    int rc = CPB200_OK;
+    void *h = c3_prepare(op, &rc);
+    if (!h) return rc;
+    TcOp *t = new TcOp();
+    t->c3 = h;
+    op.tc = t;
+    return CPB200_OK;
+  }
   const bool dcn = op.type == CPB200_OP_DCN;
   if (op.type != CPB200_OP_CONV && !dcn) return fail(CPB200_ERR_ARG, "tc: only CONV / DCN ops run on the tensor-core path");
   if (dcn && (op.kh != 3 || op.kw != 3 || op.stride != 1 || op.pad_h != 1 || op.pad_w != 1 || op.nsrc != 1 ||
@@ -428,11 +396,7 @@ int tc_prepare_op(cpb200_op &op) {
   if (op.Wo < 8 || op.Ho < 1) return fail(CPB200_ERR_ARG, "tc: output too small");
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(CPB200_ERR_STATE, "tc: cuTensorMapEncodeTiled unavailable");
-  if (!g_num_sms) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
+  const int g_num_sms = tc::num_sms();
   TcOp *t = new TcOp();
   TcArgs &a = t->args;
   memset(&a, 0, sizeof(a));
@@ -493,7 +457,9 @@ int tc_prepare_op(cpb200_op &op) {
 }
 
 int tc_release_op(cpb200_op &op) {
-  delete static_cast<TcOp *>(op.tc);
+  TcOp *t = static_cast<TcOp *>(op.tc);
+  if (t && t->c3) c3_release(t->c3);
+  delete t;
   op.tc = nullptr;
   return CPB200_OK;
 }
@@ -501,6 +467,7 @@ int tc_release_op(cpb200_op &op) {
 int tc_run_op(const cpb200_op &op, cudaStream_t st) {
   const TcOp *t = static_cast<const TcOp *>(op.tc);
   if (!t) return fail(CPB200_ERR_STATE, "tc: op not prepared");
+  if (t->c3) return c3_run(t->c3, st);
   if (t->dcn) {
     switch (t->BN) {
       case 64: return launch_tc<64, true>(*t, st);

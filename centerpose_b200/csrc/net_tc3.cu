@@ -1,0 +1,358 @@
+// tcgen05 3x3 / stride-1 / pad-1 convolution with HALO REUSE (bf16 NHWC, fp32 accumulate in TMEM).
+//
+// The tap-per-stage kernel (net_tc.cu) fetches nine shifted 128-pixel windows per tile and channel
+// slab: 9 x 128 row requests through L2 for data that overlaps 89 %.  Here ONE (16+2) x (8+2) halo
+// box per slab is brought in by TMA (180 pixel rows) and all nine taps read it in place through
+// shifted UMMA shared-memory descriptors:
+//     tile = 16 rows x 8 columns of output pixels  ->  A row m = (th, tw) = (m / 8, m % 8);
+//     every 8-row core-matrix group of the A operand is therefore one tile row, so tap (r, s) is
+//         start address = halo + ((r * 10 + s) * pixel_bytes)      (+ 32 B per K step of 16)
+//         stride between 8-row groups (SBO) = 10 * pixel_bytes     (one halo row of pixels)
+// which is NOT a multiple of the 1024-byte swizzle repeat; it works because the hardware applies the
+// 128B/64B/32B swizzle XOR to absolute shared-memory address bits — measured with
+// cpb200_probe_halo (csrc/probe.cu, tools/halo_probe.py: exact with descriptor base_offset = 0).
+// TMA's out-of-bounds zero fill provides the conv padding for the halo border.
+//
+// Weights: [tap][Cout_pad][Cin] bf16 via 3-D TMA; when the whole filter bank fits beside the halo
+// ring it is loaded ONCE per CTA and stays resident (e.g. 64->64: 72 KB), otherwise it streams
+// through its own ring.  Warps: 0 = halo producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue,
+// 6 = weight producer; persistent CTAs, two TMEM accumulator stages.
+#include "tc_common.cuh"
+
+using namespace tc;
+
+namespace {
+
+constexpr int C3_THREADS = 224;
+constexpr int TW = 8, TH = 16, HW_ = TW + 2, HH_ = TH + 2;
+constexpr int MAX_NA = 4, MAX_NB = 8;
+
+struct alignas(64) C3Args {
+  CUtensorMap amap, bmap;
+  int cin, slabs, BK;
+  int B, Ho, Wo, tiles_h, tiles_w, n_tiles, total_tiles;
+  int cout, cout_store;
+  int na, nb, b_resident;
+  unsigned a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
+  void *dst;
+  const void *res;
+  const float *bias;
+  unsigned flags, swizzle_bits;
+};
+
+__device__ __forceinline__ uint64_t desc_sbo(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ C3Args a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base, b_base = smem_base + a.na * a.a_stage_bytes;
+  __shared__ __align__(8) uint64_t bars[2 * MAX_NA + 2 * MAX_NB + 1 + 4];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_bias[2][BN];
+  const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[MAX_NA]);
+  const uint32_t bfull0 = smem_u32(&bars[2 * MAX_NA]), bempty0 = smem_u32(&bars[2 * MAX_NA + MAX_NB]);
+  const uint32_t ball = smem_u32(&bars[2 * MAX_NA + 2 * MAX_NB]);
+  const uint32_t tfull0 = ball + 8, tempty0 = ball + 24;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  if (warp == 0 && lane == 0) {
+    tmap_prefetch(&a.amap); tmap_prefetch(&a.bmap);
+    for (int s = 0; s < MAX_NA; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
+    for (int s = 0; s < MAX_NB; ++s) { mbar_init(bfull0 + 8 * s, 1); mbar_init(bempty0 + 8 * s, 1); }
+    mbar_init(ball, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+  const uint32_t pix_bytes = a.BK * 2;
+
+  auto decode_tile = [&](int t, int &n, int &h0, int &w0, int &nt) {
+    nt = t % a.n_tiles; t /= a.n_tiles;
+    const int tw = t % a.tiles_w; t /= a.tiles_w;
+    const int th = t % a.tiles_h; n = t / a.tiles_h;
+    h0 = th * TH; w0 = tw * TW;
+  };
+
+  if (warp == 0) {
+    // =============================== halo producer ===============================
+    if (lane == 0) {
+      int sa = 0; uint32_t pha = 0;
+      for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
+        for (int sl = 0; sl < a.slabs; ++sl) {
+          mbar_wait(aempty0 + 8 * sa, pha ^ 1);
+          mbar_expect_tx(afull0 + 8 * sa, a.a_tx_bytes);
+          tma_load_4d(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, w0 - 1, h0 - 1, n);
+          if (++sa == a.na) { sa = 0; pha ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // =============================== weight producer ===============================
+    if (lane == 0) {
+      if (a.b_resident) {
+        mbar_expect_tx(ball, 9u * a.slabs * a.b_tx_bytes);
+        for (int sl = 0; sl < a.slabs; ++sl)
+          for (int tap = 0; tap < 9; ++tap)
+            tma_load_3d(b_base + (sl * 9 + tap) * a.b_stage_bytes, &a.bmap, ball, sl * a.BK, 0, tap);
+      } else {
+        int sb = 0; uint32_t phb = 0;
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+          const int nt = t % a.n_tiles;
+          for (int sl = 0; sl < a.slabs; ++sl)
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(bempty0 + 8 * sb, phb ^ 1);
+              mbar_expect_tx(bfull0 + 8 * sb, a.b_tx_bytes);
+              tma_load_3d(b_base + sb * a.b_stage_bytes, &a.bmap, bfull0 + 8 * sb, sl * a.BK, nt * BN, tap);
+              if (++sb == a.nb) { sb = 0; phb ^= 1; }
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int sa = 0; uint32_t pha = 0; int sb = 0; uint32_t phb = 0; int acc = 0; uint32_t accphase = 0;
+    if (a.b_resident) { mbar_wait(ball, 0); tc_fence_after(); }
+    const int ksteps = a.BK / 16;
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int sl = 0; sl < a.slabs; ++sl) {
+        mbar_wait(afull0 + 8 * sa, pha);
+        tc_fence_after();
+        const uint32_t halo = a_base + sa * a.a_stage_bytes;
+        for (int tap = 0; tap < 9; ++tap) {
+          uint32_t bsm;
+          if (a.b_resident) {
+            bsm = b_base + (sl * 9 + tap) * a.b_stage_bytes;
+          } else {
+            mbar_wait(bfull0 + 8 * sb, phb);
+            tc_fence_after();
+            bsm = b_base + sb * a.b_stage_bytes;
+          }
+          if (lane == 0) {
+            const int r = tap / 3, s = tap - 3 * r;
+            const uint64_t ad = desc_sbo(halo + (r * HW_ + s) * pix_bytes, HW_ * pix_bytes, a.swizzle_bits);
+            const uint64_t bd = desc_sbo(bsm, 8 * pix_bytes, a.swizzle_bits);
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            if (!a.b_resident) umma_commit(bempty0 + 8 * sb);
+          }
+          __syncwarp();
+          if (!a.b_resident) { if (++sb == a.nb) { sb = 0; phb ^= 1; } }
+        }
+        if (lane == 0) {
+          umma_commit(aempty0 + 8 * sa);
+          if (sl == a.slabs - 1) umma_commit(tfull0 + 8 * acc);
+        }
+        __syncwarp();
+        if (++sa == a.na) { sa = 0; pha ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; accphase ^= 1; }
+    }
+  } else {
+    // =============================== epilogue (warps 2..5) ===============================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const bool relu = a.flags & CPB200_FLAG_RELU;
+    const bool out_f32 = a.flags & CPB200_FLAG_OUT_F32;
+    int acc = 0; uint32_t accphase = 0;
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
+      const int n0 = nt * BN;
+      for (int i = et; i < BN; i += 128) s_bias[acc][i] = (a.bias && n0 + i < a.cout) ? __ldg(a.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tfull0 + 8 * acc, accphase);
+      tc_fence_after();
+      const int ho = h0 + (row >> 3), wo = w0 + (row & 7);
+      const bool ok = ho < a.Ho && wo < a.Wo;
+      const size_t pix = ((size_t)n * a.Ho + ho) * a.Wo + wo;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c * 16, v);
+        tmem_ld_wait();
+        const int nb = n0 + c * 16;
+        if (ok && nb < a.cout) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[acc][c * 16 + j];
+          if (out_f32) {
+            float *o = static_cast<float *>(a.dst) + pix * a.cout_store + nb;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nb + j < a.cout) o[j] = relu ? fmaxf(f[j], 0.f) : f[j];
+          } else {
+            __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(a.dst) + pix * a.cout_store + nb;
+            if (a.res) {
+              const uint4 *rp = reinterpret_cast<const uint4 *>(static_cast<const __nv_bfloat16 *>(a.res) + pix * a.cout_store + nb);
+              uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+              const __nv_bfloat162 *rb0 = reinterpret_cast<const __nv_bfloat162 *>(&r0);
+              const __nv_bfloat162 *rb1 = reinterpret_cast<const __nv_bfloat162 *>(&r1);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 x0 = __bfloat1622float2(rb0[j]), x1 = __bfloat1622float2(rb1[j]);
+                f[2 * j] += x0.x; f[2 * j + 1] += x0.y; f[8 + 2 * j] += x1.x; f[8 + 2 * j + 1] += x1.y;
+              }
+            }
+            if (relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint4 o0, o1;
+            __nv_bfloat162 *ob0 = reinterpret_cast<__nv_bfloat162 *>(&o0), *ob1 = reinterpret_cast<__nv_bfloat162 *>(&o1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              ob0[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              ob1[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
+            }
+            reinterpret_cast<uint4 *>(o)[0] = o0;
+            reinterpret_cast<uint4 *>(o)[1] = o1;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (++acc == 2) { acc = 0; accphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+struct C3Op {
+  C3Args args;
+  int BN, grid;
+  size_t smem;
+};
+
+template <int BN>
+int launch_c3(const C3Op &t, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CPB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192));
+    attr_set = true;
+  }
+  conv3x3_tc_kernel<BN><<<t.grid, C3_THREADS, t.smem, st>>>(t.args);
+  return cpb::check_launch("conv3x3_tc_kernel");
+}
+
+}  // namespace
+
+namespace cpb {
+
+bool c3_eligible(const cpb200_op &op) {
+  return op.type == CPB200_OP_CONV && op.kh == 3 && op.kw == 3 && op.stride == 1 && op.pad_h == 1 && op.pad_w == 1 &&
+         op.nsrc == 1 && op.cin[0] % 16 == 0 && op.Wo >= 8 && op.Ho >= 8 && op.H == op.Ho && op.W == op.Wo &&
+         op.out_sy == 1 && op.out_sx == 1 && !op.out_oy && !op.out_ox && op.Hd == op.Ho && op.Wd == op.Wo &&
+         !(op.flags & CPB200_FLAG_OUT_NCHW_F32) && op.act_dtype == CPB200_BF16 &&
+         ((op.flags & CPB200_FLAG_OUT_F32) || op.cout % 16 == 0);
+}
+
+// returns an opaque handle (C3Op*) or nullptr + error
+void *c3_prepare(const cpb200_op &op, int *rc) {
+  *rc = CPB200_OK;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { *rc = fail(CPB200_ERR_STATE, "tc3: cuTensorMapEncodeTiled unavailable"); return nullptr; }
+  C3Op *t = new C3Op();
+  C3Args &a = t->args;
+  memset(&a, 0, sizeof(a));
+  const int cin = op.cin[0];
+  const int bk = (cin % 64 == 0) ? 64 : (cin % 32 == 0) ? 32 : 16;
+  a.cin = cin; a.BK = bk; a.slabs = cin / bk;
+  const CUtensorMapSwizzle sw = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  a.swizzle_bits = bk == 64 ? 2u : bk == 32 ? 4u : 6u;
+  a.B = op.B; a.Ho = op.Ho; a.Wo = op.Wo;
+  a.tiles_h = (op.Ho + TH - 1) / TH; a.tiles_w = (op.Wo + TW - 1) / TW;
+  int BN = 16;
+  while (BN < op.cout && BN < 256) BN <<= 1;
+  t->BN = BN;
+  a.n_tiles = (op.cout + BN - 1) / BN;
+  a.cout = op.cout; a.cout_store = op.cout;
+  a.total_tiles = op.B * a.tiles_h * a.tiles_w * a.n_tiles;
+  a.dst = op.dst; a.res = op.res; a.bias = op.bias; a.flags = op.flags;
+  a.a_tx_bytes = HW_ * HH_ * bk * 2;
+  a.a_stage_bytes = (a.a_tx_bytes + 1023u) & ~1023u;
+  a.b_tx_bytes = BN * bk * 2;
+  a.b_stage_bytes = (a.b_tx_bytes + 1023u) & ~1023u;
+  const size_t budget = 200 * 1024;
+  a.na = 3;
+  const size_t resident_bytes = (size_t)9 * a.slabs * a.b_stage_bytes;
+  if (a.n_tiles == 1 && a.na * (size_t)a.a_stage_bytes + resident_bytes <= budget) {
+    a.b_resident = 1; a.nb = 9 * a.slabs;
+    t->smem = a.na * (size_t)a.a_stage_bytes + resident_bytes + 1024;
+  } else {
+    a.b_resident = 0;
+    if (a.na * (size_t)a.a_stage_bytes + 3 * (size_t)a.b_stage_bytes > budget) a.na = 2;
+    int nb = (int)((budget - a.na * (size_t)a.a_stage_bytes) / a.b_stage_bytes);
+    if (nb > MAX_NB) nb = MAX_NB;
+    if (nb < 2) { delete t; *rc = fail(CPB200_ERR_ARG, "tc3: tile does not fit shared memory"); return nullptr; }
+    a.nb = nb;
+    t->smem = a.na * (size_t)a.a_stage_bytes + nb * (size_t)a.b_stage_bytes + 1024;
+  }
+  const int nsm = num_sms();
+  t->grid = a.total_tiles < nsm ? a.total_tiles : nsm;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)op.W * cin * 2, (cuuint64_t)op.H * op.W * cin * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)bk, HW_, HH_, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = enc(&a.amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(op.src[0]), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { delete t; *rc = fail(CPB200_ERR_CUDA, "tc3: cuTensorMapEncodeTiled(A) failed: %d", (int)r); return nullptr; }
+  }
+  {
+    const int cout_pad = (op.cout + 15) / 16 * 16;
+    const cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout_pad, 9};
+    const cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout_pad * cin * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)BN, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&a.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(op.weight), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { delete t; *rc = fail(CPB200_ERR_CUDA, "tc3: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return nullptr; }
+  }
+  return t;
+}
+
+void c3_release(void *h) { delete static_cast<C3Op *>(h); }
+
+int c3_run(const void *h, cudaStream_t st) {
+  const C3Op *t = static_cast<const C3Op *>(h);
+  switch (t->BN) {
+    case 16: return launch_c3<16>(*t, st);
+    case 32: return launch_c3<32>(*t, st);
+    case 64: return launch_c3<64>(*t, st);
+    case 128: return launch_c3<128>(*t, st);
+    case 256: return launch_c3<256>(*t, st);
+  }
+  return fail(CPB200_ERR_STATE, "tc3: bad BN");
+}
+
+}  // namespace cpb

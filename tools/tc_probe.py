@@ -28,6 +28,12 @@ CASES = [
     ("w8_tiles", [256], 256, 3, 1, 8, 8, 4, "rand"),
     ("persistent_many_tiles", [64], 64, 3, 1, 128, 128, 12, "rand"),
     ("7x7_c16", [16], 16, 7, 1, 16, 32, 1, "rand"),
+    ("3x3_c16_s1_halo_sw32", [16], 16, 3, 1, 32, 32, 2, "rand"),
+    ("3x3_c32_s1_halo_sw64", [32], 64, 3, 1, 32, 24, 2, "rand"),
+    ("3x3_c128_c64_halo_ring", [128], 64, 3, 1, 32, 32, 2, "rand"),
+    ("3x3_c128_c128_halo", [128], 128, 3, 1, 40, 24, 2, "rand"),
+    ("3x3_c512_c512_halo", [512], 512, 3, 1, 16, 16, 2, "rand"),
+    ("3x3_c64_odd_size_halo", [64], 64, 3, 1, 19, 13, 3, "rand"),
 ]
 
 
