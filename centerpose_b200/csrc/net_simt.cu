@@ -266,46 +266,66 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
   }
 }
 
-// ---- STEM: NCHW fp32 (B,Cin<=4,H,W) -> NHWC (B,Ho,Wo,Cout<=32), direct conv, bias + ReLU ----
-// weight layout: [kh*kw*cin][cout] fp32.  One thread = one output pixel, all couts.
-template <typename T, int COUT>
+// ---- STEM: NCHW fp32 (B,Cin<=4,H,W) -> NHWC (B,Ho,Wo,Cout<=64), direct conv, bias + ReLU ----
+// weight layout: [kh*kw*cin][cout] fp32 in shared memory.  One thread = PX consecutive output
+// pixels of one row x all couts: every weight vector fetched from shared memory feeds PX pixels
+// (PX*COUT FMAs per COUT/4 LDS.128), the input row segment is read once into registers.
+template <typename T, int COUT, int PX, int STRIDE, int KW>
 __global__ void __launch_bounds__(128) stem_kernel(const float *__restrict__ x, T *__restrict__ y,
                                                    const float *__restrict__ w, const float *__restrict__ bias,
                                                    int B, int Cin, int H, int W, int Ho, int Wo,
-                                                   int kh, int kw, int stride, int pad_h, int pad_w, int relu) {
-  extern __shared__ float sw[];                      // kh*kw*cin*COUT
-  const int nw = kh * kw * Cin * COUT;
+                                                   int kh, int pad_h, int pad_w, int relu) {
+  extern __shared__ float sw[];                      // kh*KW*cin*COUT
+  const int nw = kh * KW * Cin * COUT;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
-  const long long M = (long long)B * Ho * Wo;
+  const int WG = Wo / PX;                            // pixel groups per row (Wo % PX == 0 checked by the host)
+  const long long M = (long long)B * Ho * WG;
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
-  const int b = (int)(m / ((long long)Ho * Wo));
-  const int rem = (int)(m % ((long long)Ho * Wo));
-  const int ho = rem / Wo, wo = rem % Wo;
-  float acc[COUT];
+  const int b = (int)(m / ((long long)Ho * WG));
+  const int rem = (int)(m % ((long long)Ho * WG));
+  const int ho = rem / WG, wo0 = (rem % WG) * PX;
+  float acc[PX][COUT];
 #pragma unroll
-  for (int n = 0; n < COUT; ++n) acc[n] = bias ? bias[n] : 0.f;
+  for (int p = 0; p < PX; ++p)
+#pragma unroll
+    for (int n = 0; n < COUT; ++n) acc[p][n] = bias ? __ldg(bias + n) : 0.f;
+  constexpr int SEG = (PX - 1) * STRIDE + KW;        // input columns feeding PX outputs
+  const int wi0 = wo0 * STRIDE - pad_w;
   for (int r = 0; r < kh; ++r) {
-    const int hi = ho * stride - pad_h + r;
+    const int hi = ho * STRIDE - pad_h + r;
     if (hi < 0 || hi >= H) continue;
-    for (int q = 0; q < kw; ++q) {
-      const int wi = wo * stride - pad_w + q;
-      if (wi < 0 || wi >= W) continue;
-      for (int c = 0; c < Cin; ++c) {
-        const float v = __ldg(x + (((size_t)b * Cin + c) * H + hi) * W + wi);
-        const float *wp = sw + ((r * kw + q) * Cin + c) * COUT;
+    for (int c = 0; c < Cin; ++c) {
+      const float *row = x + (((size_t)b * Cin + c) * H + hi) * W;
+      float in[SEG];
 #pragma unroll
-        for (int n = 0; n < COUT; ++n) acc[n] = fmaf(v, wp[n], acc[n]);
+      for (int i = 0; i < SEG; ++i) { const int wi = wi0 + i; in[i] = (wi >= 0 && wi < W) ? __ldg(row + wi) : 0.f; }
+#pragma unroll
+      for (int q = 0; q < KW; ++q) {
+        const float4 *wp = reinterpret_cast<const float4 *>(sw + ((r * KW + q) * Cin + c) * COUT);
+#pragma unroll
+        for (int n4 = 0; n4 < COUT / 4; ++n4) {
+          const float4 w4 = wp[n4];
+#pragma unroll
+          for (int p = 0; p < PX; ++p) {
+            const float v = in[p * STRIDE + q];
+            acc[p][4 * n4] = fmaf(v, w4.x, acc[p][4 * n4]); acc[p][4 * n4 + 1] = fmaf(v, w4.y, acc[p][4 * n4 + 1]);
+            acc[p][4 * n4 + 2] = fmaf(v, w4.z, acc[p][4 * n4 + 2]); acc[p][4 * n4 + 3] = fmaf(v, w4.w, acc[p][4 * n4 + 3]);
+          }
+        }
       }
     }
   }
-  T *o = y + (size_t)m * COUT;
 #pragma unroll
-  for (int n = 0; n < COUT; n += 4) {
-    float4 v = make_float4(acc[n], acc[n + 1], acc[n + 2], acc[n + 3]);
-    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    Act<T>::st4(o + n, v);
+  for (int p = 0; p < PX; ++p) {
+    T *o = y + ((((size_t)b * Ho + ho) * Wo) + wo0 + p) * COUT;
+#pragma unroll
+    for (int n = 0; n < COUT; n += 4) {
+      float4 v = make_float4(acc[p][n], acc[p][n + 1], acc[p][n + 2], acc[p][n + 3]);
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      Act<T>::st4(o + n, v);
+    }
   }
 }
 
@@ -339,35 +359,48 @@ __global__ void maxpool_kernel(const T *__restrict__ x, T *__restrict__ y, int B
 
 // ---- depthwise ConvTranspose2d(k=2f, stride f, pad f/2) + skip add, NHWC ----
 // out[b,ho,wo,c] = skip[b,ho,wo,c] + sum_{kh,kw : (ho+p-kh)%f==0, (wo+p-kw)%f==0} x[b,(ho+p-kh)/f,(wo+p-kw)/f,c] * w[kh,kw,c]
-template <typename T>
+// VEC channels per thread (8 for bf16 = one 16-byte access, 4 for fp32).
+template <typename T, int VEC>
 __global__ void dwdeconv_add_kernel(const T *__restrict__ x, const T *__restrict__ skip, T *__restrict__ y,
                                     const float *__restrict__ w, int B, int H, int W, int C, int Ho, int Wo,
                                     int k, int f, int pad) {
-  const int C4 = C >> 2;
-  const long long total = (long long)B * Ho * Wo * C4;
+  const int CV = C / VEC;
+  const long long total = (long long)B * Ho * Wo * CV;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    long long p = i / C4;
+    const int cv = (int)(i % CV);
+    long long p = i / CV;
     const int wo = (int)(p % Wo); p /= Wo;
     const int ho = (int)(p % Ho);
     const int b = (int)(p / Ho);
-    const size_t opix = (((size_t)b * Ho + ho) * Wo + wo) * C + c4 * 4;
-    float4 acc = skip ? Act<T>::ld4(skip + opix) : make_float4(0.f, 0.f, 0.f, 0.f);
-    // valid kh: kh ≡ (ho+pad) mod f, 0 <= kh < k
+    const size_t opix = (((size_t)b * Ho + ho) * Wo + wo) * C + cv * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; q += 4) {
+      float4 s4 = skip ? Act<T>::ld4(skip + opix + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[q] = s4.x; acc[q + 1] = s4.y; acc[q + 2] = s4.z; acc[q + 3] = s4.w;
+    }
     for (int khh = (ho + pad) % f; khh < k; khh += f) {
-      const int hi = (ho + pad - khh) / f;
-      if (hi < 0 || hi >= H || ho + pad - khh < 0) continue;
+      const int hn = ho + pad - khh;
+      const int hi = hn / f;
+      if (hn < 0 || hi >= H) continue;
       for (int kww = (wo + pad) % f; kww < k; kww += f) {
-        const int wi = (wo + pad - kww) / f;
-        if (wi < 0 || wi >= W || wo + pad - kww < 0) continue;
-        const float4 v = Act<T>::ld4(x + (((size_t)b * H + hi) * W + wi) * C + c4 * 4);
-        const float4 ww = __ldg(reinterpret_cast<const float4 *>(w + ((size_t)khh * k + kww) * C + c4 * 4));
-        acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y);
-        acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
+        const int wn = wo + pad - kww;
+        const int wi = wn / f;
+        if (wn < 0 || wi >= W) continue;
+        const T *xp = x + (((size_t)b * H + hi) * W + wi) * C + cv * VEC;
+        const float *wp = w + ((size_t)khh * k + kww) * C + cv * VEC;
+#pragma unroll
+        for (int q = 0; q < VEC; q += 4) {
+          const float4 v = Act<T>::ld4(xp + q);
+          const float4 ww = __ldg(reinterpret_cast<const float4 *>(wp + q));
+          acc[q] = fmaf(v.x, ww.x, acc[q]); acc[q + 1] = fmaf(v.y, ww.y, acc[q + 1]);
+          acc[q + 2] = fmaf(v.z, ww.z, acc[q + 2]); acc[q + 3] = fmaf(v.w, ww.w, acc[q + 3]);
+        }
       }
     }
-    Act<T>::st4(y + opix, acc);
+#pragma unroll
+    for (int q = 0; q < VEC; q += 4) Act<T>::st4(y + opix + q, make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]));
   }
 }
 
@@ -411,19 +444,26 @@ int run_op_simt(const cpb200_op &op, cudaStream_t st) {
       if (op.kh != 3 || op.kw != 3 || !op.aux) return cpb::fail(CPB200_ERR_ARG, "dcn: needs 3x3 kernel and offset/mask tensor");
       return launch_conv<T, true>(op, st);
     case CPB200_OP_STEM: {
-      const long long M = (long long)op.B * op.Ho * op.Wo;
       const int cin = op.cin[0];
       const size_t smem = (size_t)op.kh * op.kw * cin * op.cout * sizeof(float);
-      if (cin > 4 || smem > 48 * 1024) return cpb::fail(CPB200_ERR_ARG, "stem: unsupported shape");
-      const unsigned grid = (unsigned)((M + 127) / 128);
+      if (cin > 4 || smem > 48 * 1024 || op.kw != 7) return cpb::fail(CPB200_ERR_ARG, "stem: unsupported shape");
       const int relu = (op.flags & CPB200_FLAG_RELU) ? 1 : 0;
-#define STEM_CASE(CO)                                                                              \
-  case CO: stem_kernel<T, CO><<<grid, 128, smem, st>>>(static_cast<const float *>(op.src[0]),     \
-      static_cast<T *>(op.dst), static_cast<const float *>(op.weight), op.bias, op.B, cin, op.H,  \
-      op.W, op.Ho, op.Wo, op.kh, op.kw, op.stride, op.pad_h, op.pad_w, relu); break;
-      switch (op.cout) { STEM_CASE(16) STEM_CASE(32) STEM_CASE(64)
-        default: return cpb::fail(CPB200_ERR_ARG, "stem: cout %d unsupported", op.cout); }
-#undef STEM_CASE
+      // (COUT, PX) register tiles: 16 couts x 4 pixels, 64 couts x 1 pixel
+#define STEM_LAUNCH(CO, PX, ST)                                                                              \
+  {                                                                                                          \
+    if (op.Wo % PX) return cpb::fail(CPB200_ERR_ARG, "stem: output width %d not a multiple of %d", op.Wo, PX); \
+    const long long M = (long long)op.B * op.Ho * (op.Wo / PX);                                              \
+    stem_kernel<T, CO, PX, ST, 7><<<(unsigned)((M + 127) / 128), 128, smem, st>>>(                           \
+        static_cast<const float *>(op.src[0]), static_cast<T *>(op.dst), static_cast<const float *>(op.weight), \
+        op.bias, op.B, cin, op.H, op.W, op.Ho, op.Wo, op.kh, op.pad_h, op.pad_w, relu);                      \
+  }
+      if (op.cout == 16 && op.stride == 1) STEM_LAUNCH(16, 4, 1)
+      else if (op.cout == 16 && op.stride == 2) STEM_LAUNCH(16, 4, 2)
+      else if (op.cout == 32 && op.stride == 2) STEM_LAUNCH(32, 2, 2)
+      else if (op.cout == 64 && op.stride == 2) STEM_LAUNCH(64, 1, 2)
+      else if (op.cout == 64 && op.stride == 1) STEM_LAUNCH(64, 1, 1)
+      else return cpb::fail(CPB200_ERR_ARG, "stem: cout %d / stride %d unsupported", op.cout, op.stride);
+#undef STEM_LAUNCH
       return cpb::check_launch("stem_kernel");
     }
     case CPB200_OP_MAXPOOL: {
@@ -435,10 +475,11 @@ int run_op_simt(const cpb200_op &op, cudaStream_t st) {
       return cpb::check_launch("maxpool_kernel");
     }
     case CPB200_OP_DWDECONV_ADD: {
-      if (op.cin[0] % 4) return cpb::fail(CPB200_ERR_ARG, "dwdeconv: C %% 4 != 0");
-      const long long total = (long long)op.B * op.Ho * op.Wo * (op.cin[0] / 4);
-      const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 32);
-      dwdeconv_add_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(op.src[0]),
+      constexpr int VEC = sizeof(T) == 2 ? 8 : 4;
+      if (op.cin[0] % VEC) return cpb::fail(CPB200_ERR_ARG, "dwdeconv: C %% %d != 0", VEC);
+      const long long total = (long long)op.B * op.Ho * op.Wo * (op.cin[0] / VEC);
+      const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 64);
+      dwdeconv_add_kernel<T, VEC><<<grid, 256, 0, st>>>(static_cast<const T *>(op.src[0]),
           static_cast<const T *>(op.aux), static_cast<T *>(op.dst), static_cast<const float *>(op.weight),
           op.B, op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h);
       return cpb::check_launch("dwdeconv_add_kernel");

@@ -46,6 +46,7 @@ struct alignas(64) TcArgs {
   const __nv_bfloat16 *dcn_src;   // (B,H,W,Cin) bf16
   const float *dcn_om;            // (B,H,W,27) fp32: 18 offsets (dy,dx per tap) | 9 mask logits
   int H, W;
+  int Hd, Wd, sy, sx, oy, ox;     // strided output mapping (dense ConvTranspose2d parity sub-convs)
 };
 
 using namespace tc;
@@ -207,23 +208,17 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
           const uint32_t sa = smem_base + stage * stage_bytes;
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
-            float acc[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+            // packed bf16x2 blend: 4 corners x 4 pairs = 16 HFMA2 per 16-byte chunk (the A operand is
+            // bf16 anyway; fp32 blending cost 64 instructions per chunk and made the gather issue-bound)
+            __nv_bfloat162 acc2[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const uint32_t u[4] = {v[it][c].x, v[it][c].y, v[it][c].z, v[it][c].w};
-              const float wgt = q[it].wt[c];
+              const __nv_bfloat162 w2 = __float2bfloat162_rn(q[it].wt[c]);
+              const __nv_bfloat162 *vv = reinterpret_cast<const __nv_bfloat162 *>(&v[it][c]);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                acc[2 * j] = fmaf(wgt, __uint_as_float(u[j] << 16), acc[2 * j]);
-                acc[2 * j + 1] = fmaf(wgt, __uint_as_float(u[j] & 0xFFFF0000u), acc[2 * j + 1]);
-              }
+              for (int j = 0; j < 4; ++j) acc2[j] = (c == 0) ? __hmul2(w2, vv[j]) : __hfma2(w2, vv[j], acc2[j]);
             }
-            uint4 o;
-            __nv_bfloat162 *ob = reinterpret_cast<__nv_bfloat162 *>(&o);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) ob[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+            const uint4 o = *reinterpret_cast<const uint4 *>(acc2);
             const int row = gw * 16 + it * 4 + (lane >> 3);
             const uint32_t dst = sa + row * 128 + ((chunk ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
@@ -252,7 +247,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
       const int th = row / a.TW, tw = row % a.TW;
       const int ho = h0 + th, wo = w0 + tw;
       const bool ok = ho < a.Ho && wo < a.Wo;
-      const size_t pix = ((size_t)n * a.Ho + ho) * a.Wo + wo;
+      const size_t pix = ((size_t)n * a.Hd + (ho * a.sy + a.oy)) * a.Wd + (wo * a.sx + a.ox);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = 0; c < BN / 16; ++c) {
@@ -391,8 +386,6 @@ int tc_prepare_op(cpb200_op &op) {
   if (op.act_dtype != CPB200_BF16) return fail(CPB200_ERR_ARG, "tc: bf16 activations required");
   if (op.flags & CPB200_FLAG_OUT_NCHW_F32) return fail(CPB200_ERR_ARG, "tc: NCHW output not supported");
   if (op.stride < 1 || op.stride > 2) return fail(CPB200_ERR_ARG, "tc: stride %d", op.stride);
-  if (op.out_sy != 1 || op.out_sx != 1 || op.out_oy || op.out_ox || op.Hd != op.Ho || op.Wd != op.Wo)
-    return fail(CPB200_ERR_ARG, "tc: strided output not supported");
   if (op.Wo < 8 || op.Ho < 1) return fail(CPB200_ERR_ARG, "tc: output too small");
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail(CPB200_ERR_STATE, "tc: cuTensorMapEncodeTiled unavailable");
@@ -419,6 +412,7 @@ int tc_prepare_op(cpb200_op &op) {
   t->BN = BN; t->dcn = dcn;
   a.dcn_src = static_cast<const __nv_bfloat16 *>(op.src[0]); a.dcn_om = static_cast<const float *>(op.aux);
   a.H = op.H; a.W = op.W;
+  a.Hd = op.Hd; a.Wd = op.Wd; a.sy = op.out_sy; a.sx = op.out_sx; a.oy = op.out_oy; a.ox = op.out_ox;
   a.n_tiles = (op.cout + BN - 1) / BN;
   a.cout = op.cout; a.cout_store = op.cout;
   if (!(op.flags & CPB200_FLAG_OUT_F32) && (op.cout % 16)) { delete t; return fail(CPB200_ERR_ARG, "tc: bf16 output needs cout %% 16 == 0"); }
@@ -428,6 +422,7 @@ int tc_prepare_op(cpb200_op &op) {
   const size_t budget = 200 * 1024;
   int stages = (int)(budget / (a_bytes + b_bytes));
   if (stages > 8) stages = 8;
+  if (dcn && stages > 4) stages = 4;      // leave the rest of the 228 KB to L1: the 9 taps x 4 corners re-read one ~30 KB footprint
   if (stages < 2) { delete t; return fail(CPB200_ERR_ARG, "tc: tile does not fit shared memory"); }
   a.stages = stages;
   t->smem = stages * (a_bytes + b_bytes) + 1024;

@@ -25,7 +25,7 @@ namespace {
 
 constexpr int C3_THREADS = 224;
 constexpr int TW = 8, TH = 16, HW_ = TW + 2, HH_ = TH + 2;
-constexpr int MAX_NA = 4, MAX_NB = 8;
+constexpr int MAX_NA = 8, MAX_NB = 8;
 
 struct alignas(64) C3Args {
   CUtensorMap amap, bmap;
@@ -177,11 +177,19 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
     const bool relu = a.flags & CPB200_FLAG_RELU;
     const bool out_f32 = a.flags & CPB200_FLAG_OUT_F32;
     int acc = 0; uint32_t accphase = 0;
+    bool bias_loaded = false;
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
       const int n0 = nt * BN;
-      for (int i = et; i < BN; i += 128) s_bias[acc][i] = (a.bias && n0 + i < a.cout) ? __ldg(a.bias + n0 + i) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (a.n_tiles > 1 || !bias_loaded) {      // one N tile: the bias never changes — load it once
+        for (int i = et; i < BN; i += 128) {
+          const float bv = (a.bias && n0 + i < a.cout) ? __ldg(a.bias + n0 + i) : 0.f;
+          s_bias[acc][i] = bv;
+          if (a.n_tiles == 1) s_bias[acc ^ 1][i] = bv;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        bias_loaded = true;
+      }
       mbar_wait(tfull0 + 8 * acc, accphase);
       tc_fence_after();
       const int ho = h0 + (row >> 3), wo = w0 + (row & 7);
@@ -304,6 +312,7 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   a.b_stage_bytes = (a.b_tx_bytes + 1023u) & ~1023u;
   const size_t budget = 200 * 1024;
   a.na = 3;
+  if (a.a_stage_bytes <= 12 * 1024) a.na = (a.a_stage_bytes <= 6 * 1024) ? 8 : 5;   // small halos: deeper ring hides TMA latency
   const size_t resident_bytes = (size_t)9 * a.slabs * a.b_stage_bytes;
   if (a.n_tiles == 1 && a.na * (size_t)a.a_stage_bytes + resident_bytes <= budget) {
     a.b_resident = 1; a.nb = 9 * a.slabs;

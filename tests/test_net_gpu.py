@@ -250,11 +250,34 @@ def test_dcn_zero_offset_identity():
     assert (2 * out - x).abs().max().item() < 1e-6
 
 
-def _model(precision):
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16tc"])
+def test_dense_deconv_lowering(mode):
+    """ConvTranspose2d(k4,s2,p1)+BN+ReLU (msra_resnet.py:168-193) lowered to four parity 2x2 convs."""
+    from centerpose_b200.archs.resnet import _deconv_bn_relu
+    from centerpose_b200.archs.common import StateView
+    B, ci, co, H, W = 2, 64, 32, 12, 16
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, ci, H, W, generator=g).bfloat16().float()
+    wt = (torch.randn(ci, co, 4, 4, generator=g) / (ci * 4) ** 0.5).bfloat16().float()
+    bnp = {"weight": torch.rand(co, generator=g) + 0.5, "bias": torch.randn(co, generator=g) * 0.1,
+           "running_mean": torch.randn(co, generator=g) * 0.1, "running_var": torch.rand(co, generator=g) + 0.5}
+    ref = F.relu(F.batch_norm(F.conv_transpose2d(x, wt, None, stride=2, padding=1), bnp["running_mean"], bnp["running_var"],
+                              bnp["weight"], bnp["bias"], False, 0.0, 1e-5))
+    sd = {"d.weight": wt, **{"b." + k: v for k, v in bnp.items()}}
+    precision = "fp32" if mode == "fp32" else "bf16"
+    pb = _builder(B, precision, tc=(mode == "bf16tc"))
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    y = _deconv_bn_relu(pb, StateView(sd, "", torch.device(DEV)), pb.external(_nhwc(x, dt)), "d", "b")
+    if mode == "bf16tc":
+        assert all(o.flags & 8 for o in pb.ops)
+    _check(_nchw(_run(pb, y)), ref, precision, 1.5e-2 if precision == "bf16" else None)
+
+
+def _model(precision, arch="dla_34"):
     from centerpose_b200.config import default_cfg
     from centerpose_b200.model import create_model
     from oracle.init_recipe import conditioned_state_dict
-    cfg = default_cfg("dla_34")
+    cfg = default_cfg(arch)
     m = create_model(cfg.MODEL.NAME, cfg.MODEL.HEAD_CONV, cfg)
     sd = conditioned_state_dict(m.state_dict(), 317)
     m.load_state_dict(sd)
@@ -310,6 +333,23 @@ def test_dla34_512_end_to_end_vs_reference_golden():
     dets = multi_pose_decode(hm, wh, hps, reg=reg, hm_hp=hm_hp, hp_offset=hp_off, K=100, apply_sigmoid=True)
     rows, elems = match_rows(dets[0].cpu().numpy(), g["dets"][0], tol=1e-3, box_tol=2e-2)
     assert rows >= 0.9 and elems >= 0.97, (rows, elems)
+
+
+def test_res50_matches_reference_golden_and_oracle():
+    """BASELINE config 1/3 backbone: ResNet-50 + 3 deconvs (msra_resnet.py) + heads."""
+    from oracle import dla_ref
+    from oracle.init_recipe import synth_images
+    g = np.load(os.path.join(GOLD, "res50_128.npz"))
+    B, H, W = [int(v) for v in g["shape"]]
+    m, sd = _model("fp32", "res_50")
+    x = synth_images(B, H, W, 317)
+    _net_close(torch.cat(m(x.to(DEV)), dim=1).cpu().numpy(), g["maps"])
+    ref = torch.cat(dla_ref.forward(sd, x, arch="res_50"), dim=1)
+    for tc in (False, True):
+        m.set_precision("bf16", tc=tc)
+        got16 = torch.cat(m(x.to(DEV)), dim=1).cpu()
+        rel = ((got16 - ref).norm() / ref.norm()).item()
+        assert rel <= 3e-2, (tc, rel)
 
 
 def test_forward_rejects_cpu_and_training():

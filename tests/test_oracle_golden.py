@@ -113,3 +113,16 @@ def test_dla34_oracle_matches_golden(tag):
     ref = g["maps"]
     assert maps.shape == ref.shape
     assert np.abs(maps - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def test_res50_oracle_matches_golden():
+    g = np.load(os.path.join(GOLD, "res50_128.npz"))
+    B, H, W = [int(v) for v in g["shape"]]
+    from centerpose_b200.model import create_model
+    from centerpose_b200.config import default_cfg
+    cfg = default_cfg("res_50")
+    sd = conditioned_state_dict(create_model(cfg.MODEL.NAME, cfg.MODEL.HEAD_CONV, cfg).state_dict(), 317)
+    assert _sha(*[sd[k].numpy() for k in sorted(sd) if sd[k].is_floating_point()]) == str(g["sd_sha"])
+    x = synth_images(B, H, W, seed=317)
+    maps = torch.cat(dla_ref.forward(sd, x, arch="res_50"), dim=1).numpy()
+    assert np.abs(maps - g["maps"]).max() <= 1e-4 * np.abs(g["maps"]).max()
