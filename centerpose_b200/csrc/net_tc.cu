@@ -47,6 +47,7 @@ struct alignas(64) TcArgs {
   const float *dcn_om;            // (B,H,W,27) fp32: 18 offsets (dy,dx per tap) | 9 mask logits
   int H, W;
   int Hd, Wd, sy, sx, oy, ox;     // strided output mapping (dense ConvTranspose2d parity sub-convs)
+  int out_ch_off, out_ch_total;   // NCHW fp32 output: channel slice of dst
 };
 
 using namespace tc;
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
     const int et = threadIdx.x - 64;                     // 0..127
     const bool relu = a.flags & CPB200_FLAG_RELU;
     const bool out_f32 = a.flags & CPB200_FLAG_OUT_F32;
+    const bool out_nchw = a.flags & CPB200_FLAG_OUT_NCHW_F32;
     int acc = 0; uint32_t accphase = 0;
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
@@ -259,7 +261,15 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[acc][c * 16 + j];
-          if (out_f32) {
+          if (out_nchw) {
+            // head outputs: lanes are consecutive pixels of a tile row -> coalesced fp32 stores per channel
+            float *o = static_cast<float *>(a.dst) +
+                       (((size_t)n * a.out_ch_total + a.out_ch_off + nb) * a.Hd + (ho * a.sy + a.oy)) * a.Wd + (wo * a.sx + a.ox);
+            const size_t plane = (size_t)a.Hd * a.Wd;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nb + j < a.cout) o[j * plane] = relu ? fmaxf(f[j], 0.f) : f[j];
+          } else if (out_f32) {
             float *o = static_cast<float *>(a.dst) + pix * a.cout_store + nb;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
@@ -384,7 +394,6 @@ int tc_prepare_op(cpb200_op &op) {
               op.cin[0] % 64 || !op.aux || op.H != op.Ho || op.W != op.Wo))
     return fail(CPB200_ERR_ARG, "tc: DCN needs 3x3/s1/p1, one input with C %% 64 == 0 and the offset/mask tensor");
   if (op.act_dtype != CPB200_BF16) return fail(CPB200_ERR_ARG, "tc: bf16 activations required");
-  if (op.flags & CPB200_FLAG_OUT_NCHW_F32) return fail(CPB200_ERR_ARG, "tc: NCHW output not supported");
   if (op.stride < 1 || op.stride > 2) return fail(CPB200_ERR_ARG, "tc: stride %d", op.stride);
   if (op.Wo < 8 || op.Ho < 1) return fail(CPB200_ERR_ARG, "tc: output too small");
   EncodeTiledFn enc = get_encode();
@@ -415,7 +424,8 @@ int tc_prepare_op(cpb200_op &op) {
   a.Hd = op.Hd; a.Wd = op.Wd; a.sy = op.out_sy; a.sx = op.out_sx; a.oy = op.out_oy; a.ox = op.out_ox;
   a.n_tiles = (op.cout + BN - 1) / BN;
   a.cout = op.cout; a.cout_store = op.cout;
-  if (!(op.flags & CPB200_FLAG_OUT_F32) && (op.cout % 16)) { delete t; return fail(CPB200_ERR_ARG, "tc: bf16 output needs cout %% 16 == 0"); }
+  if (!(op.flags & (CPB200_FLAG_OUT_F32 | CPB200_FLAG_OUT_NCHW_F32)) && (op.cout % 16)) { delete t; return fail(CPB200_ERR_ARG, "tc: bf16 output needs cout %% 16 == 0"); }
+  a.out_ch_off = op.out_ch_off; a.out_ch_total = op.out_ch_total;
   a.total_tiles = op.B * a.tiles_h * a.tiles_w * a.n_tiles;
   a.dst = op.dst; a.res = op.res; a.bias = op.bias; a.flags = op.flags;
   const size_t a_bytes = (size_t)TILE_M * bk * 2, b_bytes = ((size_t)BN * bk * 2 + 1023) / 1024 * 1024;

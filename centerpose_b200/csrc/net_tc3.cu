@@ -140,25 +140,37 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
         mbar_wait(afull0 + 8 * sa, pha);
         tc_fence_after();
         const uint32_t halo = a_base + sa * a.a_stage_bytes;
-        for (int tap = 0; tap < 9; ++tap) {
-          uint32_t bsm;
-          if (a.b_resident) {
-            bsm = b_base + (sl * 9 + tap) * a.b_stage_bytes;
-          } else {
-            mbar_wait(bfull0 + 8 * sb, phb);
-            tc_fence_after();
-            bsm = b_base + sb * a.b_stage_bytes;
-          }
+        if (a.b_resident) {
+          // resident weights: nothing to wait for inside the slab — one lane issues all 9 x ksteps MMAs
+          // back to back; descriptors differ only in the 14-bit start-address field (adds on the low word)
           if (lane == 0) {
-            const int r = tap / 3, s = tap - 3 * r;
-            const uint64_t ad = desc_sbo(halo + (r * HW_ + s) * pix_bytes, HW_ * pix_bytes, a.swizzle_bits);
-            const uint64_t bd = desc_sbo(bsm, 8 * pix_bytes, a.swizzle_bits);
-            for (int k = 0; k < ksteps; ++k)
-              umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
-            if (!a.b_resident) umma_commit(bempty0 + 8 * sb);
+            const uint64_t ad0 = desc_sbo(halo, HW_ * pix_bytes, a.swizzle_bits);
+            const uint64_t bd0 = desc_sbo(b_base + sl * 9 * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
+            const uint32_t bstep = a.b_stage_bytes >> 4, pstep = pix_bytes >> 4;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint64_t ad = ad0 + (uint32_t)((tap / 3) * HW_ + (tap % 3)) * pstep;
+              const uint64_t bd = bd0 + (uint32_t)tap * bstep;
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            }
           }
           __syncwarp();
-          if (!a.b_resident) { if (++sb == a.nb) { sb = 0; phb ^= 1; } }
+        } else {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bfull0 + 8 * sb, phb);
+            tc_fence_after();
+            if (lane == 0) {
+              const int r = tap / 3, s = tap - 3 * r;
+              const uint64_t ad = desc_sbo(halo + (r * HW_ + s) * pix_bytes, HW_ * pix_bytes, a.swizzle_bits);
+              const uint64_t bd = desc_sbo(b_base + sb * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              umma_commit(bempty0 + 8 * sb);
+            }
+            __syncwarp();
+            if (++sb == a.nb) { sb = 0; phb ^= 1; }
+          }
         }
         if (lane == 0) {
           umma_commit(aempty0 + 8 * sa);

@@ -151,9 +151,9 @@ class PlanBuilder:
         return self._dev(p, torch.bfloat16)
 
     def _tc_ok(self, srcs, co, kh, kw, stride, out, out_map, Wo):
-        return (self.use_tc and out != "nchw" and stride in (1, 2) and Wo >= 8
+        return (self.use_tc and stride in (1, 2) and Wo >= 8
                 and all(s.C % 16 == 0 and s.kind == "act" for s in srcs)
-                and (co % 16 == 0 or out == "f32") and kh * kw <= 49)
+                and (co % 16 == 0 or out in ("f32", "nchw")) and kh * kw <= 49)
 
     # ---- ops -------------------------------------------------------------------------------
     def stem(self, x: Sym, w, b, k, stride, pad, relu=True):

@@ -56,6 +56,9 @@ TC_CASES = [
     ([512, 512, 256], 512, 1, 1, 8, 8, False, True, "act"),         # TW=8 tiles
     ([128], 27, 3, 1, 24, 24, False, False, "f32"),      # DCN offset/mask conv: fp32 out, cout 27
     ([64], 256, 3, 1, 32, 32, False, True, "act"),       # head 3x3
+    ([256], 34, 1, 1, 32, 32, False, False, "nchw"),     # head 1x1 -> NCHW fp32 logits (hps)
+    ([256], 1, 1, 1, 24, 40, False, False, "nchw"),      # head 1x1 (hm), partial tiles
+    ([64], 17, 1, 1, 16, 16, False, True, "nchw"),
 ]
 
 
@@ -79,6 +82,18 @@ def test_conv_tensor_core_path(cins, cout, k, stride, H, W, res, relu, out):
     pb = _builder(B, "bf16", tc=True)
     sx = [pb.external(_nhwc(x, torch.bfloat16)) for x in xs]
     sr = pb.external(_nhwc(r, torch.bfloat16)) if res else None
+    if out == "nchw":
+        dst = pb.output(cout + 3, ref.shape[2], ref.shape[3], "o")
+        buf = torch.zeros(B, cout + 3, ref.shape[2], ref.shape[3], device=DEV)
+        pb.conv(sx, w.to(DEV), b.to(DEV), stride=stride, pad=pad, relu=relu, out="nchw", dst=dst, ch_off=2)
+        assert pb.ops[-1].flags & 8
+        plan = pb.build(); plan.bind(torch.zeros(1, device=DEV), {"o": buf})
+        plan.run(torch.cuda.current_stream().cuda_stream); torch.cuda.synchronize()
+        assert buf[:, :2].abs().max().item() == 0 and buf[:, cout + 2:].abs().max().item() == 0
+        got = buf[:, 2:cout + 2].cpu()
+        err = (got - ref).abs().max().item()
+        assert err <= 2e-3 * ref.abs().max().item(), (err, ref.abs().max().item())   # fp32 out: only accumulation order
+        return
     y = pb.conv(sx, w.to(DEV), b.to(DEV), stride=stride, pad=pad, relu=relu, res=sr, out=out)
     assert pb.ops[-1].flags & 8, "op was not routed to the tensor-core path"
     got = _nchw(_run(pb, y))
