@@ -13,7 +13,8 @@
 // Grid: one CTA per (image, heat-map channel) = B*(1+J) CTAs of 256 threads.
 //   phase 1  each CTA scans its H*W map: thread = (row strip, 4-column group), rolling
 //            3-row window in registers, horizontal neighbours by warp shuffle; local maxima
-//            above the channel's floor are compacted into shared memory (warp-ballot).
+//            above the channel's floor go to per-warp candidate segments in shared memory
+//            (ballot + popc ranking, no atomics), compacted afterwards.
 //   phase 2  exact top-K SET of the candidates by adaptive bucket select (256 linear buckets over
 //            the candidates' float-bit range; the boundary bucket is resolved by rank counting on
 //            64-bit (value,~index) keys); only the centre channel orders its K rows (rank
@@ -60,6 +61,7 @@ struct Smem {
   int hc[MAXK];
   unsigned long long red[8];
   unsigned kmin, kmax;
+  int wcnt[8], wbase[8];
   int count, nsel, nbnd, digit, need, flags;
   unsigned todo_mask;
 };
@@ -71,16 +73,23 @@ __device__ __forceinline__ float act(float v, bool sig) {
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
 // ---- phase 1, vector path (W % 4 == 0, 16-byte aligned map) -----------------------------
-// Each thread owns a 4-column group and walks down a strip of rows with a rolling 3-row window.
-// Per row it only sets bits (peak && value > floor) in a 64-bit mask (16 rows x 4 columns); the
-// rare set bits are turned into (value, index) candidates afterwards with warp-aggregated atomics.
+// Each thread owns a 4-column group and walks down a strip of rows with a rolling 3-row window
+// (one float4 load per row, horizontal neighbours by shuffle).  Peaks above the floor are appended to
+// the WARP's private candidate segment (ballot + popc ranking, no atomics, deterministic order);
+// segments are compacted after the scan.
+constexpr int SEG = CAP / (TPB / 32);      // 512 candidates per warp
+
 __device__ void scan_vec(Smem &s, const float *__restrict__ map, int H, int W, bool sig, float floorv) {
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned lt = (1u << lane) - 1u;
   const int XG = W >> 2;
   int S = TPB / XG; if (S < 1) S = 1; if (S > H) S = H;
   const int RS = cpb::ceil_div(H, S);
   const int U = XG * S;
   const float NINF = -INFINITY;
+  float *segv = s.cval + wid * SEG;
+  int *segi = s.cidx + wid * SEG;
+  int wcount = 0;                                            // warp-uniform
   for (int u0 = 0; u0 < U; u0 += TPB) {
     const int u = u0 + tid;
     const bool on = u < U;
@@ -111,53 +120,72 @@ __device__ void scan_vec(Smem &s, const float *__restrict__ map, int H, int W, b
     float4 vcur, hprev, hcur, tmp;
     load_row(r0 - 1, tmp, hprev);
     load_row(r0, vcur, hcur);
-    for (int i0 = 0; i0 < RS; i0 += 16) {
-      unsigned long long bits = 0ull;
-#pragma unroll 1
-      for (int i1 = 0; i1 < 16; i1 += 4) {
-        float4 nv[4], nh[4];
+    for (int i0 = 0; i0 < RS; i0 += 4) {
+      float4 nv[4], nh[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int y = r0 + i0 + i1 + q + 1;
-          load_row((y <= r1) ? y : -1, nv[q], nh[q]);          // row r1 is the strip's lower halo
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int y = r0 + i0 + i1 + q;
-          const float mx = max3(hprev.x, hcur.x, nh[q].x), my = max3(hprev.y, hcur.y, nh[q].y);
-          const float mz = max3(hprev.z, hcur.z, nh[q].z), mw = max3(hprev.w, hcur.w, nh[q].w);
-          unsigned b = 0;
-          b |= (vcur.x == mx && vcur.x > floorv) ? 1u : 0u;
-          b |= (vcur.y == my && vcur.y > floorv) ? 2u : 0u;
-          b |= (vcur.z == mz && vcur.z > floorv) ? 4u : 0u;
-          b |= (vcur.w == mw && vcur.w > floorv) ? 8u : 0u;
-          if (!(on && y < r1)) b = 0;
-          bits |= (unsigned long long)b << (4 * (i1 + q));
-          hprev = hcur; hcur = nh[q]; vcur = nv[q];
-        }
+      for (int q = 0; q < 4; ++q) {
+        const int y = r0 + i0 + q + 1;
+        load_row((y <= r1) ? y : -1, nv[q], nh[q]);            // row r1 is the strip's lower halo
       }
-      // deferred extraction of this 16-row batch (warp-uniform loop, aggregated atomics)
-      while (__any_sync(FULL, bits != 0ull)) {
-        const bool has = bits != 0ull;
-        int idx = 0; float val = 0.f;
-        if (has) {
-          const int bit = __ffsll((long long)bits) - 1;
-          bits &= bits - 1ull;
-          idx = (r0 + i0 + (bit >> 2)) * W + x0 + (bit & 3);
-          val = act(__ldg(map + idx), sig);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int y = r0 + i0 + q;
+        const float mx = max3(hprev.x, hcur.x, nh[q].x), my = max3(hprev.y, hcur.y, nh[q].y);
+        const float mz = max3(hprev.z, hcur.z, nh[q].z), mw = max3(hprev.w, hcur.w, nh[q].w);
+        unsigned b = 0;
+        b |= (vcur.x == mx && vcur.x > floorv) ? 1u : 0u;
+        b |= (vcur.y == my && vcur.y > floorv) ? 2u : 0u;
+        b |= (vcur.z == mz && vcur.z > floorv) ? 4u : 0u;
+        b |= (vcur.w == mw && vcur.w > floorv) ? 8u : 0u;
+        if (!(on && y < r1)) b = 0;
+        unsigned m = __ballot_sync(FULL, b != 0);
+        while (m) {                                            // 1 pass; a 2nd only if a float4 holds 2 peaks
+          if (b) {
+            const int k = __ffs(b) - 1;
+            b &= b - 1;
+            const float val = (k == 0) ? vcur.x : (k == 1) ? vcur.y : (k == 2) ? vcur.z : vcur.w;
+            const int pos = wcount + __popc(m & lt);
+            if (pos < SEG) { segv[pos] = val; segi[pos] = y * W + x0 + k; }
+          }
+          wcount += __popc(m);
+          m = __ballot_sync(FULL, b != 0);
         }
-        const unsigned m = __ballot_sync(FULL, has);
-        const int leader = __ffs(m) - 1;
-        int basep = 0;
-        if (lane == leader) basep = atomicAdd(&s.count, __popc(m));
-        basep = __shfl_sync(FULL, basep, leader);
-        if (has) {
-          const int pos = basep + __popc(m & ((1u << lane) - 1u));
-          if (pos < CAP) { s.cval[pos] = val; s.cidx[pos] = idx; }
-        }
+        hprev = hcur; hcur = nh[q]; vcur = nv[q];
       }
     }
   }
+  if (lane == 0) s.wcnt[wid] = wcount;
+}
+
+// Compact the per-warp segments [wid*SEG, wid*SEG + wcnt) into cval/cidx[0..n).  Returns n, or -1 when
+// a segment overflowed (caller takes the exact slow path).
+__device__ int compact_segments(Smem &s) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  __syncthreads();
+  int base = 0, total = 0; bool over = false;
+#pragma unroll
+  for (int w = 0; w < TPB / 32; ++w) {
+    const int c = s.wcnt[w];
+    over |= c > SEG;
+    if (w < wid) base += c;
+    total += c;
+  }
+  if (over) return -1;
+  const int mine = s.wcnt[wid];
+  float rv[SEG / 32]; int ri[SEG / 32];
+#pragma unroll
+  for (int j = 0; j < SEG / 32; ++j) {
+    const int e = j * 32 + lane;
+    if (e < mine) { rv[j] = s.cval[wid * SEG + e]; ri[j] = s.cidx[wid * SEG + e]; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < SEG / 32; ++j) {
+    const int e = j * 32 + lane;
+    if (e < mine) { s.cval[base + e] = rv[j]; s.cidx[base + e] = ri[j]; }
+  }
+  __syncthreads();
+  return total;
 }
 
 // ---- post-NMS value of one cell straight from global memory (generic / slow paths) -------
@@ -182,24 +210,25 @@ __device__ __forceinline__ float nms_value(const float *__restrict__ map, int H,
 
 // ---- phase 1, scalar path (any W / alignment) -------------------------------------------
 __device__ void scan_scalar(Smem &s, const float *__restrict__ map, int H, int W, bool sig, float floorv) {
-  const int N = H * W, lane = threadIdx.x & 31;
+  const int N = H * W, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
   const int iters = cpb::ceil_div(N, TPB);
+  float *segv = s.cval + wid * SEG;
+  int *segi = s.cidx + wid * SEG;
+  int wcount = 0;
   for (int it = 0; it < iters; ++it) {
     const int cell = it * TPB + threadIdx.x;
     bool pk = false; float v = 0.f;
     if (cell < N) v = nms_value(map, H, W, cell / W, cell % W, sig, &pk);
     const bool has = pk && v > floorv;
     const unsigned m = __ballot_sync(FULL, has);
-    if (m == 0) continue;
-    const int leader = __ffs(m) - 1;
-    int basep = 0;
-    if (lane == leader) basep = atomicAdd(&s.count, __popc(m));
-    basep = __shfl_sync(FULL, basep, leader);
     if (has) {
-      const int pos = basep + __popc(m & ((1u << lane) - 1u));
-      if (pos < CAP) { s.cval[pos] = v; s.cidx[pos] = cell; }
+      const int pos = wcount + __popc(m & lt);
+      if (pos < SEG) { segv[pos] = v; segi[pos] = cell; }
     }
+    wcount += __popc(m);
   }
+  if (lane == 0) s.wcnt[wid] = wcount;
 }
 
 __device__ __forceinline__ unsigned long long make_key(float v, int idx) {
@@ -435,6 +464,7 @@ __device__ void group_joint(Smem &s, const DecodeParams &p, int b, int j) {
     const int c0 = half ? hk : 0, c1 = half ? K : hk;
     // nearest candidate on SQUARED distance (monotone in the reference's sqrt); exact ties ->
     // the reference's first-minimum over its score-sorted list = higher score, then lower index
+#pragma unroll 4
     for (int c = c0; c < c1; ++c) {                                                 // :286-289
       const float2 g = s.gxy[c];
       const float dx = __fsub_rn(kx, g.x), dy = __fsub_rn(ky, g.y);
@@ -487,11 +517,11 @@ __global__ void __launch_bounds__(TPB) decode_kernel(const DecodeParams p) {
   const bool vec_ok = ((p.W & 3) == 0) && ((reinterpret_cast<uintptr_t>(map) & 15) == 0);
   if (vec_ok) scan_vec(s, map, p.H, p.W, sig, floorv);
   else scan_scalar(s, map, p.H, p.W, sig, floorv);
-  __syncthreads();
+  const int ncand = compact_segments(s);
 
   bool done = false;
-  if (s.count <= CAP) {
-    done = select_set(s, s.count, p.K);
+  if (ncand >= 0) {
+    done = select_set(s, ncand, p.K);
     if (done) done = finalize_list(s, map, p.H, p.W, sig, p.K, is_centre);
   }
   if (!done) {

@@ -109,6 +109,44 @@ __global__ void __launch_bounds__(128, 1) probe_halo_kernel(const __grid_constan
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64) : "memory");
 }
 
+// ---- TMA box-throughput probe: every CTA streams boxes of one shape through an N-deep smem ring ----
+struct alignas(64) TmaProbeArgs {
+  CUtensorMap map;
+  int tiles_w, tiles_h, nimg, total, stages, box_w, box_h, step_w, step_h;
+  unsigned bytes, stage_bytes;
+};
+
+__global__ void __launch_bounds__(64, 1) probe_tma_kernel(const __grid_constant__ TmaProbeArgs a) {
+  extern __shared__ __align__(1024) uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[32];
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[16]);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {                 // producer
+    int st = 0; uint32_t ph = 0;
+    for (int t = blockIdx.x; t < a.total; t += gridDim.x) {
+      const int tw = t % a.tiles_w, th = (t / a.tiles_w) % a.tiles_h, n = t / (a.tiles_w * a.tiles_h);
+      mbar_wait(empty0 + 8 * st, ph ^ 1);
+      mbar_expect_tx(full0 + 8 * st, a.bytes);
+      asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                   ::"r"(base + st * a.stage_bytes), "l"(reinterpret_cast<uint64_t>(&a.map)), "r"(full0 + 8 * st),
+                     "r"(0), "r"(tw * a.step_w - 1), "r"(th * a.step_h - 1), "r"(n) : "memory");
+      if (++st == a.stages) { st = 0; ph ^= 1; }
+    }
+  } else if (threadIdx.x == 32) {         // consumer: release the slot as soon as the bytes landed
+    int st = 0; uint32_t ph = 0;
+    for (int t = blockIdx.x; t < a.total; t += gridDim.x) {
+      mbar_wait(full0 + 8 * st, ph);
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * st) : "memory");
+      if (++st == a.stages) { st = 0; ph ^= 1; }
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -148,4 +186,33 @@ extern "C" int cpb200_probe_halo(const void *x, const void *w, float *out, int v
   CPB_CUDA(cudaFuncSetAttribute(probe_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   probe_halo_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(a);
   return cpb::check_launch("probe_halo_kernel");
+}
+
+// Streams (C,W,H,N) bf16 through TMA boxes {C, box_w, box_h, 1} stepping (step_w, step_h); returns after enqueue.
+extern "C" int cpb200_probe_tma(const void *x, int C, int W, int H, int N, int box_w, int box_h, int step_w, int step_h,
+                                int stages, void *stream) {
+  void *p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+    return cpb::fail(CPB200_ERR_STATE, "probe: cuTensorMapEncodeTiled unavailable");
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(p);
+  TmaProbeArgs a;
+  memset(&a, 0, sizeof(a));
+  const CUtensorMapSwizzle sw = C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  if (enc(&a.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(x), dims, strides, box, es,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return cpb::fail(CPB200_ERR_CUDA, "probe: encode failed");
+  a.tiles_w = (W + step_w - 1) / step_w; a.tiles_h = (H + step_h - 1) / step_h; a.nimg = N;
+  a.total = a.tiles_w * a.tiles_h * N; a.stages = stages; a.box_w = box_w; a.box_h = box_h; a.step_w = step_w; a.step_h = step_h;
+  a.bytes = (unsigned)(C * 2 * box_w * box_h); a.stage_bytes = (a.bytes + 1023u) & ~1023u;
+  const size_t smem = (size_t)stages * a.stage_bytes + 1024;
+  if (stages > 16 || smem > 200 * 1024) return cpb::fail(CPB200_ERR_ARG, "probe: ring too large");
+  CPB_CUDA(cudaFuncSetAttribute(probe_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, nsm = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  probe_tma_kernel<<<nsm, 64, smem, static_cast<cudaStream_t>(stream)>>>(a);
+  return cpb::check_launch("probe_tma_kernel");
 }

@@ -148,6 +148,10 @@ size_t cpb200_sizeof_op(void);
  * [tap][cout][cin], out (128,64) fp32 with row = th*8 + tw.  variant 0/1 = descriptor base_offset 0 /
  * (start>>7)&7.  See centerpose_b200/csrc/probe.cu and tools/halo_probe.py. */
 int cpb200_probe_halo(const void *x, const void *w, float *out, int variant, void *stream);
+/* TMA box-throughput probe: streams a (N,H,W,C) bf16 tensor through 4-D boxes {C,box_w,box_h,1} stepping
+ * (step_w,step_h) with an N-deep smem ring on every SM (tools/tma_probe.py). */
+int cpb200_probe_tma(const void *x, int C, int W, int H, int N, int box_w, int box_h, int step_w, int step_h,
+                     int stages, void *stream);
 
 #ifdef __cplusplus
 }
