@@ -36,7 +36,7 @@ struct alignas(64) TcArgs {
   int B, Ho, Wo;
   int TH, TW, tiles_h, tiles_w, n_tiles;
   int cout, cout_store;       // cout_store: channel pitch of dst/res
-  int BK, stages, total_tiles;
+  int BK, stages, total_tiles, nacc;
   void *dst;
   const void *res;
   const float *bias;
@@ -54,7 +54,7 @@ using namespace tc;
 
 constexpr int DCN_THREADS = 448;   // + 8 gather-producer warps
 
-struct __align__(16) DcnPrm { int off[4]; float wt[4]; };
+struct __align__(16) DcnPrm { int off[4]; uint32_t wt[4]; };   // element offsets, packed bf16x2 (w,w) corner weights
 
 template <int BN, bool DCN>
 __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
@@ -63,21 +63,22 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = TILE_M * a.BK * 2, b_bytes = BN * a.BK * 2;
   const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
-  __shared__ __align__(8) uint64_t bars[2 * 8 + 4];
+  __shared__ __align__(8) uint64_t bars[2 * 8 + 16];
   __shared__ uint32_t s_tmem;
   __shared__ float s_bias[2][BN];
-  __shared__ DcnPrm s_prm[DCN ? 8 : 1][DCN ? 16 : 1];
+  __shared__ DcnPrm s_prm[DCN ? 8 : 1][DCN ? 9 : 1][DCN ? 16 : 1];
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
-  const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[18]);
+  const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[24]);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  const uint32_t need_cols = (uint32_t)a.nacc * BN;
+  const uint32_t TMEM_COLS = need_cols <= 32 ? 32u : need_cols <= 64 ? 64u : need_cols <= 128 ? 128u : need_cols <= 256 ? 256u : 512u;
 
   if (warp == 0 && lane == 0) {
     if (!DCN) for (int s = 0; s < a.nsrc; ++s) tmap_prefetch(&a.amap[s]);
     tmap_prefetch(&a.bmap);
     for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, DCN ? 1 + 256 : 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
+    for (int s = 0; s < 8; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -153,81 +154,109 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
         __syncwarp();
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
-      if (++acc == 2) { acc = 0; accphase ^= 1; }
+      if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
     }
   } else if (DCN && warp >= 6) {
     // =============================== DCN gather producers (warps 6..13) ===============================
     // A[row = pixel][k = channel] of tap t is  sigmoid(mask_t) * bilinear(x, p + tap_t + offset_t)
-    // (dcn_v2_im2col_cuda.cu:25-54,125-195), blended in fp32, rounded once to bf16 and stored straight
-    // into the 128B-swizzled K-major tile the UMMA descriptor reads (16-byte chunk j of row r lives at
-    // chunk j ^ (r & 7)).  8 warps x 16 rows; lane = (row-in-group-of-4, 16-byte chunk) so a warp reads 4
-    // full 128-byte lines per corner load; all 16 corner loads of a stage are issued before the first
-    // use (64 KB in flight per SM) — the gather is latency-bound otherwise.
-    const int gw = warp - 6;                               // 0..7, rows [16*gw, 16*gw+16)
+    // (dcn_v2_im2col_cuda.cu:25-54,125-195), rounded to bf16 and stored straight into the 128B-swizzled
+    // K-major tile the UMMA descriptor reads (16-byte chunk j of row r lives at chunk j ^ (r & 7)).
+    // 8 warps x 16 rows.  Per tile each warp first turns the 27 offset/mask values of its 16 pixels into
+    // (4 corner offsets, 4 packed corner weights) for all 9 taps (one round trip to global memory instead
+    // of one per tap); the per-stage work is then software-pipelined in two half batches of 8 corner loads:
+    // the loads of the next half are always in flight while the current half is blended.
+    const int gw = warp - 6;                               // rows [16*gw, 16*gw+16)
     int stage = 0; uint32_t phase = 0;
     const int Cin = a.cin[0];
+    const int slabs = Cin >> 6;
+    const int nk = 9 * slabs;
+    const int chunk = lane & 7, rsub = lane >> 3;
+    const __nv_bfloat16 *srcc = a.dcn_src + chunk * 8;
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
-      const int rp = gw * 16 + (lane & 15);                // the pixel whose sampling parameters I compute
-      const int ho = h0 + rp / a.TW, wo = w0 + rp % a.TW;
-      const bool okp = ho < a.Ho && wo < a.Wo;
-      const float *om = a.dcn_om + (((size_t)n * a.H + ho) * a.W + wo) * 27;
-      for (int tap = 0; tap < 9; ++tap) {
-        DcnPrm pr;
+      {   // ---- sampling parameters of this warp's 16 pixels, all 9 taps ----
+        const int rp = gw * 16 + (lane & 15);
+        const int ho = h0 + rp / a.TW, wo = w0 + rp % a.TW;
+        const bool okp = ho < a.Ho && wo < a.Wo;
+        const float *om = a.dcn_om + (((size_t)n * a.H + ho) * a.W + wo) * 27;
+        const int tap0 = (lane < 16) ? 0 : 5, ntap = (lane < 16) ? 5 : 4;
+        float oh[5], ow[5], ml[5];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { pr.off[c] = 0; pr.wt[c] = 0.f; }
-        if (okp) {
-          const float oh = __ldg(om + 2 * tap), ow = __ldg(om + 2 * tap + 1);
-          const float mk = 1.0f / (1.0f + __expf(-__ldg(om + 18 + tap)));
-          const float h_im = (float)(ho - 1 + tap / 3) + oh, w_im = (float)(wo - 1 + tap % 3) + ow;
-          if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {
-            const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-            const int h_high = h_low + 1, w_high = w_low + 1;
-            const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
-            const int rowb = n * a.H;
-            if (h_low >= 0 && w_low >= 0) { pr.off[0] = (rowb + h_low) * a.W + w_low; pr.wt[0] = hh * hw * mk; }
-            if (h_low >= 0 && w_high <= a.W - 1) { pr.off[1] = (rowb + h_low) * a.W + w_high; pr.wt[1] = hh * lw * mk; }
-            if (h_high <= a.H - 1 && w_low >= 0) { pr.off[2] = (rowb + h_high) * a.W + w_low; pr.wt[2] = lh * hw * mk; }
-            if (h_high <= a.H - 1 && w_high <= a.W - 1) { pr.off[3] = (rowb + h_high) * a.W + w_high; pr.wt[3] = lh * lw * mk; }
-          }
+        for (int i = 0; i < 5; ++i) {
+          const int tap = tap0 + i;
+          const bool ld = okp && i < ntap;
+          oh[i] = ld ? __ldg(om + 2 * tap) : 0.f; ow[i] = ld ? __ldg(om + 2 * tap + 1) : 0.f; ml[i] = ld ? __ldg(om + 18 + tap) : 0.f;
         }
-        __syncwarp();
-        if (lane < 16) s_prm[gw][lane] = pr;
-        __syncwarp();
-        const int chunk = lane & 7;
-        DcnPrm q[4];
+        __syncwarp();                                      // previous tile's readers are done with s_prm
 #pragma unroll
-        for (int it = 0; it < 4; ++it) q[it] = s_prm[gw][it * 4 + (lane >> 3)];
-        for (int c0 = 0; c0 < Cin; c0 += 64) {
-          uint4 v[4][4];
+        for (int i = 0; i < 5; ++i) {
+          if (i < ntap) {
+            const int tap = tap0 + i;
+            DcnPrm pr;
 #pragma unroll
-          for (int it = 0; it < 4; ++it)
-#pragma unroll
-            for (int c = 0; c < 4; ++c)       // invalid corners have weight 0 and offset 0 (a safe address)
-              v[it][c] = __ldg(reinterpret_cast<const uint4 *>(a.dcn_src + (size_t)q[it].off[c] * Cin + c0 + chunk * 8));
-          mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          const uint32_t sa = smem_base + stage * stage_bytes;
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            // packed bf16x2 blend: 4 corners x 4 pairs = 16 HFMA2 per 16-byte chunk (the A operand is
-            // bf16 anyway; fp32 blending cost 64 instructions per chunk and made the gather issue-bound)
-            __nv_bfloat162 acc2[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const __nv_bfloat162 w2 = __float2bfloat162_rn(q[it].wt[c]);
-              const __nv_bfloat162 *vv = reinterpret_cast<const __nv_bfloat162 *>(&v[it][c]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) acc2[j] = (c == 0) ? __hmul2(w2, vv[j]) : __hfma2(w2, vv[j], acc2[j]);
+            for (int c = 0; c < 4; ++c) { pr.off[c] = 0; pr.wt[c] = 0u; }
+            if (okp) {
+              const float mk = 1.0f / (1.0f + __expf(-ml[i]));
+              const float h_im = (float)(ho - 1 + tap / 3) + oh[i], w_im = (float)(wo - 1 + tap % 3) + ow[i];
+              if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {
+                const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                const int h_high = h_low + 1, w_high = w_low + 1;
+                const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+                const int rowb = n * a.H;
+                auto pk = [](float w) { __nv_bfloat162 b = __float2bfloat162_rn(w); return *reinterpret_cast<uint32_t *>(&b); };
+                if (h_low >= 0 && w_low >= 0) { pr.off[0] = ((rowb + h_low) * a.W + w_low) * Cin; pr.wt[0] = pk(hh * hw * mk); }
+                if (h_low >= 0 && w_high <= a.W - 1) { pr.off[1] = ((rowb + h_low) * a.W + w_high) * Cin; pr.wt[1] = pk(hh * lw * mk); }
+                if (h_high <= a.H - 1 && w_low >= 0) { pr.off[2] = ((rowb + h_high) * a.W + w_low) * Cin; pr.wt[2] = pk(lh * hw * mk); }
+                if (h_high <= a.H - 1 && w_high <= a.W - 1) { pr.off[3] = ((rowb + h_high) * a.W + w_high) * Cin; pr.wt[3] = pk(lh * lw * mk); }
+              }
             }
-            const uint4 o = *reinterpret_cast<const uint4 *>(acc2);
-            const int row = gw * 16 + it * 4 + (lane >> 3);
-            const uint32_t dst = sa + row * 128 + ((chunk ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+            s_prm[gw][tap][lane & 15] = pr;
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(full0 + 8 * stage);
-          if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+      }
+      uint4 vA[2][4], vB[2][4];
+      uint32_t wA[2][4], wB[2][4];
+      auto issue = [&](int k, int half, uint4 (&v)[2][4], uint32_t (&w)[2][4]) {
+        const int tap = k / slabs, c0 = (k - tap * slabs) << 6;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const DcnPrm q = s_prm[gw][tap][(half * 2 + i) * 4 + rsub];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {       // invalid corners: weight 0, offset 0 (a safe address)
+            v[i][c] = __ldg(reinterpret_cast<const uint4 *>(srcc + (size_t)(unsigned)q.off[c] + c0));
+            w[i][c] = q.wt[c];
+          }
+        }
+      };
+      auto blend_store = [&](uint32_t sa, int half, const uint4 (&v)[2][4], const uint32_t (&w)[2][4]) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          __nv_bfloat162 acc2[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const __nv_bfloat162 w2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[i][c]);
+            const __nv_bfloat162 *vv = reinterpret_cast<const __nv_bfloat162 *>(&v[i][c]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc2[j] = (c == 0) ? __hmul2(w2, vv[j]) : __hfma2(w2, vv[j], acc2[j]);
+          }
+          const uint4 o = *reinterpret_cast<const uint4 *>(acc2);
+          const int row = gw * 16 + (half * 2 + i) * 4 + rsub;
+          const uint32_t dst = sa + row * 128 + ((chunk ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+        }
+      };
+      issue(0, 0, vA, wA);
+      for (int k = 0; k < nk; ++k) {
+        issue(k, 1, vB, wB);
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const uint32_t sa = smem_base + stage * stage_bytes;
+        blend_store(sa, 0, vA, wA);
+        if (k + 1 < nk) issue(k + 1, 0, vA, wA);
+        blend_store(sa, 1, vB, wB);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(full0 + 8 * stage);
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -242,7 +271,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
       const int n0 = nt * BN;
-      for (int i = et; i < BN; i += 128) s_bias[acc][i] = (a.bias && n0 + i < a.cout) ? __ldg(a.bias + n0 + i) : 0.f;
+      for (int i = et; i < BN; i += 128) s_bias[acc & 1][i] = (a.bias && n0 + i < a.cout) ? __ldg(a.bias + n0 + i) : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(tfull0 + 8 * acc, accphase);
       tc_fence_after();
@@ -260,7 +289,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
         if (ok && nb < a.cout) {
           float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[acc][c * 16 + j];
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[acc & 1][c * 16 + j];
           if (out_nchw) {
             // head outputs: lanes are consecutive pixels of a tile row -> coalesced fp32 stores per channel
             float *o = static_cast<float *>(a.dst) +
@@ -306,7 +335,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-      if (++acc == 2) { acc = 0; accphase ^= 1; }
+      if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
     }
   }
 
@@ -427,6 +456,7 @@ int tc_prepare_op(cpb200_op &op) {
   if (!(op.flags & (CPB200_FLAG_OUT_F32 | CPB200_FLAG_OUT_NCHW_F32)) && (op.cout % 16)) { delete t; return fail(CPB200_ERR_ARG, "tc: bf16 output needs cout %% 16 == 0"); }
   a.out_ch_off = op.out_ch_off; a.out_ch_total = op.out_ch_total;
   a.total_tiles = op.B * a.tiles_h * a.tiles_w * a.n_tiles;
+  a.nacc = 512 / BN > 8 ? 8 : 512 / BN;      // TMEM accumulator stages
   a.dst = op.dst; a.res = op.res; a.bias = op.bias; a.flags = op.flags;
   const size_t a_bytes = (size_t)TILE_M * bk * 2, b_bytes = ((size_t)BN * bk * 2 + 1023) / 1024 * 1024;
   const size_t budget = 200 * 1024;

@@ -32,7 +32,7 @@ struct alignas(64) C3Args {
   int cin, slabs, BK;
   int B, Ho, Wo, tiles_h, tiles_w, n_tiles, total_tiles;
   int cout, cout_store;
-  int na, nb, b_resident;
+  int na, nb, b_resident, nacc;
   unsigned a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
   void *dst;
   const void *res;
@@ -55,22 +55,23 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base, b_base = smem_base + a.na * a.a_stage_bytes;
-  __shared__ __align__(8) uint64_t bars[2 * MAX_NA + 2 * MAX_NB + 1 + 4];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_NA + 2 * MAX_NB + 1 + 16];
   __shared__ uint32_t s_tmem;
   __shared__ float s_bias[2][BN];
   const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[MAX_NA]);
   const uint32_t bfull0 = smem_u32(&bars[2 * MAX_NA]), bempty0 = smem_u32(&bars[2 * MAX_NA + MAX_NB]);
   const uint32_t ball = smem_u32(&bars[2 * MAX_NA + 2 * MAX_NB]);
-  const uint32_t tfull0 = ball + 8, tempty0 = ball + 24;
+  const uint32_t tfull0 = ball + 8, tempty0 = ball + 8 + 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  const uint32_t need_cols = (uint32_t)a.nacc * BN;
+  const uint32_t TMEM_COLS = need_cols <= 32 ? 32u : need_cols <= 64 ? 64u : need_cols <= 128 ? 128u : need_cols <= 256 ? 256u : 512u;
 
   if (warp == 0 && lane == 0) {
     tmap_prefetch(&a.amap); tmap_prefetch(&a.bmap);
     for (int s = 0; s < MAX_NA; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
     for (int s = 0; s < MAX_NB; ++s) { mbar_init(bfull0 + 8 * s, 1); mbar_init(bempty0 + 8 * s, 1); }
     mbar_init(ball, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
+    for (int s = 0; s < 8; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
         __syncwarp();
         if (++sa == a.na) { sa = 0; pha ^= 1; }
       }
-      if (++acc == 2) { acc = 0; accphase ^= 1; }
+      if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
     }
   } else {
     // =============================== epilogue (warps 2..5) ===============================
@@ -196,8 +197,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       if (a.n_tiles > 1 || !bias_loaded) {      // one N tile: the bias never changes — load it once
         for (int i = et; i < BN; i += 128) {
           const float bv = (a.bias && n0 + i < a.cout) ? __ldg(a.bias + n0 + i) : 0.f;
-          s_bias[acc][i] = bv;
-          if (a.n_tiles == 1) s_bias[acc ^ 1][i] = bv;
+          s_bias[acc & 1][i] = bv;
+          if (a.n_tiles == 1) s_bias[(acc & 1) ^ 1][i] = bv;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         bias_loaded = true;
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
         if (ok && nb < a.cout) {
           float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[acc][c * 16 + j];
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[acc & 1][c * 16 + j];
           if (out_f32) {
             float *o = static_cast<float *>(a.dst) + pix * a.cout_store + nb;
 #pragma unroll
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-      if (++acc == 2) { acc = 0; accphase ^= 1; }
+      if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
     }
   }
 
@@ -317,6 +318,7 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   a.n_tiles = (op.cout + BN - 1) / BN;
   a.cout = op.cout; a.cout_store = op.cout;
   a.total_tiles = op.B * a.tiles_h * a.tiles_w * a.n_tiles;
+  a.nacc = 512 / BN > 8 ? 8 : 512 / BN;      // TMEM accumulator stages (hides the MMA<->epilogue hand-off latency)
   a.dst = op.dst; a.res = op.res; a.bias = op.bias; a.flags = op.flags;
   a.a_tx_bytes = HW_ * HH_ * bk * 2;
   a.a_stage_bytes = (a.a_tx_bytes + 1023u) & ~1023u;
