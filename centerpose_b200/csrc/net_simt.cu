@@ -359,20 +359,21 @@ __global__ void maxpool_kernel(const T *__restrict__ x, T *__restrict__ y, int B
 
 // ---- depthwise ConvTranspose2d(k=2f, stride f, pad f/2) + skip add, NHWC ----
 // out[b,ho,wo,c] = skip[b,ho,wo,c] + sum_{kh,kw : (ho+p-kh)%f==0, (wo+p-kw)%f==0} x[b,(ho+p-kh)/f,(wo+p-kw)/f,c] * w[kh,kw,c]
-// VEC channels per thread (8 for bf16 = one 16-byte access, 4 for fp32).
+// One CTA = one output row (b, ho); thread = (wo, group of VEC channels), VEC*sizeof(T) = 16 bytes.  The
+// k*k*C filter taps sit in shared memory; no integer division in the inner loop.
 template <typename T, int VEC>
-__global__ void dwdeconv_add_kernel(const T *__restrict__ x, const T *__restrict__ skip, T *__restrict__ y,
-                                    const float *__restrict__ w, int B, int H, int W, int C, int Ho, int Wo,
-                                    int k, int f, int pad) {
+__global__ void __launch_bounds__(256) dwdeconv_add_kernel(const T *__restrict__ x, const T *__restrict__ skip, T *__restrict__ y,
+                                                           const float *__restrict__ w, int H, int W, int C, int Ho, int Wo,
+                                                           int k, int f, int pad) {
+  extern __shared__ float sw[];                       // [k*k][C]
+  for (int i = threadIdx.x; i < k * k * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
   const int CV = C / VEC;
-  const long long total = (long long)B * Ho * Wo * CV;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % CV);
-    long long p = i / CV;
-    const int wo = (int)(p % Wo); p /= Wo;
-    const int ho = (int)(p % Ho);
-    const int b = (int)(p / Ho);
+  const int b = blockIdx.x / Ho, ho = blockIdx.x % Ho;
+  const int kh0 = (ho + pad) % f;
+  const T *xb = x + (size_t)b * H * W * C;
+  for (int i = threadIdx.x; i < Wo * CV; i += blockDim.x) {
+    const int wo = i / CV, cv = i - wo * CV;
     const size_t opix = (((size_t)b * Ho + ho) * Wo + wo) * C + cv * VEC;
     float acc[VEC];
 #pragma unroll
@@ -380,20 +381,21 @@ __global__ void dwdeconv_add_kernel(const T *__restrict__ x, const T *__restrict
       float4 s4 = skip ? Act<T>::ld4(skip + opix + q) : make_float4(0.f, 0.f, 0.f, 0.f);
       acc[q] = s4.x; acc[q + 1] = s4.y; acc[q + 2] = s4.z; acc[q + 3] = s4.w;
     }
-    for (int khh = (ho + pad) % f; khh < k; khh += f) {
+    const int kw0 = (wo + pad) % f;
+    for (int khh = kh0; khh < k; khh += f) {
       const int hn = ho + pad - khh;
       const int hi = hn / f;
       if (hn < 0 || hi >= H) continue;
-      for (int kww = (wo + pad) % f; kww < k; kww += f) {
+      for (int kww = kw0; kww < k; kww += f) {
         const int wn = wo + pad - kww;
         const int wi = wn / f;
         if (wn < 0 || wi >= W) continue;
-        const T *xp = x + (((size_t)b * H + hi) * W + wi) * C + cv * VEC;
-        const float *wp = w + ((size_t)khh * k + kww) * C + cv * VEC;
+        const T *xp = xb + ((size_t)hi * W + wi) * C + cv * VEC;
+        const float *wp = sw + (khh * k + kww) * C + cv * VEC;
 #pragma unroll
         for (int q = 0; q < VEC; q += 4) {
           const float4 v = Act<T>::ld4(xp + q);
-          const float4 ww = __ldg(reinterpret_cast<const float4 *>(wp + q));
+          const float4 ww = *reinterpret_cast<const float4 *>(wp + q);
           acc[q] = fmaf(v.x, ww.x, acc[q]); acc[q + 1] = fmaf(v.y, ww.y, acc[q + 1]);
           acc[q + 2] = fmaf(v.z, ww.z, acc[q + 2]); acc[q + 3] = fmaf(v.w, ww.w, acc[q + 3]);
         }
@@ -477,11 +479,11 @@ int run_op_simt(const cpb200_op &op, cudaStream_t st) {
     case CPB200_OP_DWDECONV_ADD: {
       constexpr int VEC = sizeof(T) == 2 ? 8 : 4;
       if (op.cin[0] % VEC) return cpb::fail(CPB200_ERR_ARG, "dwdeconv: C %% %d != 0", VEC);
-      const long long total = (long long)op.B * op.Ho * op.Wo * (op.cin[0] / VEC);
-      const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 64);
-      dwdeconv_add_kernel<T, VEC><<<grid, 256, 0, st>>>(static_cast<const T *>(op.src[0]),
+      const size_t smem = (size_t)op.kh * op.kh * op.cin[0] * sizeof(float);
+      if (smem > 48 * 1024) return cpb::fail(CPB200_ERR_ARG, "dwdeconv: filter does not fit shared memory");
+      dwdeconv_add_kernel<T, VEC><<<(unsigned)(op.B * op.Ho), 256, smem, st>>>(static_cast<const T *>(op.src[0]),
           static_cast<const T *>(op.aux), static_cast<T *>(op.dst), static_cast<const float *>(op.weight),
-          op.B, op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h);
+          op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h);
       return cpb::check_launch("dwdeconv_add_kernel");
     }
     default: return cpb::fail(CPB200_ERR_ARG, "unknown op type %d", op.type);

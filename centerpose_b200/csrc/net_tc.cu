@@ -360,10 +360,10 @@ struct TcOp {
 
 template <int BN, bool DCN>
 int launch_tc(const TcOp &t, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CPB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, DCN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192));
-    attr_set = true;
+  static size_t attr_smem = 0;
+  if (t.smem > attr_smem) {
+    CPB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, DCN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
+    attr_smem = t.smem;
   }
   conv_tc_kernel<BN, DCN><<<t.grid, DCN ? DCN_THREADS : TC_THREADS, t.smem, st>>>(t.args);
   return cpb::check_launch(DCN ? "dcn_tc_kernel" : "conv_tc_kernel");

@@ -18,6 +18,7 @@
 // through its own ring.  Warps: 0 = halo producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue,
 // 6 = weight producer; persistent CTAs, two TMEM accumulator stages.
 #include "tc_common.cuh"
+#include <cstdlib>
 
 using namespace tc;
 
@@ -25,7 +26,7 @@ namespace {
 
 constexpr int C3_THREADS = 224;
 constexpr int TW = 8, TH = 16, HW_ = TW + 2, HH_ = TH + 2;
-constexpr int MAX_NA = 8, MAX_NB = 8;
+constexpr int MAX_NA = 16, MAX_NB = 8;
 
 struct alignas(64) C3Args {
   CUtensorMap amap, bmap;
@@ -276,10 +277,10 @@ struct C3Op {
 
 template <int BN>
 int launch_c3(const C3Op &t, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    CPB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8192));
-    attr_set = true;
+  static size_t attr_smem = 0;
+  if (t.smem > attr_smem) {
+    CPB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
+    attr_smem = t.smem;
   }
   conv3x3_tc_kernel<BN><<<t.grid, C3_THREADS, t.smem, st>>>(t.args);
   return cpb::check_launch("conv3x3_tc_kernel");
@@ -326,7 +327,8 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   a.b_stage_bytes = (a.b_tx_bytes + 1023u) & ~1023u;
   const size_t budget = 200 * 1024;
   a.na = 3;
-  if (a.a_stage_bytes <= 12 * 1024) a.na = (a.a_stage_bytes <= 6 * 1024) ? 8 : 5;   // small halos: deeper ring hides TMA latency
+  if (a.a_stage_bytes <= 12 * 1024) a.na = (a.a_stage_bytes <= 6 * 1024) ? 16 : 8;   // small halos: deeper ring hides TMA latency
+  if (const char *e = getenv("CPB200_C3_NA")) { int v = atoi(e); if (v >= 2 && v <= MAX_NA) a.na = v; }
   const size_t resident_bytes = (size_t)9 * a.slabs * a.b_stage_bytes;
   if (a.n_tiles == 1 && a.na * (size_t)a.a_stage_bytes + resident_bytes <= budget) {
     a.b_resident = 1; a.nb = 9 * a.slabs;
