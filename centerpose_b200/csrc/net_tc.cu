@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(full0 + 8 * stage, phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
           const uint64_t ad = make_desc(sa, row_bytes, a.swizzle_bits), bd = make_desc(sb, row_bytes, a.swizzle_bits);
           for (int k = 0; k < a.BK / 16; ++k)
@@ -459,7 +459,7 @@ int tc_prepare_op(cpb200_op &op) {
   a.nacc = 512 / BN > 8 ? 8 : 512 / BN;      // TMEM accumulator stages
   a.dst = op.dst; a.res = op.res; a.bias = op.bias; a.flags = op.flags;
   const size_t a_bytes = (size_t)TILE_M * bk * 2, b_bytes = ((size_t)BN * bk * 2 + 1023) / 1024 * 1024;
-  const size_t budget = 200 * 1024;
+  const size_t budget = dcn ? 176 * 1024 : 200 * 1024;     // the DCN variant keeps 39 KB of sampling parameters in static smem
   int stages = (int)(budget / (a_bytes + b_bytes));
   if (stages > 8) stages = 8;
   if (dcn && stages > 4) stages = 4;      // leave the rest of the 228 KB to L1: the 9 taps x 4 corners re-read one ~30 KB footprint

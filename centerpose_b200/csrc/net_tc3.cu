@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
         if (a.b_resident) {
           // resident weights: nothing to wait for inside the slab — one lane issues all 9 x ksteps MMAs
           // back to back; descriptors differ only in the 14-bit start-address field (adds on the low word)
-          if (lane == 0) {
+          if (elect_one()) {
             const uint64_t ad0 = desc_sbo(halo, HW_ * pix_bytes, a.swizzle_bits);
             const uint64_t bd0 = desc_sbo(b_base + sl * 9 * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
             const uint32_t bstep = a.b_stage_bytes >> 4, pstep = pix_bytes >> 4;
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait(bfull0 + 8 * sb, phb);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
               const int r = tap / 3, s = tap - 3 * r;
               const uint64_t ad = desc_sbo(halo + (r * HW_ + s) * pix_bytes, HW_ * pix_bytes, a.swizzle_bits);
               const uint64_t bd = desc_sbo(b_base + sb * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
             if (++sb == a.nb) { sb = 0; phb ^= 1; }
           }
         }
-        if (lane == 0) {
+        if (elect_one()) {
           umma_commit(aempty0 + 8 * sa);
           if (sl == a.slabs - 1) umma_commit(tfull0 + 8 * acc);
         }
