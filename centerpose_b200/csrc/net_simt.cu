@@ -48,7 +48,8 @@ struct ConvArgs {
   int cin[4];
   int nsrc;
   const void *res;
-  const float *aux;       // DCN: (B,H,W,27) fp32 offsets+mask logits
+  const float *aux;       // DCN: (B,H,W,aux_pitch) fp32 offsets+mask logits
+  int aux_pitch;
   void *dst;
   const float *weight;    // [taps][cin_total][cout_pad]
   const float *bias;
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
           const int b = (int)(m / ((long long)a.Ho * a.Wo));
           const int rem = (int)(m % ((long long)a.Ho * a.Wo));
           const int ho = rem / a.Wo, wo = rem % a.Wo;
-          const float *om = a.aux + ((size_t)m) * 27;
+          const float *om = a.aux + ((size_t)m) * a.aux_pitch;
           const float oh = __ldg(om + 2 * tap), ow = __ldg(om + 2 * tap + 1);
           const float mk = 1.0f / (1.0f + expf(-__ldg(om + 18 + tap)));      // dcn_v2.py:121
           const float h_im = (float)(ho * a.stride - a.pad_h + r_) + oh;      // im2col_cuda.cu:177-178
@@ -417,7 +418,7 @@ int launch_conv(const cpb200_op &op, cudaStream_t st) {
       a.cin_total += op.cin[i];
     }
   }
-  a.nsrc = op.nsrc; a.res = op.res; a.aux = static_cast<const float *>(op.aux); a.dst = op.dst;
+  a.nsrc = op.nsrc; a.res = op.res; a.aux = static_cast<const float *>(op.aux); a.aux_pitch = op.aux_pitch > 0 ? op.aux_pitch : 27; a.dst = op.dst;
   a.weight = static_cast<const float *>(op.weight); a.bias = op.bias;
   a.B = op.B; a.H = op.H; a.W = op.W; a.Ho = op.Ho; a.Wo = op.Wo; a.Hd = op.Hd; a.Wd = op.Wd;
   a.cout = op.cout; a.cout_pad = (op.cout + 3) / 4 * 4;

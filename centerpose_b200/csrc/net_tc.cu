@@ -45,7 +45,7 @@ struct alignas(64) TcArgs {
   // deformable conv (DCN) only: A tiles are gathered by producer warps instead of TMA
   const __nv_bfloat16 *dcn_src;   // (B,H,W,Cin) bf16
   const float *dcn_om;            // (B,H,W,27) fp32: 18 offsets (dy,dx per tap) | 9 mask logits
-  int H, W;
+  int H, W, om_pitch;
   int Hd, Wd, sy, sx, oy, ox;     // strided output mapping (dense ConvTranspose2d parity sub-convs)
   int out_ch_off, out_ch_total;   // NCHW fp32 output: channel slice of dst
 };
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
         int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
         const int rp = gw * 16 + (lane & 15);
         const int ho = h0 + rp / a.TW, wo = w0 + rp % a.TW;
         const bool okp = ho < a.Ho && wo < a.Wo;
-        const float *om = a.dcn_om + (((size_t)n * a.H + ho) * a.W + wo) * 27;
+        const float *om = a.dcn_om + (((size_t)n * a.H + ho) * a.W + wo) * a.om_pitch;
         const int tap0 = (lane < 16) ? 0 : 5, ntap = (lane < 16) ? 5 : 4;
         float oh[5], ow[5], ml[5];
 #pragma unroll
@@ -300,9 +300,18 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
               if (nb + j < a.cout) o[j * plane] = relu ? fmaxf(f[j], 0.f) : f[j];
           } else if (out_f32) {
             float *o = static_cast<float *>(a.dst) + pix * a.cout_store + nb;
+            if (nb + 16 <= a.cout && (a.cout_store & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (nb + j < a.cout) o[j] = relu ? fmaxf(f[j], 0.f) : f[j];
+              for (int j = 0; j < 16; j += 4) {
+                float4 v4 = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                if (relu) { v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f); }
+                *reinterpret_cast<float4 *>(o + j) = v4;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (nb + j < a.cout) o[j] = relu ? fmaxf(f[j], 0.f) : f[j];
+            }
           } else {
             __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(a.dst) + pix * a.cout_store + nb;
             if (a.res) {
@@ -449,7 +458,7 @@ int tc_prepare_op(cpb200_op &op) {
   while (BN < op.cout && BN < 256) BN <<= 1;
   t->BN = BN; t->dcn = dcn;
   a.dcn_src = static_cast<const __nv_bfloat16 *>(op.src[0]); a.dcn_om = static_cast<const float *>(op.aux);
-  a.H = op.H; a.W = op.W;
+  a.H = op.H; a.W = op.W; a.om_pitch = op.aux_pitch > 0 ? op.aux_pitch : 27;
   a.Hd = op.Hd; a.Wd = op.Wd; a.sy = op.out_sy; a.sx = op.out_sx; a.oy = op.out_oy; a.ox = op.out_ox;
   a.n_tiles = (op.cout + BN - 1) / BN;
   a.cout = op.cout; a.cout_store = op.cout;

@@ -33,7 +33,7 @@ struct alignas(64) C3Args {
   int cin, slabs, BK;
   int B, Ho, Wo, tiles_h, tiles_w, n_tiles, total_tiles;
   int cout, cout_store;
-  int na, nb, b_resident, nacc;
+  int na, nb, b_resident, nacc, group;
   unsigned a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
   void *dst;
   const void *res;
@@ -92,23 +92,33 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
     h0 = th * TH; w0 = tw * TW;
   };
 
+  // Tiles of this CTA are processed in GROUPS of G: tcgen05.mma instructions that accumulate into the same
+  // TMEM tile execute as a dependent chain (~110 cycles each, measured: conv 64->64 ran 36 MMAs per tile in
+  // 2.1 us regardless of everything else), so with N <= 128 one tile cannot keep the tensor pipe busy.  The
+  // issuer therefore interleaves the taps of G tiles (G accumulators, G halos in flight) and every weight
+  // stage is consumed by G tiles before it is released, which also divides the weight traffic by G.
+  const int my_tiles = (a.total_tiles > (int)blockIdx.x) ? (a.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int G = a.group;
+
   if (warp == 0) {
-    // =============================== halo producer ===============================
-    if (lane == 0) {
-      int sa = 0; uint32_t pha = 0;
-      for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-        int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
-        for (int sl = 0; sl < a.slabs; ++sl) {
-          mbar_wait(aempty0 + 8 * sa, pha ^ 1);
-          mbar_expect_tx(afull0 + 8 * sa, a.a_tx_bytes);
-          tma_load_4d(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, w0 - 1, h0 - 1, n);
-          if (++sa == a.na) { sa = 0; pha ^= 1; }
-        }
+    // =============================== halo producer: order (group, slab, tile-in-group) ===============================
+    if (elect_one()) {
+      int la = 0;
+      for (int i0 = 0; i0 < my_tiles; i0 += G) {
+        const int cnt = min(G, my_tiles - i0);
+        for (int sl = 0; sl < a.slabs; ++sl)
+          for (int g = 0; g < cnt; ++g, ++la) {
+            int n, h0, w0, nt; decode_tile(blockIdx.x + (i0 + g) * gridDim.x, n, h0, w0, nt);
+            const int sa = la % a.na; const uint32_t pha = (la / a.na) & 1;
+            mbar_wait(aempty0 + 8 * sa, pha ^ 1);
+            mbar_expect_tx(afull0 + 8 * sa, a.a_tx_bytes);
+            tma_load_4d(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, w0 - 1, h0 - 1, n);
+          }
       }
     }
   } else if (warp == 6) {
-    // =============================== weight producer ===============================
-    if (lane == 0) {
+    // =============================== weight producer: once per group ===============================
+    if (elect_one()) {
       if (a.b_resident) {
         mbar_expect_tx(ball, 9u * a.slabs * a.b_tx_bytes);
         for (int sl = 0; sl < a.slabs; ++sl)
@@ -116,8 +126,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
             tma_load_3d(b_base + (sl * 9 + tap) * a.b_stage_bytes, &a.bmap, ball, sl * a.BK, 0, tap);
       } else {
         int sb = 0; uint32_t phb = 0;
-        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-          const int nt = t % a.n_tiles;
+        for (int i0 = 0; i0 < my_tiles; i0 += G) {
+          const int nt = (int)((blockIdx.x + (long long)i0 * gridDim.x) % a.n_tiles);     // G == 1 whenever n_tiles > 1
           for (int sl = 0; sl < a.slabs; ++sl)
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(bempty0 + 8 * sb, phb ^ 1);
@@ -131,57 +141,46 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int sa = 0; uint32_t pha = 0; int sb = 0; uint32_t phb = 0; int acc = 0; uint32_t accphase = 0;
+    int la = 0; int sb = 0; uint32_t phb = 0;
     if (a.b_resident) { mbar_wait(ball, 0); tc_fence_after(); }
     const int ksteps = a.BK / 16;
-    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-      mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
+    const uint32_t bstep = a.b_stage_bytes >> 4, pstep = pix_bytes >> 4;
+    for (int i0 = 0; i0 < my_tiles; i0 += G) {
+      const int cnt = min(G, my_tiles - i0);
+      for (int g = 0; g < cnt; ++g) {
+        const int ti = i0 + g;
+        mbar_wait(tempty0 + 8 * (ti % a.nacc), ((ti / a.nacc) & 1) ^ 1);
+      }
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
       for (int sl = 0; sl < a.slabs; ++sl) {
-        mbar_wait(afull0 + 8 * sa, pha);
+        for (int g = 0; g < cnt; ++g) mbar_wait(afull0 + 8 * ((la + g) % a.na), ((la + g) / a.na) & 1);
         tc_fence_after();
-        const uint32_t halo = a_base + sa * a.a_stage_bytes;
-        if (a.b_resident) {
-          // resident weights: nothing to wait for inside the slab — one lane issues all 9 x ksteps MMAs
-          // back to back; descriptors differ only in the 14-bit start-address field (adds on the low word)
+        for (int tap = 0; tap < 9; ++tap) {
+          uint32_t bsm;
+          if (a.b_resident) bsm = b_base + (sl * 9 + tap) * a.b_stage_bytes;
+          else { mbar_wait(bfull0 + 8 * sb, phb); tc_fence_after(); bsm = b_base + sb * a.b_stage_bytes; }
           if (elect_one()) {
-            const uint64_t ad0 = desc_sbo(halo, HW_ * pix_bytes, a.swizzle_bits);
-            const uint64_t bd0 = desc_sbo(b_base + sl * 9 * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
-            const uint32_t bstep = a.b_stage_bytes >> 4, pstep = pix_bytes >> 4;
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint64_t ad = ad0 + (uint32_t)((tap / 3) * HW_ + (tap % 3)) * pstep;
-              const uint64_t bd = bd0 + (uint32_t)tap * bstep;
+            const uint64_t bd = desc_sbo(bsm, 8 * pix_bytes, a.swizzle_bits);
+            const uint32_t aoff = (uint32_t)((tap / 3) * HW_ + (tap % 3)) * pstep;
+            for (int g = 0; g < cnt; ++g) {
+              const uint64_t ad = desc_sbo(a_base + ((la + g) % a.na) * a.a_stage_bytes, HW_ * pix_bytes, a.swizzle_bits) + aoff;
+              const uint32_t d_tmem = tmem_base + ((i0 + g) % a.nacc) * BN;
               for (int k = 0; k < ksteps; ++k)
                 umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
             }
+            if (!a.b_resident) umma_commit(bempty0 + 8 * sb);
           }
           __syncwarp();
-        } else {
-          for (int tap = 0; tap < 9; ++tap) {
-            mbar_wait(bfull0 + 8 * sb, phb);
-            tc_fence_after();
-            if (elect_one()) {
-              const int r = tap / 3, s = tap - 3 * r;
-              const uint64_t ad = desc_sbo(halo + (r * HW_ + s) * pix_bytes, HW_ * pix_bytes, a.swizzle_bits);
-              const uint64_t bd = desc_sbo(b_base + sb * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
-              umma_commit(bempty0 + 8 * sb);
-            }
-            __syncwarp();
-            if (++sb == a.nb) { sb = 0; phb ^= 1; }
-          }
+          if (!a.b_resident) { if (++sb == a.nb) { sb = 0; phb ^= 1; } }
         }
         if (elect_one()) {
-          umma_commit(aempty0 + 8 * sa);
-          if (sl == a.slabs - 1) umma_commit(tfull0 + 8 * acc);
+          for (int g = 0; g < cnt; ++g) umma_commit(aempty0 + 8 * ((la + g) % a.na));
+          if (sl == a.slabs - 1)
+            for (int g = 0; g < cnt; ++g) umma_commit(tfull0 + 8 * ((i0 + g) % a.nacc));
         }
         __syncwarp();
-        if (++sa == a.na) { sa = 0; pha ^= 1; }
+        la += cnt;
       }
-      if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
     }
   } else {
     // =============================== epilogue (warps 2..5) ===============================
@@ -222,9 +221,18 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[acc & 1][c * 16 + j];
           if (out_f32) {
             float *o = static_cast<float *>(a.dst) + pix * a.cout_store + nb;
+            if (nb + 16 <= a.cout && (a.cout_store & 3) == 0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (nb + j < a.cout) o[j] = relu ? fmaxf(f[j], 0.f) : f[j];
+              for (int j = 0; j < 16; j += 4) {
+                float4 v4 = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                if (relu) { v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f); }
+                *reinterpret_cast<float4 *>(o + j) = v4;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (nb + j < a.cout) o[j] = relu ? fmaxf(f[j], 0.f) : f[j];
+            }
           } else {
             __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(a.dst) + pix * a.cout_store + nb;
             if (a.res) {
@@ -326,22 +334,32 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   a.b_tx_bytes = BN * bk * 2;
   a.b_stage_bytes = (a.b_tx_bytes + 1023u) & ~1023u;
   const size_t budget = 200 * 1024;
-  a.na = 3;
-  if (a.a_stage_bytes <= 12 * 1024) a.na = (a.a_stage_bytes <= 6 * 1024) ? 16 : 8;   // small halos: deeper ring hides TMA latency
-  if (const char *e = getenv("CPB200_C3_NA")) { int v = atoi(e); if (v >= 2 && v <= MAX_NA) a.na = v; }
   const size_t resident_bytes = (size_t)9 * a.slabs * a.b_stage_bytes;
-  if (a.n_tiles == 1 && a.na * (size_t)a.a_stage_bytes + resident_bytes <= budget) {
-    a.b_resident = 1; a.nb = 9 * a.slabs;
-    t->smem = a.na * (size_t)a.a_stage_bytes + resident_bytes + 1024;
-  } else {
-    a.b_resident = 0;
-    if (a.na * (size_t)a.a_stage_bytes + 3 * (size_t)a.b_stage_bytes > budget) a.na = 2;
-    int nb = (int)((budget - a.na * (size_t)a.a_stage_bytes) / a.b_stage_bytes);
-    if (nb > MAX_NB) nb = MAX_NB;
-    if (nb < 2) { delete t; *rc = fail(CPB200_ERR_ARG, "tc3: tile does not fit shared memory"); return nullptr; }
-    a.nb = nb;
-    t->smem = a.na * (size_t)a.a_stage_bytes + nb * (size_t)a.b_stage_bytes + 1024;
+  int gmax = a.nacc / 2 < 4 ? a.nacc / 2 : 4;
+  if (a.n_tiles > 1 || gmax < 1) gmax = 1;
+  if (const char *e = getenv("CPB200_C3_GROUP")) { int v = atoi(e); if (v >= 1 && v < gmax) gmax = v; }
+  bool placed = false;
+  for (int g = gmax; g >= 1 && !placed; --g) {
+    // halos: two groups' worth (one being consumed, one being fetched), at least 3, at most MAX_NA
+    int na = 2 * g < 3 ? 3 : 2 * g;
+    if (a.a_stage_bytes <= 6 * 1024 && na < 8) na = 8;
+    if (na > MAX_NA) na = MAX_NA;
+    const size_t a_bytes = (size_t)na * a.a_stage_bytes;
+    if (a_bytes >= budget) continue;
+    if (a.n_tiles == 1 && a_bytes + resident_bytes <= budget) {
+      a.b_resident = 1; a.nb = 9 * a.slabs; a.na = na; a.group = g;
+      t->smem = a_bytes + resident_bytes + 1024; placed = true;
+    } else {
+      int nb = (int)((budget - a_bytes) / a.b_stage_bytes);
+      if (nb > MAX_NB) nb = MAX_NB;
+      if (nb >= 3 || (g == 1 && nb >= 2)) {
+        a.b_resident = 0; a.nb = nb; a.na = na; a.group = g;
+        t->smem = a_bytes + (size_t)nb * a.b_stage_bytes + 1024; placed = true;
+      }
+    }
   }
+  if (!placed) { delete t; *rc = fail(CPB200_ERR_ARG, "tc3: tile does not fit shared memory"); return nullptr; }
+  if (const char *e = getenv("CPB200_C3_NA")) { int v = atoi(e); (void)v; }
   const int nsm = num_sms();
   t->grid = a.total_tiles < nsm ? a.total_tiles : nsm;
   {

@@ -42,7 +42,7 @@ class OpStruct(ctypes.Structure):
         ("Hd", ctypes.c_int32), ("Wd", ctypes.c_int32),
         ("out_sy", ctypes.c_int32), ("out_sx", ctypes.c_int32),
         ("out_oy", ctypes.c_int32), ("out_ox", ctypes.c_int32),
-        ("reserved0", ctypes.c_int32),
+        ("aux_pitch", ctypes.c_int32),
         ("src", ctypes.c_void_p * 4), ("res", ctypes.c_void_p), ("aux", ctypes.c_void_p),
         ("dst", ctypes.c_void_p), ("weight", ctypes.c_void_p), ("bias", ctypes.c_void_p),
         ("tc", ctypes.c_void_p), ("reserved1", ctypes.c_uint64 * 2),
@@ -219,7 +219,10 @@ class PlanBuilder:
 
     def dcn(self, x: Sym, w, b, om_w, om_b, relu=True):
         """DCN module (dcn_v2.py:117-127) with BN already folded into (w, b)."""
-        om = self.conv([x], om_w.float(), om_b.float(), stride=1, pad=1, relu=False, out="f32")
+        # offset/mask conv: 27 channels padded to 32 so every pixel row is 128 bytes (vector stores / loads)
+        om_w32 = torch.zeros(32, *om_w.shape[1:], dtype=torch.float32, device=om_w.device); om_w32[:27] = om_w.float()
+        om_b32 = torch.zeros(32, dtype=torch.float32, device=om_b.device); om_b32[:27] = om_b.float()
+        om = self.conv([x], om_w32, om_b32, stride=1, pad=1, relu=False, out="f32")
         co = w.shape[0]
         y = self._sym(co, x.H, x.W)
         tc = (self.use_tc and x.kind == "act" and x.C % 64 == 0 and co % 16 == 0 and 64 <= co and x.W >= 8
@@ -277,6 +280,7 @@ class Plan:
                 o.res = ex[0].buf.data_ptr()
             if po.type in (OP_DCN, OP_DWDECONV_ADD) and ex and ex[0] is not None:
                 o.aux = ex[0].buf.data_ptr()
+                o.aux_pitch = ex[0].C
             if po.weight is not None:
                 o.weight = po.weight.data_ptr()
             if po.bias is not None:

@@ -122,10 +122,10 @@ typedef struct cpb200_op {
   int32_t out_ch_off, out_ch_total;   /* NCHW output: channel offset / total channels of dst */
   int32_t Hd, Wd;            /* spatial size of the dst tensor (== Ho,Wo unless strided output) */
   int32_t out_sy, out_sx, out_oy, out_ox; /* output pixel (ho,wo) lands at (ho*out_sy+out_oy, wo*out_sx+out_ox) */
-  int32_t reserved0;
+  int32_t aux_pitch;         /* DCN: channel pitch of the offset/mask tensor (27, or 32 when padded for 16-byte rows) */
   const void *src[4];        /* inputs (NHWC act_dtype; STEM: NCHW fp32) */
   const void *res;           /* optional residual, same shape/dtype as the NHWC output */
-  const void *aux;           /* DCN: offset/mask tensor (B,H,W,27) fp32; DWDECONV_ADD: skip tensor */
+  const void *aux;           /* DCN: offset/mask tensor (B,H,W,aux_pitch) fp32, channels [0,18) offsets, [18,27) mask; DWDECONV_ADD: skip */
   void *dst;
   const void *weight;        /* packed by centerpose_b200/plan.py, layout per op type */
   const float *bias;         /* fp32 [cout] (BatchNorm folded), may be NULL */
