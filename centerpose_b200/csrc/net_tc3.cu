@@ -103,16 +103,17 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
   if (warp == 0) {
     // =============================== halo producer: order (group, slab, tile-in-group) ===============================
     if (elect_one()) {
-      int la = 0;
+      int sa = 0; uint32_t pha = 0;
       for (int i0 = 0; i0 < my_tiles; i0 += G) {
         const int cnt = min(G, my_tiles - i0);
+        int tn[4], th0[4], tw0[4];
+        for (int g = 0; g < cnt; ++g) { int nt; decode_tile(blockIdx.x + (i0 + g) * gridDim.x, tn[g], th0[g], tw0[g], nt); }
         for (int sl = 0; sl < a.slabs; ++sl)
-          for (int g = 0; g < cnt; ++g, ++la) {
-            int n, h0, w0, nt; decode_tile(blockIdx.x + (i0 + g) * gridDim.x, n, h0, w0, nt);
-            const int sa = la % a.na; const uint32_t pha = (la / a.na) & 1;
+          for (int g = 0; g < cnt; ++g) {
             mbar_wait(aempty0 + 8 * sa, pha ^ 1);
             mbar_expect_tx(afull0 + 8 * sa, a.a_tx_bytes);
-            tma_load_4d(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, w0 - 1, h0 - 1, n);
+            tma_load_4d(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, tw0[g] - 1, th0[g] - 1, tn[g]);
+            if (++sa == a.na) { sa = 0; pha ^= 1; }
           }
       }
     }
@@ -140,46 +141,88 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
+    // The issue loop is latency-critical (one lane feeds the tensor pipe): no integer division, descriptors
+    // are built once per slab and only their 14-bit start-address field is advanced, and with resident
+    // weights a whole slab (9 taps x G tiles x ksteps MMAs) is issued from ONE elected region.
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int la = 0; int sb = 0; uint32_t phb = 0;
+    int sa = 0; uint32_t pha = 0; int sb = 0; uint32_t phb = 0; int acc = 0; uint32_t accphase = 0;
     if (a.b_resident) { mbar_wait(ball, 0); tc_fence_after(); }
     const int ksteps = a.BK / 16;
     const uint32_t bstep = a.b_stage_bytes >> 4, pstep = pix_bytes >> 4;
     for (int i0 = 0; i0 < my_tiles; i0 += G) {
       const int cnt = min(G, my_tiles - i0);
-      for (int g = 0; g < cnt; ++g) {
-        const int ti = i0 + g;
-        mbar_wait(tempty0 + 8 * (ti % a.nacc), ((ti / a.nacc) & 1) ^ 1);
+      uint32_t dt[4]; uint32_t tf[4];
+      {
+        int ac = acc; uint32_t ap = accphase;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g < cnt) {
+            mbar_wait(tempty0 + 8 * ac, ap ^ 1);
+            dt[g] = tmem_base + ac * BN; tf[g] = tfull0 + 8 * ac;
+            if (++ac == a.nacc) { ac = 0; ap ^= 1; }
+          }
+        }
+        acc = ac; accphase = ap;
       }
       tc_fence_after();
       for (int sl = 0; sl < a.slabs; ++sl) {
-        for (int g = 0; g < cnt; ++g) mbar_wait(afull0 + 8 * ((la + g) % a.na), ((la + g) / a.na) & 1);
+        uint64_t ad[4]; uint32_t ae[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g < cnt) {
+            mbar_wait(afull0 + 8 * sa, pha);
+            ad[g] = desc_sbo(a_base + sa * a.a_stage_bytes, HW_ * pix_bytes, a.swizzle_bits);
+            ae[g] = aempty0 + 8 * sa;
+            if (++sa == a.na) { sa = 0; pha ^= 1; }
+          }
+        }
         tc_fence_after();
-        for (int tap = 0; tap < 9; ++tap) {
-          uint32_t bsm;
-          if (a.b_resident) bsm = b_base + (sl * 9 + tap) * a.b_stage_bytes;
-          else { mbar_wait(bfull0 + 8 * sb, phb); tc_fence_after(); bsm = b_base + sb * a.b_stage_bytes; }
+        const bool last = (sl == a.slabs - 1);
+        if (a.b_resident) {
           if (elect_one()) {
-            const uint64_t bd = desc_sbo(bsm, 8 * pix_bytes, a.swizzle_bits);
-            const uint32_t aoff = (uint32_t)((tap / 3) * HW_ + (tap % 3)) * pstep;
-            for (int g = 0; g < cnt; ++g) {
-              const uint64_t ad = desc_sbo(a_base + ((la + g) % a.na) * a.a_stage_bytes, HW_ * pix_bytes, a.swizzle_bits) + aoff;
-              const uint32_t d_tmem = tmem_base + ((i0 + g) % a.nacc) * BN;
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+            const uint64_t bd0 = desc_sbo(b_base + sl * 9 * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t aoff = (uint32_t)((tap / 3) * HW_ + (tap % 3)) * pstep;
+              const uint64_t bd = bd0 + (uint32_t)tap * bstep;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (g < cnt) {
+                  const uint64_t adg = ad[g] + aoff;
+                  for (int k = 0; k < ksteps; ++k)
+                    umma_bf16(dt[g], adg + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                }
+              }
             }
-            if (!a.b_resident) umma_commit(bempty0 + 8 * sb);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) if (g < cnt) { umma_commit(ae[g]); if (last) umma_commit(tf[g]); }
           }
           __syncwarp();
-          if (!a.b_resident) { if (++sb == a.nb) { sb = 0; phb ^= 1; } }
+        } else {
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(bfull0 + 8 * sb, phb);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t bd = desc_sbo(b_base + sb * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
+              const uint32_t aoff = (uint32_t)((tap / 3) * HW_ + (tap % 3)) * pstep;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (g < cnt) {
+                  const uint64_t adg = ad[g] + aoff;
+                  for (int k = 0; k < ksteps; ++k)
+                    umma_bf16(dt[g], adg + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                }
+              }
+              umma_commit(bempty0 + 8 * sb);
+              if (tap == 8) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) if (g < cnt) { umma_commit(ae[g]); if (last) umma_commit(tf[g]); }
+              }
+            }
+            __syncwarp();
+            if (++sb == a.nb) { sb = 0; phb ^= 1; }
+          }
         }
-        if (elect_one()) {
-          for (int g = 0; g < cnt; ++g) umma_commit(aempty0 + 8 * ((la + g) % a.na));
-          if (sl == a.slabs - 1)
-            for (int g = 0; g < cnt; ++g) umma_commit(tfull0 + 8 * ((i0 + g) % a.nacc));
-        }
-        __syncwarp();
-        la += cnt;
       }
     }
   } else {
