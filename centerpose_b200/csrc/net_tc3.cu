@@ -16,7 +16,14 @@
 // Weights: [tap][Cout_pad][Cin] bf16 via 3-D TMA; when the whole filter bank fits beside the halo
 // ring it is loaded ONCE per CTA and stays resident (e.g. 64->64: 72 KB), otherwise it streams
 // through its own ring.  Warps: 0 = halo producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue,
-// 6 = weight producer; persistent CTAs, two TMEM accumulator stages.
+// 6 = weight producer; persistent CTAs, up to eight TMEM accumulator stages.
+//
+// Tried and dropped (round 1, see profiles/r01_group_interleave_experiment.log): interleaving the taps of G
+// tiles in the issue loop so that consecutive tcgen05.mma instructions target different accumulators (and
+// every weight stage serves G tiles).  It beat its own G = 1 baseline (conv 128->128: 60 -> 46 us) but the
+// extra bookkeeping in the single issuing lane made that baseline slower than this straight-line version
+// (64->64: 59 us here, 67 us grouped), i.e. the issuer is bound by instructions issued, not by the
+// accumulator dependency chain.
 #include "tc_common.cuh"
 #include <cstdlib>
 
@@ -33,7 +40,7 @@ struct alignas(64) C3Args {
   int cin, slabs, BK;
   int B, Ho, Wo, tiles_h, tiles_w, n_tiles, total_tiles;
   int cout, cout_store;
-  int na, nb, b_resident, nacc, group;
+  int na, nb, b_resident, nacc;
   unsigned a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
   void *dst;
   const void *res;
@@ -92,33 +99,22 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
     h0 = th * TH; w0 = tw * TW;
   };
 
-  // Tiles of this CTA are processed in GROUPS of G: tcgen05.mma instructions that accumulate into the same
-  // TMEM tile execute as a dependent chain (~110 cycles each, measured: conv 64->64 ran 36 MMAs per tile in
-  // 2.1 us regardless of everything else), so with N <= 128 one tile cannot keep the tensor pipe busy.  The
-  // issuer therefore interleaves the taps of G tiles (G accumulators, G halos in flight) and every weight
-  // stage is consumed by G tiles before it is released, which also divides the weight traffic by G.
-  const int my_tiles = (a.total_tiles > (int)blockIdx.x) ? (a.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int G = a.group;
-
   if (warp == 0) {
-    // =============================== halo producer: order (group, slab, tile-in-group) ===============================
+    // =============================== halo producer ===============================
     if (elect_one()) {
       int sa = 0; uint32_t pha = 0;
-      for (int i0 = 0; i0 < my_tiles; i0 += G) {
-        const int cnt = min(G, my_tiles - i0);
-        int tn[4], th0[4], tw0[4];
-        for (int g = 0; g < cnt; ++g) { int nt; decode_tile(blockIdx.x + (i0 + g) * gridDim.x, tn[g], th0[g], tw0[g], nt); }
-        for (int sl = 0; sl < a.slabs; ++sl)
-          for (int g = 0; g < cnt; ++g) {
-            mbar_wait(aempty0 + 8 * sa, pha ^ 1);
-            mbar_expect_tx(afull0 + 8 * sa, a.a_tx_bytes);
-            tma_load_4d(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, tw0[g] - 1, th0[g] - 1, tn[g]);
-            if (++sa == a.na) { sa = 0; pha ^= 1; }
-          }
+      for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
+        for (int sl = 0; sl < a.slabs; ++sl) {
+          mbar_wait(aempty0 + 8 * sa, pha ^ 1);
+          mbar_expect_tx(afull0 + 8 * sa, a.a_tx_bytes);
+          tma_load_4d(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, w0 - 1, h0 - 1, n);
+          if (++sa == a.na) { sa = 0; pha ^= 1; }
+        }
       }
     }
   } else if (warp == 6) {
-    // =============================== weight producer: once per group ===============================
+    // =============================== weight producer ===============================
     if (elect_one()) {
       if (a.b_resident) {
         mbar_expect_tx(ball, 9u * a.slabs * a.b_tx_bytes);
@@ -127,8 +123,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
             tma_load_3d(b_base + (sl * 9 + tap) * a.b_stage_bytes, &a.bmap, ball, sl * a.BK, 0, tap);
       } else {
         int sb = 0; uint32_t phb = 0;
-        for (int i0 = 0; i0 < my_tiles; i0 += G) {
-          const int nt = (int)((blockIdx.x + (long long)i0 * gridDim.x) % a.n_tiles);     // G == 1 whenever n_tiles > 1
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+          const int nt = t % a.n_tiles;
           for (int sl = 0; sl < a.slabs; ++sl)
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(bempty0 + 8 * sb, phb ^ 1);
@@ -141,61 +137,32 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    // The issue loop is latency-critical (one lane feeds the tensor pipe): no integer division, descriptors
-    // are built once per slab and only their 14-bit start-address field is advanced, and with resident
-    // weights a whole slab (9 taps x G tiles x ksteps MMAs) is issued from ONE elected region.
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int sa = 0; uint32_t pha = 0; int sb = 0; uint32_t phb = 0; int acc = 0; uint32_t accphase = 0;
     if (a.b_resident) { mbar_wait(ball, 0); tc_fence_after(); }
     const int ksteps = a.BK / 16;
-    const uint32_t bstep = a.b_stage_bytes >> 4, pstep = pix_bytes >> 4;
-    for (int i0 = 0; i0 < my_tiles; i0 += G) {
-      const int cnt = min(G, my_tiles - i0);
-      uint32_t dt[4]; uint32_t tf[4];
-      {
-        int ac = acc; uint32_t ap = accphase;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g < cnt) {
-            mbar_wait(tempty0 + 8 * ac, ap ^ 1);
-            dt[g] = tmem_base + ac * BN; tf[g] = tfull0 + 8 * ac;
-            if (++ac == a.nacc) { ac = 0; ap ^= 1; }
-          }
-        }
-        acc = ac; accphase = ap;
-      }
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
       tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
       for (int sl = 0; sl < a.slabs; ++sl) {
-        uint64_t ad[4]; uint32_t ae[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g < cnt) {
-            mbar_wait(afull0 + 8 * sa, pha);
-            ad[g] = desc_sbo(a_base + sa * a.a_stage_bytes, HW_ * pix_bytes, a.swizzle_bits);
-            ae[g] = aempty0 + 8 * sa;
-            if (++sa == a.na) { sa = 0; pha ^= 1; }
-          }
-        }
+        mbar_wait(afull0 + 8 * sa, pha);
         tc_fence_after();
-        const bool last = (sl == a.slabs - 1);
+        const uint32_t halo = a_base + sa * a.a_stage_bytes;
         if (a.b_resident) {
+          // resident weights: nothing to wait for inside the slab — one lane issues all 9 x ksteps MMAs
+          // back to back; descriptors differ only in the 14-bit start-address field (adds on the low word)
           if (elect_one()) {
+            const uint64_t ad0 = desc_sbo(halo, HW_ * pix_bytes, a.swizzle_bits);
             const uint64_t bd0 = desc_sbo(b_base + sl * 9 * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
+            const uint32_t bstep = a.b_stage_bytes >> 4, pstep = pix_bytes >> 4;
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t aoff = (uint32_t)((tap / 3) * HW_ + (tap % 3)) * pstep;
+              const uint64_t ad = ad0 + (uint32_t)((tap / 3) * HW_ + (tap % 3)) * pstep;
               const uint64_t bd = bd0 + (uint32_t)tap * bstep;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (g < cnt) {
-                  const uint64_t adg = ad[g] + aoff;
-                  for (int k = 0; k < ksteps; ++k)
-                    umma_bf16(dt[g], adg + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                }
-              }
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
             }
-#pragma unroll
-            for (int g = 0; g < 4; ++g) if (g < cnt) { umma_commit(ae[g]); if (last) umma_commit(tf[g]); }
           }
           __syncwarp();
         } else {
@@ -203,27 +170,25 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
             mbar_wait(bfull0 + 8 * sb, phb);
             tc_fence_after();
             if (elect_one()) {
+              const int r = tap / 3, s = tap - 3 * r;
+              const uint64_t ad = desc_sbo(halo + (r * HW_ + s) * pix_bytes, HW_ * pix_bytes, a.swizzle_bits);
               const uint64_t bd = desc_sbo(b_base + sb * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
-              const uint32_t aoff = (uint32_t)((tap / 3) * HW_ + (tap % 3)) * pstep;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                if (g < cnt) {
-                  const uint64_t adg = ad[g] + aoff;
-                  for (int k = 0; k < ksteps; ++k)
-                    umma_bf16(dt[g], adg + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                }
-              }
+              for (int k = 0; k < ksteps; ++k)
+                umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
               umma_commit(bempty0 + 8 * sb);
-              if (tap == 8) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) if (g < cnt) { umma_commit(ae[g]); if (last) umma_commit(tf[g]); }
-              }
             }
             __syncwarp();
             if (++sb == a.nb) { sb = 0; phb ^= 1; }
           }
         }
+        if (elect_one()) {
+          umma_commit(aempty0 + 8 * sa);
+          if (sl == a.slabs - 1) umma_commit(tfull0 + 8 * acc);
+        }
+        __syncwarp();
+        if (++sa == a.na) { sa = 0; pha ^= 1; }
       }
+      if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
     }
   } else {
     // =============================== epilogue (warps 2..5) ===============================
@@ -377,32 +342,22 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   a.b_tx_bytes = BN * bk * 2;
   a.b_stage_bytes = (a.b_tx_bytes + 1023u) & ~1023u;
   const size_t budget = 200 * 1024;
+  a.na = 3;
+  if (a.a_stage_bytes <= 12 * 1024) a.na = (a.a_stage_bytes <= 6 * 1024) ? 16 : 8;   // small halos: deeper ring hides TMA latency
+  if (const char *e = getenv("CPB200_C3_NA")) { int v = atoi(e); if (v >= 2 && v <= MAX_NA) a.na = v; }
   const size_t resident_bytes = (size_t)9 * a.slabs * a.b_stage_bytes;
-  int gmax = a.nacc / 2 < 4 ? a.nacc / 2 : 4;
-  if (a.n_tiles > 1 || gmax < 1) gmax = 1;
-  if (const char *e = getenv("CPB200_C3_GROUP")) { int v = atoi(e); if (v >= 1 && v < gmax) gmax = v; }
-  bool placed = false;
-  for (int g = gmax; g >= 1 && !placed; --g) {
-    // halos: two groups' worth (one being consumed, one being fetched), at least 3, at most MAX_NA
-    int na = 2 * g < 3 ? 3 : 2 * g;
-    if (a.a_stage_bytes <= 6 * 1024 && na < 8) na = 8;
-    if (na > MAX_NA) na = MAX_NA;
-    const size_t a_bytes = (size_t)na * a.a_stage_bytes;
-    if (a_bytes >= budget) continue;
-    if (a.n_tiles == 1 && a_bytes + resident_bytes <= budget) {
-      a.b_resident = 1; a.nb = 9 * a.slabs; a.na = na; a.group = g;
-      t->smem = a_bytes + resident_bytes + 1024; placed = true;
-    } else {
-      int nb = (int)((budget - a_bytes) / a.b_stage_bytes);
-      if (nb > MAX_NB) nb = MAX_NB;
-      if (nb >= 3 || (g == 1 && nb >= 2)) {
-        a.b_resident = 0; a.nb = nb; a.na = na; a.group = g;
-        t->smem = a_bytes + (size_t)nb * a.b_stage_bytes + 1024; placed = true;
-      }
-    }
+  if (a.n_tiles == 1 && a.na * (size_t)a.a_stage_bytes + resident_bytes <= budget) {
+    a.b_resident = 1; a.nb = 9 * a.slabs;
+    t->smem = a.na * (size_t)a.a_stage_bytes + resident_bytes + 1024;
+  } else {
+    a.b_resident = 0;
+    if (a.na * (size_t)a.a_stage_bytes + 3 * (size_t)a.b_stage_bytes > budget) a.na = 2;
+    int nb = (int)((budget - a.na * (size_t)a.a_stage_bytes) / a.b_stage_bytes);
+    if (nb > MAX_NB) nb = MAX_NB;
+    if (nb < 2) { delete t; *rc = fail(CPB200_ERR_ARG, "tc3: tile does not fit shared memory"); return nullptr; }
+    a.nb = nb;
+    t->smem = a.na * (size_t)a.a_stage_bytes + nb * (size_t)a.b_stage_bytes + 1024;
   }
-  if (!placed) { delete t; *rc = fail(CPB200_ERR_ARG, "tc3: tile does not fit shared memory"); return nullptr; }
-  if (const char *e = getenv("CPB200_C3_NA")) { int v = atoi(e); (void)v; }
   const int nsm = num_sms();
   t->grid = a.total_tiles < nsm ? a.total_tiles : nsm;
   {
