@@ -247,12 +247,45 @@ def main():
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- end to end through the public API with host buffers --------------------------------
-    def e2e_step(i):
-        x = host[i % NROT].to(dev, non_blocking=True)
-        d = step(x)
-        host_dets.copy_(d[:B] if world > 1 else d, non_blocking=True)
-    e2e_step(0)
-    ms_e2e = timed(e2e_step, args.steps)
+    # Every step copies its own batch from pinned host memory (H2D, on a copy stream so that the copy of
+    # step i+1 overlaps the kernels of step i) and reads its detections back (D2H) — both inside the timed region.
+    copy_stream = torch.cuda.Stream(dev)
+    dev_in = [torch.empty_like(resident[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def stage_in(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])            # the step that last read this slot is done
+            dev_in[slot].copy_(host[i % NROT], non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_run(steps):
+        for ev in consumed:
+            ev.record(torch.cuda.current_stream(dev))
+        stage_in(0)
+        for i in range(steps):
+            slot = i % 2
+            if i + 1 < steps:
+                stage_in(i + 1)
+            torch.cuda.current_stream(dev).wait_event(ready[slot])
+            d = step(dev_in[slot])
+            consumed[slot].record(torch.cuda.current_stream(dev))
+            host_dets.copy_(d[:B] if world > 1 else d, non_blocking=True)
+
+    e2e_run(2)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_run(args.steps)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tt.item())
     e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
 
     # ---- network-only and decode-only kernel timings (roofline) -------------------------------

@@ -330,6 +330,34 @@ __global__ void __launch_bounds__(128) stem_kernel(const float *__restrict__ x, 
   }
 }
 
+// ---- IM2COL_W: NCHW fp32 (B,cin,H,W) -> NHWC (B,H,W,COUT): channel s*cin+c = x[c,h,w+s-pad], zero padded ----
+template <typename T, int COUT>
+__global__ void __launch_bounds__(256) im2col_w_kernel(const float *__restrict__ x, T *__restrict__ y, int B, int Cin,
+                                                       int H, int W, int kw, int pad) {
+  const long long M = (long long)B * H * W;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const int w = (int)(m % W);
+  const int h = (int)((m / W) % H);
+  const int b = (int)(m / ((long long)W * H));
+  float v[COUT];
+#pragma unroll
+  for (int i = 0; i < COUT; ++i) v[i] = 0.f;
+  for (int c = 0; c < Cin; ++c) {
+    const float *row = x + (((size_t)b * Cin + c) * H + h) * W;
+    for (int s_ = 0; s_ < kw; ++s_) {
+      const int wi = w + s_ - pad;
+      const float val = (wi >= 0 && wi < W) ? __ldg(row + wi) : 0.f;
+      const int ch = s_ * Cin + c;
+#pragma unroll
+      for (int i = 0; i < COUT; ++i) if (i == ch) v[i] = val;      // static indexing keeps v[] in registers
+    }
+  }
+  T *o = y + (size_t)m * COUT;
+#pragma unroll
+  for (int i = 0; i < COUT; i += 4) Act<T>::st4(o + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+}
+
 // ---- MAXPOOL k x k / stride / pad, NHWC, 4 channels per thread ----
 template <typename T>
 __global__ void maxpool_kernel(const T *__restrict__ x, T *__restrict__ y, int B, int H, int W, int C,
@@ -468,6 +496,14 @@ int run_op_simt(const cpb200_op &op, cudaStream_t st) {
       else return cpb::fail(CPB200_ERR_ARG, "stem: cout %d / stride %d unsupported", op.cout, op.stride);
 #undef STEM_LAUNCH
       return cpb::check_launch("stem_kernel");
+    }
+    case CPB200_OP_IM2COL_W: {
+      const int cin = op.cin[0];
+      if (op.cout != 32 || cin * op.kw > 32) return cpb::fail(CPB200_ERR_ARG, "im2col_w: needs kw*cin <= 32 output channels");
+      const long long M = (long long)op.B * op.H * op.W;
+      im2col_w_kernel<T, 32><<<(unsigned)((M + 255) / 256), 256, 0, st>>>(static_cast<const float *>(op.src[0]),
+          static_cast<T *>(op.dst), op.B, cin, op.H, op.W, op.kw, op.pad_w);
+      return cpb::check_launch("im2col_w_kernel");
     }
     case CPB200_OP_MAXPOOL: {
       if (op.cin[0] % 4) return cpb::fail(CPB200_ERR_ARG, "maxpool: C %% 4 != 0");

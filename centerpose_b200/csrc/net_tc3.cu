@@ -41,6 +41,7 @@ struct alignas(64) C3Args {
   int B, Ho, Wo, tiles_h, tiles_w, n_tiles, total_tiles;
   int cout, cout_store;
   int na, nb, b_resident, nacc;
+  int kh, kw, taps, hw;        // filter size, kh*kw, halo width in pixels (TW + kw - 1)
   unsigned a_stage_bytes, b_stage_bytes, a_tx_bytes, b_tx_bytes;
   void *dst;
   const void *res;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
         for (int sl = 0; sl < a.slabs; ++sl) {
           mbar_wait(aempty0 + 8 * sa, pha ^ 1);
           mbar_expect_tx(afull0 + 8 * sa, a.a_tx_bytes);
-          tma_load_4d(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, w0 - 1, h0 - 1, n);
+          tma_load_4d(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, w0 - (a.kw >> 1), h0 - (a.kh >> 1), n);
           if (++sa == a.na) { sa = 0; pha ^= 1; }
         }
       }
@@ -117,16 +118,16 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
     // =============================== weight producer ===============================
     if (elect_one()) {
       if (a.b_resident) {
-        mbar_expect_tx(ball, 9u * a.slabs * a.b_tx_bytes);
+        mbar_expect_tx(ball, (uint32_t)a.taps * a.slabs * a.b_tx_bytes);
         for (int sl = 0; sl < a.slabs; ++sl)
-          for (int tap = 0; tap < 9; ++tap)
-            tma_load_3d(b_base + (sl * 9 + tap) * a.b_stage_bytes, &a.bmap, ball, sl * a.BK, 0, tap);
+          for (int tap = 0; tap < a.taps; ++tap)
+            tma_load_3d(b_base + (sl * a.taps + tap) * a.b_stage_bytes, &a.bmap, ball, sl * a.BK, 0, tap);
       } else {
         int sb = 0; uint32_t phb = 0;
         for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
           const int nt = t % a.n_tiles;
           for (int sl = 0; sl < a.slabs; ++sl)
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = 0; tap < a.taps; ++tap) {
               mbar_wait(bempty0 + 8 * sb, phb ^ 1);
               mbar_expect_tx(bfull0 + 8 * sb, a.b_tx_bytes);
               tma_load_3d(b_base + sb * a.b_stage_bytes, &a.bmap, bfull0 + 8 * sb, sl * a.BK, nt * BN, tap);
@@ -153,25 +154,36 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
           // resident weights: nothing to wait for inside the slab — one lane issues all 9 x ksteps MMAs
           // back to back; descriptors differ only in the 14-bit start-address field (adds on the low word)
           if (elect_one()) {
-            const uint64_t ad0 = desc_sbo(halo, HW_ * pix_bytes, a.swizzle_bits);
-            const uint64_t bd0 = desc_sbo(b_base + sl * 9 * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
+            const uint64_t ad0 = desc_sbo(halo, a.hw * pix_bytes, a.swizzle_bits);
+            const uint64_t bd0 = desc_sbo(b_base + sl * a.taps * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
             const uint32_t bstep = a.b_stage_bytes >> 4, pstep = pix_bytes >> 4;
+            if (a.taps == 9) {
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint64_t ad = ad0 + (uint32_t)((tap / 3) * HW_ + (tap % 3)) * pstep;
-              const uint64_t bd = bd0 + (uint32_t)tap * bstep;
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint64_t ad = ad0 + (uint32_t)((tap / 3) * HW_ + (tap % 3)) * pstep;
+                const uint64_t bd = bd0 + (uint32_t)tap * bstep;
+                for (int k = 0; k < ksteps; ++k)
+                  umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              }
+            } else {
+              int tap = 0;
+              for (int r = 0; r < a.kh; ++r)
+                for (int q2 = 0; q2 < a.kw; ++q2, ++tap) {
+                  const uint64_t ad = ad0 + (uint32_t)(r * a.hw + q2) * pstep;
+                  const uint64_t bd = bd0 + (uint32_t)tap * bstep;
+                  for (int k = 0; k < ksteps; ++k)
+                    umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                }
             }
           }
           __syncwarp();
         } else {
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tap = 0; tap < a.taps; ++tap) {
             mbar_wait(bfull0 + 8 * sb, phb);
             tc_fence_after();
             if (elect_one()) {
-              const int r = tap / 3, s = tap - 3 * r;
-              const uint64_t ad = desc_sbo(halo + (r * HW_ + s) * pix_bytes, HW_ * pix_bytes, a.swizzle_bits);
+              const int r = tap / a.kw, s = tap - a.kw * r;
+              const uint64_t ad = desc_sbo(halo + (r * a.hw + s) * pix_bytes, a.hw * pix_bytes, a.swizzle_bits);
               const uint64_t bd = desc_sbo(b_base + sb * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
               for (int k = 0; k < ksteps; ++k)
                 umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
@@ -307,7 +319,8 @@ int launch_c3(const C3Op &t, cudaStream_t st) {
 namespace cpb {
 
 bool c3_eligible(const cpb200_op &op) {
-  return op.type == CPB200_OP_CONV && op.kh == 3 && op.kw == 3 && op.stride == 1 && op.pad_h == 1 && op.pad_w == 1 &&
+  const bool geom = (op.kh == 3 && op.kw == 3) || (op.kh == 7 && op.kw == 1) || (op.kh == 1 && op.kw == 7) || (op.kh == 5 && op.kw == 5);
+  return op.type == CPB200_OP_CONV && geom && op.stride == 1 && op.pad_h == op.kh / 2 && op.pad_w == op.kw / 2 &&
          op.nsrc == 1 && op.cin[0] % 16 == 0 && op.Wo >= 8 && op.Ho >= 8 && op.H == op.Ho && op.W == op.Wo &&
          op.out_sy == 1 && op.out_sx == 1 && !op.out_oy && !op.out_ox && op.Hd == op.Ho && op.Wd == op.Wo &&
          !(op.flags & CPB200_FLAG_OUT_NCHW_F32) && op.act_dtype == CPB200_BF16 &&
@@ -337,7 +350,9 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   a.total_tiles = op.B * a.tiles_h * a.tiles_w * a.n_tiles;
   a.nacc = 512 / BN > 8 ? 8 : 512 / BN;      // TMEM accumulator stages (hides the MMA<->epilogue hand-off latency)
   a.dst = op.dst; a.res = op.res; a.bias = op.bias; a.flags = op.flags;
-  a.a_tx_bytes = HW_ * HH_ * bk * 2;
+  a.kh = op.kh; a.kw = op.kw; a.taps = op.kh * op.kw; a.hw = TW + op.kw - 1;
+  const int hh = TH + op.kh - 1;
+  a.a_tx_bytes = (unsigned)(a.hw * hh * bk * 2);
   a.a_stage_bytes = (a.a_tx_bytes + 1023u) & ~1023u;
   a.b_tx_bytes = BN * bk * 2;
   a.b_stage_bytes = (a.b_tx_bytes + 1023u) & ~1023u;
@@ -345,9 +360,9 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   a.na = 3;
   if (a.a_stage_bytes <= 12 * 1024) a.na = (a.a_stage_bytes <= 6 * 1024) ? 16 : 8;   // small halos: deeper ring hides TMA latency
   if (const char *e = getenv("CPB200_C3_NA")) { int v = atoi(e); if (v >= 2 && v <= MAX_NA) a.na = v; }
-  const size_t resident_bytes = (size_t)9 * a.slabs * a.b_stage_bytes;
+  const size_t resident_bytes = (size_t)a.taps * a.slabs * a.b_stage_bytes;
   if (a.n_tiles == 1 && a.na * (size_t)a.a_stage_bytes + resident_bytes <= budget) {
-    a.b_resident = 1; a.nb = 9 * a.slabs;
+    a.b_resident = 1; a.nb = a.taps * a.slabs;
     t->smem = a.na * (size_t)a.a_stage_bytes + resident_bytes + 1024;
   } else {
     a.b_resident = 0;
@@ -363,7 +378,7 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   {
     const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.B};
     const cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)op.W * cin * 2, (cuuint64_t)op.H * op.W * cin * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)bk, HW_, HH_, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)a.hw, (cuuint32_t)hh, 1};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = enc(&a.amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(op.src[0]), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -371,7 +386,7 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   }
   {
     const int cout_pad = (op.cout + 15) / 16 * 16;
-    const cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout_pad, 9};
+    const cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout_pad, (cuuint64_t)a.taps};
     const cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout_pad * cin * 2};
     const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)BN, 1};
     const cuuint32_t es[3] = {1, 1, 1};

@@ -24,7 +24,7 @@ import torch
 
 from . import _lib
 
-OP_CONV, OP_STEM, OP_MAXPOOL, OP_DWDECONV_ADD, OP_DCN = 1, 2, 3, 4, 5
+OP_CONV, OP_STEM, OP_MAXPOOL, OP_DWDECONV_ADD, OP_DCN, OP_IM2COL_W = 1, 2, 3, 4, 5, 6
 FLAG_RELU, FLAG_OUT_NCHW_F32, FLAG_OUT_F32, FLAG_TC = 1, 2, 4, 8
 F32, BF16 = 0, 1
 BN_EPS = 1e-5
@@ -158,6 +158,17 @@ class PlanBuilder:
     # ---- ops -------------------------------------------------------------------------------
     def stem(self, x: Sym, w, b, k, stride, pad, relu=True):
         co, ci = w.shape[0], w.shape[1]
+        if (self.use_tc and stride == 1 and k * ci <= 32 and co % 16 == 0 and pad == k // 2
+                and os.environ.get("CPB200_TC_STEM", "1") != "0"):
+            # tensor-core stem: gather the k horizontal taps of every pixel into 32 channels (one memory-bound
+            # pass), then a k x 1 conv with K = k * 32 runs on the halo-reuse tcgen05 kernel.
+            t = self._sym(32, x.H, x.W)
+            self._emit(_PendingOp(type=OP_IM2COL_W, flags=0, k=(1, k), stride=1, pad=(0, pad), weight=None,
+                                  bias=None, cout=32), [x], t)
+            w2 = torch.zeros(co, 32, k, 1, dtype=torch.float32, device=w.device)
+            # w2[o, s*ci + c, r, 0] = w[o, c, r, s]
+            w2[:, :k * ci, :, 0] = w.float().permute(0, 3, 1, 2).reshape(co, k * ci, k)
+            return self.conv([t], w2, b.float(), stride=1, relu=relu, pad_hw=(pad, 0))
         Ho = (x.H + 2 * pad - k) // stride + 1; Wo = (x.W + 2 * pad - k) // stride + 1
         y = self._sym(co, Ho, Wo)
         wp = self._dev(w.permute(2, 3, 1, 0).reshape(k * k * ci, co))
@@ -176,7 +187,7 @@ class PlanBuilder:
         H, W = srcs[0].H, srcs[0].W
         ph, pw = pad_hw if pad_hw is not None else (pad, pad)
         if out_map is None:
-            Ho = (H + 2 * pad - kh) // stride + 1; Wo = (W + 2 * pad - kw) // stride + 1
+            Ho = (H + 2 * ph - kh) // stride + 1; Wo = (W + 2 * pw - kw) // stride + 1
             Hd, Wd, sy, sx, oy, ox = Ho, Wo, 1, 1, 0, 0
         else:
             Hd, Wd, sy, sx, oy, ox, Ho, Wo = out_map

@@ -265,6 +265,23 @@ def test_dcn_zero_offset_identity():
     assert (2 * out - x).abs().max().item() < 1e-6
 
 
+def test_stem_tensor_core_path():
+    """7x7 stem lowered to im2col-W (32 ch) + 7x1 tcgen05 halo conv vs torch fp32 on bf16-rounded data."""
+    B, H, W = 2, 48, 40
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, 3, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(16, 3, 7, 7, generator=g) * 0.1).bfloat16().float(); b = torch.randn(16, generator=g)
+    ref = F.relu(F.conv2d(x, w, b, padding=3))
+    pb = _builder(B, "bf16", tc=True); pb.H, pb.W = H, W
+    y = pb.stem(pb.input(3), w.to(DEV), b.to(DEV), 7, 1, 3, relu=True)
+    assert [o.type for o in pb.ops] == [6, 1] and pb.ops[1].flags & 8
+    plan = pb.build(); plan.bind(x.to(DEV), {}); plan.run(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = _nchw(plan.tensor(y))
+    err = (got - ref).abs().max().item()
+    assert err <= 1e-2 * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16tc"])
 def test_dense_deconv_lowering(mode):
     """ConvTranspose2d(k4,s2,p1)+BN+ReLU (msra_resnet.py:168-193) lowered to four parity 2x2 convs."""
