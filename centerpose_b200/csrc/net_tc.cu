@@ -45,7 +45,7 @@ struct alignas(64) TcArgs {
   // deformable conv (DCN) only: A tiles are gathered by producer warps instead of TMA
   const __nv_bfloat16 *dcn_src;   // (B,H,W,Cin) bf16
   const float *dcn_om;            // (B,H,W,27) fp32: 18 offsets (dy,dx per tap) | 9 mask logits
-  int H, W, om_pitch;
+  int H, W, om_pitch, dcn_prefetch;
   int Hd, Wd, sy, sx, oy, ox;     // strided output mapping (dense ConvTranspose2d parity sub-convs)
   int out_ch_off, out_ch_total;   // NCHW fp32 output: channel slice of dst
 };
@@ -246,8 +246,23 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
         }
       };
+      // L1 prefetch of the corner lines two stages ahead: the register pipeline only covers half a stage of
+      // latency, and ~1/3 of the warp-level corner loads miss L1 (they touch 4 lines each)
+      auto prefetch = [&](int k) {
+        const int tap = k / slabs, c0 = (k - tap * slabs) << 6;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const DcnPrm q = s_prm[gw][tap][i * 4 + rsub];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(srcc + (size_t)(unsigned)q.off[c] + c0));
+        }
+      };
+      const bool do_pf = a.dcn_prefetch != 0;
+      if (do_pf) { prefetch(0); if (nk > 1) prefetch(1); }
       issue(0, 0, vA, wA);
       for (int k = 0; k < nk; ++k) {
+        if (do_pf && k + 2 < nk) prefetch(k + 2);
         issue(k, 1, vB, wB);
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
         const uint32_t sa = smem_base + stage * stage_bytes;
@@ -459,6 +474,7 @@ int tc_prepare_op(cpb200_op &op) {
   t->BN = BN; t->dcn = dcn;
   a.dcn_src = static_cast<const __nv_bfloat16 *>(op.src[0]); a.dcn_om = static_cast<const float *>(op.aux);
   a.H = op.H; a.W = op.W; a.om_pitch = op.aux_pitch > 0 ? op.aux_pitch : 27;
+  { const char *e = getenv("CPB200_DCN_PREFETCH"); a.dcn_prefetch = (e && e[0] == '0') ? 0 : 1; }
   a.Hd = op.Hd; a.Wd = op.Wd; a.sy = op.out_sy; a.sx = op.out_sx; a.oy = op.out_oy; a.ox = op.out_ox;
   a.n_tiles = (op.cout + BN - 1) / BN;
   a.cout = op.cout; a.cout_store = op.cout;

@@ -159,9 +159,11 @@ class PlanBuilder:
     def stem(self, x: Sym, w, b, k, stride, pad, relu=True):
         co, ci = w.shape[0], w.shape[1]
         if (self.use_tc and stride == 1 and k * ci <= 32 and co % 16 == 0 and pad == k // 2
-                and os.environ.get("CPB200_TC_STEM", "1") != "0"):
-            # tensor-core stem: gather the k horizontal taps of every pixel into 32 channels (one memory-bound
-            # pass), then a k x 1 conv with K = k * 32 runs on the halo-reuse tcgen05 kernel.
+                and os.environ.get("CPB200_TC_STEM", "0") == "1"):
+            # tensor-core stem (opt-in, CPB200_TC_STEM=1): gather the k horizontal taps of every pixel into 32
+            # channels, then a k x 1 conv with K = k * 32 runs on the halo-reuse tcgen05 kernel.  Correct
+            # (tests/test_net_gpu.py::test_stem_tensor_core_path) but measured SLOWER than the register-tiled
+            # CUDA-core stem at B=32 512x512 (1430 us vs 1045 us: 537 MB intermediate + 65 536 N=16 tiles), so off.
             t = self._sym(32, x.H, x.W)
             self._emit(_PendingOp(type=OP_IM2COL_W, flags=0, k=(1, k), stride=1, pad=(0, pad), weight=None,
                                   bias=None, cout=32), [x], t)

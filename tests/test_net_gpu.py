@@ -272,8 +272,12 @@ def test_stem_tensor_core_path():
     x = torch.randn(B, 3, H, W, generator=g).bfloat16().float()
     w = (torch.randn(16, 3, 7, 7, generator=g) * 0.1).bfloat16().float(); b = torch.randn(16, generator=g)
     ref = F.relu(F.conv2d(x, w, b, padding=3))
-    pb = _builder(B, "bf16", tc=True); pb.H, pb.W = H, W
-    y = pb.stem(pb.input(3), w.to(DEV), b.to(DEV), 7, 1, 3, relu=True)
+    os.environ["CPB200_TC_STEM"] = "1"
+    try:
+        pb = _builder(B, "bf16", tc=True); pb.H, pb.W = H, W
+        y = pb.stem(pb.input(3), w.to(DEV), b.to(DEV), 7, 1, 3, relu=True)
+    finally:
+        os.environ.pop("CPB200_TC_STEM", None)
     assert [o.type for o in pb.ops] == [6, 1] and pb.ops[1].flags & 8
     plan = pb.build(); plan.bind(x.to(DEV), {}); plan.run(torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
