@@ -33,6 +33,9 @@ def lib() -> ctypes.CDLL:
     L.cpb200_multi_pose_decode.restype = ctypes.c_int
     L.cpb200_multi_pose_decode.argtypes = [ctypes.c_void_p] * 7 + [ctypes.c_int] * 6 + \
         [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    L.cpb200_multi_pose_decode_affine.restype = ctypes.c_int
+    L.cpb200_multi_pose_decode_affine.argtypes = [ctypes.c_void_p] * 8 + [ctypes.c_int] * 6 + \
+        [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     L.cpb200_sigmoid_inplace.restype = ctypes.c_int
     L.cpb200_sigmoid_inplace.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     _bind_optional(L)

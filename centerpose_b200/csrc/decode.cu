@@ -42,6 +42,7 @@ struct DecodeParams {
   int B, H, W, J, K;
   int apply_sigmoid;
   float thresh;
+  const float *affine;   // optional (B,6): row-major 2x3 matrix applied to every (x,y) of image b
 };
 
 struct Smem {
@@ -494,8 +495,22 @@ __device__ void group_joint(Smem &s, const DecodeParams &p, int b, int j) {
                      (min_dist > __fmul_rn(fmaxf(__fsub_rn(bt, t), __fsub_rn(r, l)), 0.3f));   // :300-302
     const int row = 5 + 3 * J;
     float *o = p.out + ((size_t)b * K + pidx) * row;
-    o[5 + 2 * j] = rej ? kx : sx;
-    o[5 + 2 * j + 1] = rej ? ky : sy;
+    float ox = rej ? kx : sx, oy = rej ? ky : sy;
+    if (p.affine) {
+      // fused back-projection to image pixels (lib/utils/post_process.py:8-19 + image.py:19-24,63-66):
+      // [x', y'] = A(2x3) . [x, y, 1]
+      const float *A = p.affine + (size_t)b * 6;
+      const float a0 = __ldg(A), a1 = __ldg(A + 1), a2 = __ldg(A + 2), a3 = __ldg(A + 3), a4 = __ldg(A + 4), a5 = __ldg(A + 5);
+      const float tx = fmaf(a0, ox, fmaf(a1, oy, a2)), ty = fmaf(a3, ox, fmaf(a4, oy, a5));
+      ox = tx; oy = ty;
+      if (j == 0) {
+        const float l2 = fmaf(a0, l, fmaf(a1, t, a2)), t2 = fmaf(a3, l, fmaf(a4, t, a5));
+        const float r2 = fmaf(a0, r, fmaf(a1, bt, a2)), b2 = fmaf(a3, r, fmaf(a4, bt, a5));
+        l = l2; t = t2; r = r2; bt = b2;
+      }
+    }
+    o[5 + 2 * j] = ox;
+    o[5 + 2 * j + 1] = oy;
     o[5 + 2 * J + j] = ss;
     if (j == 0) { o[0] = l; o[1] = t; o[2] = r; o[3] = bt; o[4] = score; }
   }
@@ -576,11 +591,9 @@ extern "C" size_t cpb200_decode_workspace_bytes(int B, int J, int K) {
   return align_up(n * 4, 16) + align_up(n * 4, 16) + align_up((size_t)B * J * 4, 16);
 }
 
-extern "C" int cpb200_multi_pose_decode(const float *heat, const float *wh, const float *kps,
-                                        const float *reg, const float *hm_hp,
-                                        const float *hp_offset, float *out, int B, int H, int W,
-                                        int J, int K, int apply_sigmoid, void *workspace,
-                                        size_t workspace_bytes, void *stream) {
+static int decode_impl(const float *heat, const float *wh, const float *kps, const float *reg, const float *hm_hp,
+                       const float *hp_offset, const float *affine, float *out, int B, int H, int W, int J, int K,
+                       int apply_sigmoid, void *workspace, size_t workspace_bytes, void *stream) {
   if (!heat || !wh || !kps || !out) return cpb::fail(CPB200_ERR_ARG, "decode: null tensor pointer");
   if (!hm_hp)
     return cpb::fail(CPB200_ERR_ARG, "decode: hm_hp is required (the reference's decode.py:307 "
@@ -606,9 +619,29 @@ extern "C" int cpb200_multi_pose_decode(const float *heat, const float *wh, cons
   p.sync = reinterpret_cast<int *>(ws + 2 * align_up(n * 4, 16));
   p.B = B; p.H = H; p.W = W; p.J = J; p.K = K;
   p.apply_sigmoid = apply_sigmoid;
+  p.affine = affine;
   p.thresh = 0.1f;                                   // decode.py:267
   decode_kernel<<<B * (1 + J), TPB, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return cpb::check_launch("decode_kernel");
+}
+
+extern "C" int cpb200_multi_pose_decode(const float *heat, const float *wh, const float *kps,
+                                        const float *reg, const float *hm_hp,
+                                        const float *hp_offset, float *out, int B, int H, int W,
+                                        int J, int K, int apply_sigmoid, void *workspace,
+                                        size_t workspace_bytes, void *stream) {
+  return decode_impl(heat, wh, kps, reg, hm_hp, hp_offset, nullptr, out, B, H, W, J, K, apply_sigmoid, workspace,
+                     workspace_bytes, stream);
+}
+
+extern "C" int cpb200_multi_pose_decode_affine(const float *heat, const float *wh, const float *kps,
+                                               const float *reg, const float *hm_hp, const float *hp_offset,
+                                               const float *affine, float *out, int B, int H, int W, int J, int K,
+                                               int apply_sigmoid, void *workspace, size_t workspace_bytes,
+                                               void *stream) {
+  if (!affine) return cpb::fail(CPB200_ERR_ARG, "decode_affine: null affine");
+  return decode_impl(heat, wh, kps, reg, hm_hp, hp_offset, affine, out, B, H, W, J, K, apply_sigmoid, workspace,
+                     workspace_bytes, stream);
 }
 
 extern "C" int cpb200_sigmoid_inplace(float *x, size_t n, void *stream) {

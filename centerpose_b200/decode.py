@@ -43,10 +43,12 @@ def _prep(t, name, shape=None):
 
 
 def multi_pose_decode(heat, wh, kps, reg=None, hm_hp=None, hp_offset=None, K=100,
-                      apply_sigmoid=False, out=None):
+                      apply_sigmoid=False, out=None, affine=None):
     """Same contract as the reference (``decode.py:235-236``): ``heat``/``hm_hp`` already
     sigmoid'ed (unless ``apply_sigmoid=True`` — additive: the kernel then applies the logistic
     itself, replacing ``multi_pose.py:35-37``), returns ``(B, K, 5+3J)`` fp32 on the input device.
+    ``affine`` (additive): ``(B, 6)`` fp32 device tensor of per-image 2x3 matrices; when given, box corners
+    and keypoints come out in original-image pixels (``post_process`` fused, see :func:`affine_for_meta`).
     """
     heat = _prep(heat, "heat")
     if heat.dim() != 4:
@@ -73,12 +75,32 @@ def multi_pose_decode(heat, wh, kps, reg=None, hm_hp=None, hp_offset=None, K=100
     ws = _workspace(dev, B, J, K)
     ptr = lambda t: None if t is None else t.data_ptr()
     with torch.cuda.device(dev):
-        st = _lib.lib().cpb200_multi_pose_decode(
-            ptr(heat), ptr(wh), ptr(kps), ptr(reg), ptr(hm_hp), ptr(hp_offset), out.data_ptr(),
-            B, H, W, J, K, 1 if apply_sigmoid else 0, ws.data_ptr(), ws.numel(),
-            torch.cuda.current_stream(dev).cuda_stream)
+        if affine is None:
+            st = _lib.lib().cpb200_multi_pose_decode(
+                ptr(heat), ptr(wh), ptr(kps), ptr(reg), ptr(hm_hp), ptr(hp_offset), out.data_ptr(),
+                B, H, W, J, K, 1 if apply_sigmoid else 0, ws.data_ptr(), ws.numel(),
+                torch.cuda.current_stream(dev).cuda_stream)
+        else:
+            affine = _prep(affine, "affine", (B, 6))
+            st = _lib.lib().cpb200_multi_pose_decode_affine(
+                ptr(heat), ptr(wh), ptr(kps), ptr(reg), ptr(hm_hp), ptr(hp_offset), affine.data_ptr(),
+                out.data_ptr(), B, H, W, J, K, 1 if apply_sigmoid else 0, ws.data_ptr(), ws.numel(),
+                torch.cuda.current_stream(dev).cuda_stream)
     _lib.check(st, "multi_pose_decode")
     return out
+
+
+def affine_for_meta(metas, scale=1.0):
+    """Host helper: per-image 2x3 matrices (float32 (B,6)) that map output-grid coordinates to original-image
+    pixels — ``get_affine_transform(c, s, 0, (out_w, out_h), inv=1)`` (``lib/utils/image.py:27-60``) divided by
+    the test ``scale`` (``multi_pose.py:68-69``)."""
+    import numpy as np
+    from .image import get_affine_transform
+    rows = []
+    for m in metas:
+        t = get_affine_transform(m["c"], m["s"], 0, (m["out_width"], m["out_height"]), inv=1) / float(scale)
+        rows.append(np.asarray(t, np.float64).reshape(6))
+    return torch.from_numpy(np.stack(rows).astype(np.float32))
 
 
 def sigmoid_(x: torch.Tensor) -> torch.Tensor:

@@ -246,5 +246,19 @@ class MultiPoseDetector(BaseDetector):
         host = dets.cpu().numpy()
         return [self.post_process(torch.from_numpy(host[i:i + 1]), metas[i]) for i in range(host.shape[0])]
 
+    @torch.no_grad()
+    def run_batch_fused(self, images: torch.Tensor, metas, scale=1.0):
+        """Like ``run_batch(images, metas)`` but with ``post_process`` fused into the decode kernel: returns a
+        ``(B, K, 56)`` float32 numpy array already in original-image pixels (one D2H copy, no host math)."""
+        from .decode import affine_for_meta
+        images = images.to(torch.device("cuda"), non_blocking=True)
+        hm, wh, hps, reg, hm_hp, hp_offset = self.model(images)
+        cfg = self.cfg
+        aff = affine_for_meta(metas, scale).to(images.device, non_blocking=True)
+        dets = multi_pose_decode(hm, wh, hps, reg=reg if cfg.LOSS.REG_OFFSET else None, hm_hp=hm_hp,
+                                 hp_offset=hp_offset if cfg.LOSS.REG_HP_OFFSET else None,
+                                 K=cfg.TEST.TOPK, apply_sigmoid=True, affine=aff)
+        return dets.cpu().numpy()
+
 
 detector_factory = {"multi_pose": MultiPoseDetector}     # detector_factory.py:5-7

@@ -69,6 +69,19 @@ int cpb200_multi_pose_decode(const float *heat, const float *wh, const float *kp
                              int apply_sigmoid, void *workspace, size_t workspace_bytes,
                              void *stream);
 
+/* Same, with the detector's back-projection fused into the epilogue: replaces, in addition,
+ * lib/detectors/multi_pose.py:62-71 `post_process` -> lib/utils/post_process.py:8-19
+ * `multi_pose_post_process` -> lib/utils/image.py:19-24,63-66 (`transform_preds` / `affine_transform`, a Python
+ * loop over 1 900 points per image in the reference).  `affine` is (B,6) fp32 on the device: per image the
+ * row-major 2x3 inverse crop matrix of `get_affine_transform(c, s, 0, (out_w, out_h), inv=1)`
+ * (lib/utils/image.py:27-60), optionally pre-divided by the test scale.  Every (x,y) of the box corners and
+ * keypoints is mapped to original-image pixels; scores are untouched. */
+int cpb200_multi_pose_decode_affine(const float *heat, const float *wh, const float *kps,
+                                    const float *reg, const float *hm_hp, const float *hp_offset,
+                                    const float *affine, float *out, int B, int H, int W, int J, int K,
+                                    int apply_sigmoid, void *workspace, size_t workspace_bytes,
+                                    void *stream);
+
 /* In-place logistic on n floats — lib/detectors/multi_pose.py:35-37 `hm.sigmoid_()`. */
 int cpb200_sigmoid_inplace(float *x, size_t n, void *stream);
 

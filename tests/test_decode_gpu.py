@@ -120,6 +120,27 @@ def test_decode_full_size_properties():
     _assert_same(a[:4].cpu().numpy(), ref)
 
 
+def test_decode_fused_post_process():
+    """decode + fused back-projection == oracle decode followed by the oracle's multi_pose_post_process
+    (which is pinned against the reference).  Tolerance 2e-3 px on coordinates up to ~2000 px (fp32 affine on the
+    device vs the reference's float64)."""
+    from centerpose_b200 import multi_pose_decode
+    from centerpose_b200.decode import affine_for_meta
+    from oracle import post_process_ref
+    B, H, W, K = 3, 128, 128, 100
+    inp = decode_ref.synth_decode_inputs(B, H, W, seed=55, kind="smooth")
+    metas = [post_process_ref.make_meta(480, 640, 1.0, True), post_process_ref.make_meta(1080, 1920, 1.0, True),
+             post_process_ref.make_meta(333, 500, 1.0, True)]
+    t = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    got = multi_pose_decode(t["heat"], t["wh"], t["kps"], t["reg"], t["hm_hp"], t["hp_offset"], K=K,
+                            affine=affine_for_meta(metas).cuda()).cpu().numpy()
+    ref = _oracle(inp, K)
+    for b in range(B):
+        want = post_process_ref.multi_pose_post_process(ref[b:b + 1].copy(), [metas[b]["c"]], [metas[b]["s"]],
+                                                        metas[b]["out_height"], metas[b]["out_width"])[0][1]
+        assert np.abs(got[b] - want).max() <= 2e-3, np.abs(got[b] - want).max()
+
+
 def test_decode_error_behaviour():
     from centerpose_b200 import multi_pose_decode
     inp = decode_ref.synth_decode_inputs(1, 8, 8, seed=2)

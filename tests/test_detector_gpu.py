@@ -1,0 +1,89 @@
+"""GPU tests of the detector mirror (run / process / post_process / merge_outputs, flip test, batch API)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _detector(precision="fp32", flip=False, nms=False):
+    from centerpose_b200.config import default_cfg
+    from centerpose_b200.detector import detector_factory
+    from oracle.init_recipe import conditioned_state_dict
+    cfg = default_cfg("dla_34")
+    cfg.TEST.FLIP_TEST = flip
+    cfg.TEST.NMS = nms
+    det = detector_factory[cfg.TEST.TASK](cfg)
+    sd = conditioned_state_dict(det.model.state_dict(), 317)
+    det.model.load_state_dict(sd)
+    det.model.set_precision(precision)
+    return det, sd, cfg
+
+
+def test_flip_helpers_match_reference_golden():
+    """Device-side flip_lr / flip_lr_off == the reference's numpy round-trip versions (lib/models/utils.py:27-47)."""
+    g = np.load(os.path.join(GOLD, "flip.npz"))
+    det, _, _ = _detector()
+    hm_hp = torch.from_numpy(g["hm_hp"]).cuda(); hps = torch.from_numpy(g["hps"]).cuda()
+    assert np.array_equal(torch.flip(hm_hp, [3]).cpu().numpy(), g["flip_tensor"])
+    assert np.array_equal(det._flip_lr(hm_hp).cpu().numpy(), g["flip_lr"])
+    assert np.array_equal(det._flip_lr_off(hps).cpu().numpy(), g["flip_lr_off"])
+
+
+def _oracle_run(det, sd, cfg, image, flip):
+    from oracle import decode_ref, dla_ref, post_process_ref
+    images, meta = det.pre_process(image, 1.0)
+    hm, wh, hps, reg, hm_hp, hp_off = dla_ref.forward(sd, images)
+    hm = hm.sigmoid(); hm_hp = hm_hp.sigmoid()
+    if flip:
+        idx = list(range(17))
+        for a, b in det.flip_idx:
+            idx[a], idx[b] = idx[b], idx[a]
+        fl = lambda t: torch.flip(t, [3])
+        hm = (hm[0:1] + fl(hm[1:2])) / 2
+        wh = (wh[0:1] + fl(wh[1:2])) / 2
+        h2 = fl(hps[1:2]).view(1, 17, 2, *hps.shape[2:]).clone(); h2[:, :, 0] *= -1
+        hps = (hps[0:1] + h2[:, idx].reshape(1, 34, *hps.shape[2:])) / 2
+        hm_hp = (hm_hp[0:1] + fl(hm_hp[1:2])[:, idx]) / 2
+        reg = reg[0:1]; hp_off = hp_off[0:1]
+    dets = decode_ref.multi_pose_decode(hm.numpy(), wh.numpy(), hps.numpy(), reg.numpy(), hm_hp.numpy(), hp_off.numpy(), K=100)
+    return post_process_ref.detector_post_process(dets, meta, 1.0)[1]
+
+
+@pytest.mark.parametrize("flip", [False, True])
+def test_detector_run_matches_oracle_pipeline(flip):
+    from tests.util import match_rows
+    det, sd, cfg = _detector("fp32", flip=flip)
+    rng = np.random.RandomState(7)
+    image = rng.randint(0, 256, size=(360, 480, 3)).astype(np.uint8)
+    ret = det.run(image)
+    assert set(ret) == {"results", "tot", "load", "pre", "net", "dec", "post", "merge"}
+    rows = np.asarray(ret["results"][1], dtype=np.float32)
+    assert rows.shape == (100, 56)
+    want = _oracle_run(det, sd, cfg, image, flip)
+    frac_rows, frac_elems = match_rows(rows, want, tol=2e-3, box_tol=5e-2)
+    assert frac_rows >= 0.9 and frac_elems >= 0.97, (frac_rows, frac_elems)
+
+
+def test_run_batch_and_fused_post_process_agree():
+    from oracle import post_process_ref
+    det, sd, cfg = _detector("bf16")
+    x = torch.randn(3, 3, 512, 512, generator=torch.Generator().manual_seed(1))
+    metas = [post_process_ref.make_meta(480, 640), post_process_ref.make_meta(720, 1280), post_process_ref.make_meta(512, 512)]
+    a = det.run_batch(x, metas)
+    b = det.run_batch_fused(x, metas)
+    assert b.shape == (3, 100, 56)
+    for i in range(3):
+        assert np.abs(np.asarray(a[i][1]) - b[i]).max() <= 2e-3
+
+
+def test_merge_outputs_soft_nms_path():
+    det, _, _ = _detector("bf16", nms=True)
+    rng = np.random.RandomState(0)
+    d = {1: rng.uniform(0, 100, size=(100, 56)).astype(np.float32)}
+    d[1][:, 2:4] = d[1][:, 0:2] + 30
+    out = det.merge_outputs([d])
+    assert len(out) == 100 and len(out[0]) == 56
