@@ -31,6 +31,8 @@ IMG = 512
 B_PER_GPU = 32
 K_DET = 100
 GFLOP_PER_IMG = 80.48            # SURVEY.md §8d (2*MAC of conv+deconv+DCN+heads, DLA-34 @512)
+ARCH_GFLOP = {"dla_34": 80.48, "res_50": 86.85}
+ARCH_BATCH = {"dla_34": 32, "res_50": 16}           # BASELINE.json configs[1] / configs[2] (128 over 8 GPUs)
 DECODE_BYTES_PER_IMG = 1230848
 METRIC = "images/sec 512x512 DLA-34"
 
@@ -112,7 +114,7 @@ def cpu_reference_step(sd, x):
     """The reference's CPU path restated by the oracle: forward -> sigmoid -> multi_pose_decode
     (lib/models/model.py:57-59, lib/detectors/multi_pose.py:32-55, lib/models/decode.py:235-308)."""
     from oracle import decode_ref, dla_ref
-    hm, wh, hps, reg, hm_hp, hp_off = dla_ref.forward(sd, x)
+    hm, wh, hps, reg, hm_hp, hp_off = dla_ref.forward(sd, x, arch=ARCH)
     hm = hm.sigmoid_(); hm_hp = hm_hp.sigmoid_()
     return decode_ref.multi_pose_decode(hm.numpy(), wh.numpy(), hps.numpy(), reg.numpy(), hm_hp.numpy(),
                                         hp_off.numpy(), K=K_DET)
@@ -176,9 +178,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CPB200_PRECISION", "bf16"), choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--arch", default="dla_34", choices=sorted(ARCH_GFLOP), help="dla_34 = the headline config")
+    ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global ARCH, GFLOP_PER_IMG, B_PER_GPU, METRIC
+    ARCH = args.arch; GFLOP_PER_IMG = ARCH_GFLOP[ARCH]; B_PER_GPU = args.batch or ARCH_BATCH[ARCH]
+    args.batch = B_PER_GPU
+    METRIC = "images/sec 512x512 " + {"dla_34": "DLA-34", "res_50": "ResNet-50"}[ARCH]
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)

@@ -86,58 +86,56 @@ class BaseDetector(object):
     def show_results(self, debugger, image, results):
         raise NotImplementedError
 
-    def run(self, image_or_path_or_tensor, meta=None):
-        """base_detector.py:79-140 — same inputs (ndarray / path / pre-processed dict), same result
-        dict: ``{'results': {1: rows}, 'tot','load','pre','net','dec','post','merge'}``."""
-        load_time = pre_time = net_time = dec_time = post_time = merge_time = tot_time = 0
-        start_time = time.time()
-        pre_processed = False
-        if isinstance(image_or_path_or_tensor, np.ndarray):
-            image = image_or_path_or_tensor
-        elif isinstance(image_or_path_or_tensor, str):
-            image = cv2.imread(image_or_path_or_tensor)
+    # -- run(): orchestration + the reference's seven wall-clock timers -----------------------------
+    def _load(self, source):
+        """ndarray (BGR HWC uint8) | path | pre-processed dict -> (image, pre_processed dict or None)."""
+        if isinstance(source, np.ndarray):
+            return source, None
+        if isinstance(source, str):
+            image = cv2.imread(source)
             if image is None:
-                raise FileNotFoundError(image_or_path_or_tensor)
-        else:
-            image = image_or_path_or_tensor["image"][0].numpy()
-            pre_processed_images = image_or_path_or_tensor
-            pre_processed = True
-        loaded_time = time.time()
-        load_time += loaded_time - start_time
-        detections = []
+                raise FileNotFoundError(source)
+            return image, None
+        return source["image"][0].numpy(), source
+
+    def run(self, image_or_path_or_tensor, meta=None):
+        """Same contract as ``base_detector.py:79-140``: returns ``{'results': {1: rows}, 'tot', 'load', 'pre',
+        'net', 'dec', 'post', 'merge'}`` (seconds, CUDA-synchronised like the reference's timers)."""
+        clock = {k: 0.0 for k in ("load", "pre", "net", "dec", "post", "merge", "tot")}
+        sync = torch.cuda.synchronize
+        t_start = time.time()
+        image, prepared = self._load(image_or_path_or_tensor)
+        t_prev = time.time()
+        clock["load"] = t_prev - t_start
+        per_scale = []
         for scale in self.scales:
-            scale_start_time = time.time()
-            if not pre_processed:
+            if prepared is None:
                 images, meta = self.pre_process(image, scale, meta)
             else:
-                images = pre_processed_images["images"][scale][0]
-                meta = pre_processed_images["meta"][scale]
-                meta = {k: v.numpy()[0] for k, v in meta.items()}
+                images = prepared["images"][scale][0]
+                meta = {k: v.numpy()[0] for k, v in prepared["meta"][scale].items()}
             images = images.to(torch.device("cuda"))
-            torch.cuda.synchronize()
-            pre_process_time = time.time()
-            pre_time += pre_process_time - scale_start_time
-            output, dets, forward_time = self.process(images, return_time=True)
-            torch.cuda.synchronize()
-            net_time += forward_time - pre_process_time
-            decode_time = time.time()
-            dec_time += decode_time - forward_time
+            sync()
+            t_now = time.time(); clock["pre"] += t_now - t_prev; t_prev = t_now
+            output, dets, t_forward = self.process(images, return_time=True)
+            sync()
+            clock["net"] += t_forward - t_prev
+            t_now = time.time(); clock["dec"] += t_now - t_forward; t_prev = t_now
             if self.cfg.DEBUG >= 2:
                 self.debug(None, images, dets, output, scale)
-            dets = self.post_process(dets, meta, scale)
-            torch.cuda.synchronize()
-            post_process_time = time.time()
-            post_time += post_process_time - decode_time
-            detections.append(dets)
-        results = self.merge_outputs(detections)
-        torch.cuda.synchronize()
-        end_time = time.time()
-        merge_time += end_time - post_process_time
-        tot_time += end_time - start_time
+            per_scale.append(self.post_process(dets, meta, scale))
+            sync()
+            t_now = time.time(); clock["post"] += t_now - t_prev; t_prev = t_now
+        results = self.merge_outputs(per_scale)
+        sync()
+        t_end = time.time()
+        clock["merge"] = t_end - t_prev
+        clock["tot"] = t_end - t_start
         if self.cfg.DEBUG >= 1:
             self.show_results(None, image, results)
-        return {"results": {1: results}, "tot": tot_time, "load": load_time, "pre": pre_time,
-                "net": net_time, "dec": dec_time, "post": post_time, "merge": merge_time}
+        out = {"results": {1: results}}
+        out.update(clock)
+        return out
 
 
 def _swap_pairs(C, pairs, device):
