@@ -33,6 +33,8 @@ K_DET = 100
 GFLOP_PER_IMG = 80.48            # SURVEY.md §8d (2*MAC of conv+deconv+DCN+heads, DLA-34 @512)
 ARCH_GFLOP = {"dla_34": 80.48, "res_50": 86.85}
 ARCH_BATCH = {"dla_34": 32, "res_50": 16}           # BASELINE.json configs[1] / configs[2] (128 over 8 GPUs)
+# dram__bytes_read+write summed over the 97 launches of one DLA-34 B=32 step (ncu, profiles/r01_traffic_per_kernel_v13.txt)
+NCU_TRAFFIC_BYTES = {("dla_34", 32): 9.534e9}
 DECODE_BYTES_PER_IMG = 1230848
 METRIC = "images/sec 512x512 DLA-34"
 
@@ -304,7 +306,7 @@ def main():
     peaks = measured_peaks()
     tf = GFLOP_PER_IMG * B / (ms_net * 1e-3) / 1e3
     roof = {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-            "frac": tf / peaks["bf16_tflops_sustained"], "traffic": None,
+            "frac": tf / peaks["bf16_tflops_sustained"], "traffic": NCU_TRAFFIC_BYTES.get((ARCH, B)),
             "kernel": "conv/DCN/head op program (all launches of one forward)", "ms_per_launch_set": ms_net,
             "peak_source": peaks["source"] + " sustained cuBLAS bf16"}
     dec_gbs = DECODE_BYTES_PER_IMG * B / (ms_dec * 1e-3) / 1e9

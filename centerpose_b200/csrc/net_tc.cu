@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
       }
       uint4 vA[2][4], vB[2][4];
       uint32_t wA[2][4], wB[2][4];
-      auto issue = [&](int k, int half, uint4 (&v)[2][4], uint32_t (&w)[2][4]) {
-        const int tap = k / slabs, c0 = (k - tap * slabs) << 6;
+      // (tap, channel offset) of a stage are tracked incrementally — no integer division in the hot loop
+      auto issue = [&](int tap, int c0, int half, uint4 (&v)[2][4], uint32_t (&w)[2][4]) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const DcnPrm q = s_prm[gw][tap][(half * 2 + i) * 4 + rsub];
@@ -246,32 +246,23 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
         }
       };
-      // L1 prefetch of the corner lines two stages ahead: the register pipeline only covers half a stage of
-      // latency, and ~1/3 of the warp-level corner loads miss L1 (they touch 4 lines each)
-      auto prefetch = [&](int k) {
-        const int tap = k / slabs, c0 = (k - tap * slabs) << 6;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const DcnPrm q = s_prm[gw][tap][i * 4 + rsub];
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(srcc + (size_t)(unsigned)q.off[c] + c0));
-        }
-      };
-      const bool do_pf = a.dcn_prefetch != 0;
-      if (do_pf) { prefetch(0); if (nk > 1) prefetch(1); }
-      issue(0, 0, vA, wA);
+      int tap_c = 0, c0_c = 0;            // current stage
+      int tap_n = 0, c0_n = 64;           // next stage
+      if (c0_n >= Cin) { c0_n = 0; tap_n = 1; }
+      issue(tap_c, c0_c, 0, vA, wA);
       for (int k = 0; k < nk; ++k) {
-        if (do_pf && k + 2 < nk) prefetch(k + 2);
-        issue(k, 1, vB, wB);
+        issue(tap_c, c0_c, 1, vB, wB);
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
         const uint32_t sa = smem_base + stage * stage_bytes;
         blend_store(sa, 0, vA, wA);
-        if (k + 1 < nk) issue(k + 1, 0, vA, wA);
+        if (k + 1 < nk) issue(tap_n, c0_n, 0, vA, wA);
         blend_store(sa, 1, vB, wB);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive(full0 + 8 * stage);
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        tap_c = tap_n; c0_c = c0_n;
+        c0_n += 64;
+        if (c0_n >= Cin) { c0_n = 0; ++tap_n; }
       }
     }
   } else {
@@ -474,8 +465,7 @@ int tc_prepare_op(cpb200_op &op) {
   t->BN = BN; t->dcn = dcn;
   a.dcn_src = static_cast<const __nv_bfloat16 *>(op.src[0]); a.dcn_om = static_cast<const float *>(op.aux);
   a.H = op.H; a.W = op.W; a.om_pitch = op.aux_pitch > 0 ? op.aux_pitch : 27;
-  // L1 prefetch two stages ahead measured slower (dcn64 312 -> 355 us): opt-in only
-  { const char *e = getenv("CPB200_DCN_PREFETCH"); a.dcn_prefetch = (e && e[0] == '1') ? 1 : 0; }
+  a.dcn_prefetch = 0;   // (an L1 prefetch two stages ahead was measured slower, dcn64 312 -> 355 us, and removed)
   a.Hd = op.Hd; a.Wd = op.Wd; a.sy = op.out_sy; a.sx = op.out_sx; a.oy = op.out_oy; a.ox = op.out_ox;
   a.n_tiles = (op.cout + BN - 1) / BN;
   a.cout = op.cout; a.cout_store = op.cout;
