@@ -63,7 +63,7 @@ def _dla_up_plan():
     return stages
 
 
-def build_params() -> nn.Module:
+def build_params(cfg=None) -> nn.Module:
     root = nn.Module()
     attach(root, "base.base_layer.0", conv(3, CH[0], 7, 1, 3))
     attach(root, "base.base_layer.1", bn(CH[0]))

@@ -21,7 +21,7 @@ EXP = 4                               # Bottleneck.expansion
 DECONV = [256, 256, 256]              # msra_resnet.py:131-135
 
 
-def build_params() -> nn.Module:
+def build_params(cfg=None) -> nn.Module:
     root = nn.Module()
     attach(root, "conv1", conv(3, 64, 7, 2, 3)); attach(root, "bn1", bn(64))
     inplanes = 64

@@ -435,6 +435,28 @@ __global__ void __launch_bounds__(256) dwdeconv_add_kernel(const T *__restrict__
   }
 }
 
+// ---- nearest-neighbour upsample x f (+ skip add)(+ReLU), NHWC ----
+// out[b,ho,wo,c] = act(skip[b,ho,wo,c] + x[b,ho/f,wo/f,c])     (HRNet fuse_layers, pose_higher_hrnet.py:186-187,224-232)
+// Thread = 4 channels of one output pixel; f is a power of two (shift).
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_add_kernel(const T *__restrict__ x, const T *__restrict__ skip, T *__restrict__ y,
+                                                           long long total, int H, int W, int C4, int Ho, int Wo, int sh, int relu) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long long p = i / C4;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float4 v = Act<T>::ld4(x + ((((size_t)b * H + (ho >> sh)) * W + (wo >> sh)) * C4 + c4) * 4);
+    if (skip) {
+      const float4 s4 = Act<T>::ld4(skip + (size_t)i * 4);
+      v.x += s4.x; v.y += s4.y; v.z += s4.z; v.w += s4.w;
+    }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    Act<T>::st4(y + (size_t)i * 4, v);
+  }
+}
+
 template <typename T, bool DCN>
 int launch_conv(const cpb200_op &op, cudaStream_t st) {
   ConvArgs a;
@@ -477,24 +499,29 @@ int run_op_simt(const cpb200_op &op, cudaStream_t st) {
     case CPB200_OP_STEM: {
       const int cin = op.cin[0];
       const size_t smem = (size_t)op.kh * op.kw * cin * op.cout * sizeof(float);
-      if (cin > 4 || smem > 48 * 1024 || op.kw != 7) return cpb::fail(CPB200_ERR_ARG, "stem: unsupported shape");
+      if (cin > 4 || smem > 48 * 1024 || (op.kw != 7 && op.kw != 3)) return cpb::fail(CPB200_ERR_ARG, "stem: unsupported shape");
       const int relu = (op.flags & CPB200_FLAG_RELU) ? 1 : 0;
       // (COUT, PX) register tiles: 16 couts x 4 pixels, 64 couts x 1 pixel
-#define STEM_LAUNCH(CO, PX, ST)                                                                              \
+#define STEM_LAUNCH(CO, PX, ST) STEM_LAUNCH_K(CO, PX, ST, 7)
+#define STEM_LAUNCH_K(CO, PX, ST, KW)                                                                            \
   {                                                                                                          \
     if (op.Wo % PX) return cpb::fail(CPB200_ERR_ARG, "stem: output width %d not a multiple of %d", op.Wo, PX); \
     const long long M = (long long)op.B * op.Ho * (op.Wo / PX);                                              \
-    stem_kernel<T, CO, PX, ST, 7><<<(unsigned)((M + 127) / 128), 128, smem, st>>>(                           \
+    stem_kernel<T, CO, PX, ST, KW><<<(unsigned)((M + 127) / 128), 128, smem, st>>>(                           \
         static_cast<const float *>(op.src[0]), static_cast<T *>(op.dst), static_cast<const float *>(op.weight), \
         op.bias, op.B, cin, op.H, op.W, op.Ho, op.Wo, op.kh, op.pad_h, op.pad_w, relu);                      \
   }
-      if (op.cout == 16 && op.stride == 1) STEM_LAUNCH(16, 4, 1)
+      if (op.kw == 3) {                               // HRNet conv1 (pose_higher_hrnet.py:243-244)
+        if (op.cout == 64 && op.stride == 2) STEM_LAUNCH_K(64, 1, 2, 3)
+        else return cpb::fail(CPB200_ERR_ARG, "stem 3x3: cout %d / stride %d unsupported", op.cout, op.stride);
+      } else if (op.cout == 16 && op.stride == 1) STEM_LAUNCH(16, 4, 1)
       else if (op.cout == 16 && op.stride == 2) STEM_LAUNCH(16, 4, 2)
       else if (op.cout == 32 && op.stride == 2) STEM_LAUNCH(32, 2, 2)
       else if (op.cout == 64 && op.stride == 2) STEM_LAUNCH(64, 1, 2)
       else if (op.cout == 64 && op.stride == 1) STEM_LAUNCH(64, 1, 1)
       else return cpb::fail(CPB200_ERR_ARG, "stem: cout %d / stride %d unsupported", op.cout, op.stride);
 #undef STEM_LAUNCH
+#undef STEM_LAUNCH_K
       return cpb::check_launch("stem_kernel");
     }
     case CPB200_OP_IM2COL_W: {
@@ -522,6 +549,18 @@ int run_op_simt(const cpb200_op &op, cudaStream_t st) {
           static_cast<const T *>(op.aux), static_cast<T *>(op.dst), static_cast<const float *>(op.weight),
           op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h);
       return cpb::check_launch("dwdeconv_add_kernel");
+    }
+    case CPB200_OP_UPSAMPLE_ADD: {
+      const int f = op.stride;
+      int sh = 0;
+      while ((1 << sh) < f) ++sh;
+      if (f < 1 || (1 << sh) != f || op.Ho != op.H * f || op.Wo != op.W * f || op.cin[0] % 4)
+        return cpb::fail(CPB200_ERR_ARG, "upsample_add: factor %d must be a power of two, C %% 4 == 0", f);
+      const long long total = (long long)op.B * op.Ho * op.Wo * (op.cin[0] / 4);
+      const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
+      upsample_add_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(op.src[0]), static_cast<const T *>(op.aux),
+          static_cast<T *>(op.dst), total, op.H, op.W, op.cin[0] / 4, op.Ho, op.Wo, sh, (op.flags & CPB200_FLAG_RELU) ? 1 : 0);
+      return cpb::check_launch("upsample_add_kernel");
     }
     default: return cpb::fail(CPB200_ERR_ARG, "unknown op type %d", op.type);
   }

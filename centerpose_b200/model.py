@@ -24,10 +24,16 @@ def _res_arch():
     return _res
 
 
+def _hrnet_arch():
+    from .archs import hrnet as _hr
+    return _hr
+
+
 _backbone_factory = {
-    # arch name -> (module with build_params()/lower(), feature channels)   model.py:24-38
+    # arch name -> (module with build_params(cfg)/lower(), feature channels or None = ask the module)   model.py:24-38
     "dla": lambda n: (_dla, 64) if n == 34 else None,
     "res": lambda n: (_res_arch(), 256) if n == 50 else None,
+    "hrnet": lambda n: (_hrnet_arch(), None),
 }
 
 
@@ -56,10 +62,12 @@ class BackBoneWithHead(nn.Module):
         arch_name = arch[:arch.find("_")] if "_" in arch else arch
         if arch_name not in _backbone_factory or _backbone_factory[arch_name](num_layers) is None:
             raise KeyError(f"centerpose_b200: backbone {arch!r} is not implemented "
-                           f"(available: dla_34, res_50)")
+                           f"(available: dla_34, res_50, hrnet)")
         self._arch_mod, feat_c = _backbone_factory[arch_name](num_layers)
+        if feat_c is None:
+            feat_c = self._arch_mod.feature_channels(cfg)
         self.arch = arch
-        self.backbone_model = self._arch_mod.build_params()
+        self.backbone_model = self._arch_mod.build_params(cfg)
         inter = int(getattr(cfg.MODEL, "INTERMEDIATE_CHANNEL", feat_c))
         if inter != feat_c:
             raise ValueError(f"MODEL.INTERMEDIATE_CHANNEL={inter} but {arch} produces {feat_c} channels")

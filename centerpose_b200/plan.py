@@ -24,7 +24,7 @@ import torch
 
 from . import _lib
 
-OP_CONV, OP_STEM, OP_MAXPOOL, OP_DWDECONV_ADD, OP_DCN, OP_IM2COL_W = 1, 2, 3, 4, 5, 6
+OP_CONV, OP_STEM, OP_MAXPOOL, OP_DWDECONV_ADD, OP_DCN, OP_IM2COL_W, OP_UPSAMPLE_ADD = 1, 2, 3, 4, 5, 6, 7
 FLAG_RELU, FLAG_OUT_NCHW_F32, FLAG_OUT_F32, FLAG_TC = 1, 2, 4, 8
 F32, BF16 = 0, 1
 BN_EPS = 1e-5
@@ -230,6 +230,13 @@ class PlanBuilder:
                               weight=wp, bias=None, cout=C), [x], y, [skip])
         return y
 
+    def upsample_add(self, x: Sym, skip: Optional[Sym], f: int, relu=False):
+        """nearest-neighbour upsample x f of ``x`` (+ skip)(+ReLU)   (pose_higher_hrnet.py:186-187,224-232)."""
+        y = self._sym(x.C, x.H * f, x.W * f)
+        self._emit(_PendingOp(type=OP_UPSAMPLE_ADD, flags=FLAG_RELU if relu else 0, k=(1, 1), stride=f, pad=(0, 0),
+                              weight=None, bias=None, cout=x.C), [x], y, [skip])
+        return y
+
     def dcn(self, x: Sym, w, b, om_w, om_b, relu=True):
         """DCN module (dcn_v2.py:117-127) with BN already folded into (w, b)."""
         # offset/mask conv: 27 channels padded to 32 so every pixel row is 128 bytes (vector stores / loads)
@@ -291,7 +298,7 @@ class Plan:
             ex = po.extra
             if po.type == OP_CONV and ex and ex[0] is not None:
                 o.res = ex[0].buf.data_ptr()
-            if po.type in (OP_DCN, OP_DWDECONV_ADD) and ex and ex[0] is not None:
+            if po.type in (OP_DCN, OP_DWDECONV_ADD, OP_UPSAMPLE_ADD) and ex and ex[0] is not None:
                 o.aux = ex[0].buf.data_ptr()
                 o.aux_pitch = ex[0].C
             if po.weight is not None:

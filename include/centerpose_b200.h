@@ -112,8 +112,10 @@ enum cpb200_op_type {
   CPB200_OP_MAXPOOL = 3,     /* k x k / stride s / pad p max-pool, NHWC                                     */
   CPB200_OP_DWDECONV_ADD = 4,/* depthwise ConvTranspose2d(k=2f,s=f,p=f/2) (+ skip add), NHWC  (IDAUp up_*) */
   CPB200_OP_DCN = 5,         /* modulated deformable 3x3 conv (DCNv2 forward) (+bias)(+ReLU)                */
-  CPB200_OP_IM2COL_W = 6     /* NCHW fp32 image -> NHWC act: channel s*cin+c = x[c, h, w+s-pad_w], s < kw, zero-padded
+  CPB200_OP_IM2COL_W = 6,    /* NCHW fp32 image -> NHWC act: channel s*cin+c = x[c, h, w+s-pad_w], s < kw, zero-padded
                                 to `cout` channels.  Turns the 7x7 stem into a 7x1 tensor-core conv (K = 7 x 32).   */
+  CPB200_OP_UPSAMPLE_ADD = 7 /* nearest-neighbour upsample x `stride` (power of two) of src[0] (+ aux skip add)(+ReLU),
+                                NHWC  (HRNet fuse_layers, pose_higher_hrnet.py:186-187,224-232)                     */
 };
 /* A dense ConvTranspose2d(k4,s2,p1) (msra_resnet.py:168-193) is lowered by the host into four
  * 2x2 CONV ops, one per output parity, using pad_h/pad_w and the strided-output fields below. */
@@ -140,7 +142,7 @@ typedef struct cpb200_op {
   int32_t aux_pitch;         /* DCN: channel pitch of the offset/mask tensor (27, or 32 when padded for 16-byte rows) */
   const void *src[4];        /* inputs (NHWC act_dtype; STEM: NCHW fp32) */
   const void *res;           /* optional residual, same shape/dtype as the NHWC output */
-  const void *aux;           /* DCN: offset/mask tensor (B,H,W,aux_pitch) fp32, channels [0,18) offsets, [18,27) mask; DWDECONV_ADD: skip */
+  const void *aux;           /* DCN: offset/mask tensor (B,H,W,aux_pitch) fp32, channels [0,18) offsets, [18,27) mask; DWDECONV_ADD / UPSAMPLE_ADD: skip */
   void *dst;
   const void *weight;        /* packed by centerpose_b200/plan.py, layout per op type */
   const float *bias;         /* fp32 [cout] (BatchNorm folded), may be NULL */

@@ -21,7 +21,8 @@ exercised.  This recipe keeps the architecture and shapes and only changes the V
                                  amplification is 1.7 and fp32-vs-fp64 noise is 2e-6.  Large data-dependent
                                  offsets (gain 1.5, many samples out of bounds) are covered at op level
                                  (tests/test_net_gpu.py::test_dcn_op_matches_oracle).
-  * BatchNorm                    weight ~ U(0.5,1.5) (U(0.1,0.3) for a bottleneck's last ``bn3``), bias ~ N(0,0.1),
+  * BatchNorm                    weight ~ U(0.5,1.5) (U(0.1,0.3) for a bottleneck's last ``bn3`` and an HRNet branch
+                                 block's last ``bn2``; U(0.2,0.6) inside HRNet ``fuse_layers``), bias ~ N(0,0.1),
                                  mean ~ N(0,0.1), var ~ U(0.5,1.5)
   * conv / DCN biases            ~ N(0, 0.1)
   * head final 1x1 (``.2``)      per-head gain so logits/regressions have realistic spread;
@@ -73,7 +74,12 @@ def conditioned_state_dict(template: "OrderedDict[str, torch.Tensor]", seed: int
             if leaf == "weight":
                 # the last BN of a bottleneck residual branch is damped (cf. zero-gamma init) so that 16
                 # stacked blocks keep activations O(1..10) instead of growing by ~sqrt(2) per block
-                new[k] = rand(shape, 0.1, 0.3) if k.endswith(".bn3.weight") else rand(shape, 0.5, 1.5)
+                if k.endswith(".bn3.weight") or (".branches." in k and k.endswith(".bn2.weight")):
+                    new[k] = rand(shape, 0.1, 0.3)
+                elif ".fuse_layers." in k:                         # HRNet cross-resolution terms: y_i = sum_j f_ij(x_j)
+                    new[k] = rand(shape, 0.2, 0.6)
+                else:
+                    new[k] = rand(shape, 0.5, 1.5)
             elif leaf == "bias": new[k] = 0.1 * randn(shape)
             elif leaf == "running_mean": new[k] = 0.1 * randn(shape)
             elif leaf == "running_var": new[k] = rand(shape, 0.5, 1.5)

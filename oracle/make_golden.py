@@ -145,6 +145,25 @@ def gen_res50(ns):
         print(f"res50 {tag}: oracle max abs err {err:.2e} (scale {scale:.1f})")
 
 
+def gen_hrnet(ns):
+    model, cfg = ref_create_model("hrnet_w32_512")
+    sd = conditioned_state_dict(model.state_dict(), 317)
+    model.load_state_dict(sd)
+    sd_sha = sha(*[sd[k].numpy() for k in sorted(sd) if sd[k].is_floating_point()])
+    for tag, B, H, W, stride in (("128", 2, 128, 128, 1), ("256x320", 1, 256, 320, 2), ("512", 1, 512, 512, 4)):
+        x = synth_images(B, H, W, seed=317)
+        with torch.no_grad():
+            ref = model(x)
+            mine = dla_ref.forward(sd, x, arch="hrnet")
+        err = max(float((a - b).abs().max()) for a, b in zip(ref, mine))
+        scale = max(float(a.abs().max()) for a in ref)
+        assert err <= 1e-4 * scale, f"hrnet oracle != reference ({err})"
+        maps = torch.cat(ref, dim=1).numpy()[:, :, ::stride, ::stride]
+        np.savez_compressed(os.path.join(GOLD, f"hrnet32_{tag}.npz"), maps=maps.astype(np.float32), stride=np.array(stride),
+                            shape=np.array([B, H, W]), sd_sha=np.array(sd_sha), x_sha=np.array(sha(x.numpy())))
+        print(f"hrnet_w32 {tag}: oracle max abs err {err:.2e} (scale {scale:.1f})")
+
+
 def gen_post(ns):
     rng = np.random.RandomState(3)
     dets = rng.uniform(0, 128, size=(1, 100, 56)).astype(np.float32)
@@ -175,12 +194,17 @@ def gen_flip(ns):
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ns = load_reference()
+    if len(sys.argv) > 1:                       # python -m oracle.make_golden hrnet  -> only that family
+        for name in sys.argv[1:]:
+            globals()["gen_" + name](ns) if name not in ("dcn",) else gen_dcn()
+        return
     gen_decode(ns)
     gen_dcn()
     gen_post(ns)
     gen_flip(ns)
     gen_dla(ns)
     gen_res50(ns)
+    gen_hrnet(ns)
     print("golden fixtures written to", GOLD)
 
 

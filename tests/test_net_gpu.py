@@ -388,6 +388,50 @@ def test_res50_matches_reference_golden_and_oracle():
         assert rel <= 3e-2, (tc, rel)
 
 
+@pytest.mark.parametrize("tag", ["128", "256x320"])
+def test_hrnet_matches_reference_golden_and_oracle(tag):
+    """BASELINE config 4 backbone: HRNet-W32 (pose_higher_hrnet.py) + heads.  128x128 drives the lowest-resolution
+    branches (4x4, 8x8) through the CUDA-core fallbacks; 256x320 keeps every conv on the tcgen05 kernels."""
+    from oracle import dla_ref
+    from oracle.init_recipe import synth_images
+    g = np.load(os.path.join(GOLD, f"hrnet32_{tag}.npz"))
+    B, H, W = [int(v) for v in g["shape"]]
+    st = int(g["stride"])
+    m, sd = _model("fp32", "hrnet")
+    x = synth_images(B, H, W, 317)
+    _net_close(torch.cat(m(x.to(DEV)), dim=1).cpu().numpy()[:, :, ::st, ::st], g["maps"])
+    ref = torch.cat(dla_ref.forward(sd, x, arch="hrnet"), dim=1)
+    for tc in (False, True):
+        m.set_precision("bf16", tc=tc)
+        got16 = torch.cat(m(x.to(DEV)), dim=1).cpu()
+        rel = ((got16 - ref).norm() / ref.norm()).item()
+        assert rel <= 3e-2, (tc, rel)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_upsample_add_op_matches_torch(precision):
+    """CPB200_OP_UPSAMPLE_ADD (HRNet fuse term): nearest upsample x f + skip (+ReLU); exact in both dtypes up to
+    the output rounding.  Also the 3x3 / stride-2 stem (HRNet conv1)."""
+    g = torch.Generator().manual_seed(3)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    B, C, H, W = 2, 32, 5, 7
+    for f, relu, skip in ((2, True, True), (4, False, True), (8, True, False)):
+        xt = torch.randn(B, C, H, W, generator=g).bfloat16().float()
+        st = torch.randn(B, C, H * f, W * f, generator=g).bfloat16().float()
+        pb = _builder(B, precision)
+        y = pb.upsample_add(pb.external(_nhwc(xt, dt)), pb.external(_nhwc(st, dt)) if skip else None, f, relu=relu)
+        ref = F.interpolate(xt, scale_factor=f, mode="nearest") + (st if skip else 0)
+        ref = F.relu(ref) if relu else ref
+        _check(_nchw(_run(pb, y)), ref, precision)
+    img = torch.randn(B, 3, 32, 48, generator=g)
+    w = torch.randn(64, 3, 3, 3, generator=g) * 0.2; b = torch.randn(64, generator=g)
+    pb = _builder(B, precision); pb.H, pb.W = 32, 48
+    y = pb.stem(pb.input(3), w.to(DEV), b.to(DEV), 3, 2, 1, relu=True)
+    plan = pb.build(); plan.bind(img.to(DEV), {})
+    plan.run(torch.cuda.current_stream().cuda_stream); torch.cuda.synchronize()
+    _check(_nchw(plan.tensor(y)), F.relu(F.conv2d(img, w, b, stride=2, padding=1)), precision)
+
+
 def test_forward_rejects_cpu_and_training():
     m, _ = _model("bf16")
     with pytest.raises(RuntimeError):

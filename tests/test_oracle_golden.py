@@ -126,3 +126,19 @@ def test_res50_oracle_matches_golden():
     x = synth_images(B, H, W, seed=317)
     maps = torch.cat(dla_ref.forward(sd, x, arch="res_50"), dim=1).numpy()
     assert np.abs(maps - g["maps"]).max() <= 1e-4 * np.abs(g["maps"]).max()
+
+
+def test_hrnet_oracle_matches_golden():
+    """HRNet-W32 (BASELINE config 4): oracle restatement vs the reference module's golden maps; also pins that the
+    product's parameter tree has exactly the reference's key names (the recipe draws in sorted-key order)."""
+    g = np.load(os.path.join(GOLD, "hrnet32_128.npz"))
+    B, H, W = [int(v) for v in g["shape"]]
+    from centerpose_b200.model import create_model
+    from centerpose_b200.config import default_cfg
+    cfg = default_cfg("hrnet")
+    sd = conditioned_state_dict(create_model(cfg.MODEL.NAME, cfg.MODEL.HEAD_CONV, cfg).state_dict(), 317)
+    assert len(sd) == 1776
+    assert _sha(*[sd[k].numpy() for k in sorted(sd) if sd[k].is_floating_point()]) == str(g["sd_sha"])
+    x = synth_images(B, H, W, seed=317)
+    maps = torch.cat(dla_ref.forward(sd, x, arch="hrnet"), dim=1).numpy()
+    assert np.abs(maps - g["maps"]).max() <= 1e-4 * np.abs(g["maps"]).max()
