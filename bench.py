@@ -31,8 +31,8 @@ IMG = 512
 B_PER_GPU = 32
 K_DET = 100
 GFLOP_PER_IMG = 80.48            # SURVEY.md §8d (2*MAC of conv+deconv+DCN+heads, DLA-34 @512)
-ARCH_GFLOP = {"dla_34": 80.48, "res_50": 86.85, "hrnet": 85.27}
-ARCH_BATCH = {"dla_34": 32, "res_50": 16, "hrnet": 16}   # BASELINE.json configs[1] / [2] (128 over 8 GPUs) / [3]
+ARCH_GFLOP = {"dla_34": 80.48, "res_50": 86.85, "hrnet": 85.27, "mobilenetv3": 15.59}
+ARCH_BATCH = {"dla_34": 32, "res_50": 16, "hrnet": 16, "mobilenetv3": 64}   # BASELINE.json configs[1..4] per GPU
 # dram__bytes_read+write summed over the 97 launches of one DLA-34 B=32 step (ncu, profiles/r01_traffic_per_kernel_v13.txt)
 NCU_TRAFFIC_BYTES = {("dla_34", 32): 9.534e9}
 DECODE_BYTES_PER_IMG = 1230848
@@ -187,7 +187,7 @@ def main():
     global ARCH, GFLOP_PER_IMG, B_PER_GPU, METRIC
     ARCH = args.arch; GFLOP_PER_IMG = ARCH_GFLOP[ARCH]; B_PER_GPU = args.batch or ARCH_BATCH[ARCH]
     args.batch = B_PER_GPU
-    METRIC = "images/sec 512x512 " + {"dla_34": "DLA-34", "res_50": "ResNet-50", "hrnet": "HRNet-W32"}[ARCH]
+    METRIC = "images/sec 512x512 " + {"dla_34": "DLA-34", "res_50": "ResNet-50", "hrnet": "HRNet-W32", "mobilenetv3": "MobileNetV3"}[ARCH]
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)

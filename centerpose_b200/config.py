@@ -40,6 +40,7 @@ _ARCH = {
     # arch: (HEAD_CONV, INTERMEDIATE_CHANNEL)   experiments/{dla_34,res_50}_512x512.yaml:28-30
     "dla_34": (256, 64),
     "res_50": (64, 256),
+    "mobilenetv3": (256, 24),  # experiments/mobilenetv3_512x512.yaml:28-29
     "hrnet": (64, 32),        # experiments/hrnet_w32_512.yaml:62,73 (MODEL.EXTRA defaults to W32, archs/hrnet.py)
 }
 

@@ -38,4 +38,14 @@ inline int check_launch(const char *what) {
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+#define CPB_ACT_MASK (CPB200_FLAG_RELU | CPB200_FLAG_HSWISH | CPB200_FLAG_HSIGMOID)
+// Epilogue non-linearity selected by the op flags (at most one of RELU / HSWISH / HSIGMOID).  hswish and
+// hsigmoid keep the reference's operation order x * relu6(x + 3) / 6 (mobilenetv3.py:84-93).
+__device__ __forceinline__ float act_fn(float v, uint32_t act) {
+  if (act == CPB200_FLAG_RELU) return fmaxf(v, 0.f);
+  if (act == 0u) return v;
+  const float r = fminf(fmaxf(v + 3.f, 0.f), 6.f);
+  return act == CPB200_FLAG_HSWISH ? v * r / 6.f : r / 6.f;
+}
+
 }  // namespace cpb

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
   }
 
   // ---- epilogue ----
-  const bool relu = a.flags & CPB200_FLAG_RELU;
+  const uint32_t act = a.flags & CPB_ACT_MASK;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     const long long m = m0 + ty * TM + i;
@@ -237,21 +237,21 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
 #pragma unroll
       for (int j = 0; j < TN; ++j)
         if (nb + j < a.cout) {
-          float x = v[j]; if (relu) x = fmaxf(x, 0.f);
+          float x = v[j]; x = cpb::act_fn(x, act);
           o[(((size_t)b * a.out_ch_total + a.out_ch_off + nb + j) * a.Hd + hd) * a.Wd + wd] = x;
         }
     } else if (a.flags & CPB200_FLAG_OUT_F32) {
       float *o = static_cast<float *>(a.dst) + pix * a.cout;
 #pragma unroll
       for (int j = 0; j < TN; ++j)
-        if (nb + j < a.cout) { float x = v[j]; if (relu) x = fmaxf(x, 0.f); o[nb + j] = x; }
+        if (nb + j < a.cout) { float x = v[j]; x = cpb::act_fn(x, act); o[nb + j] = x; }
     } else {
       T *o = static_cast<T *>(a.dst) + pix * a.cout;
       const T *rs = a.res ? static_cast<const T *>(a.res) + pix * a.cout : nullptr;
       if (nb + TN <= a.cout && (a.cout & 3) == 0) {
         float4 x = make_float4(v[0], v[1], v[2], v[3]);
         if (rs) { float4 r4 = Act<T>::ld4(rs + nb); x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w; }
-        if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+        if (act) { x.x = cpb::act_fn(x.x, act); x.y = cpb::act_fn(x.y, act); x.z = cpb::act_fn(x.z, act); x.w = cpb::act_fn(x.w, act); }
         Act<T>::st4(o + nb, x);
       } else {
 #pragma unroll
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
           if (nb + j < a.cout) {
             float x = v[j];
             if (rs) x += Act<T>::ld(rs + nb + j);
-            if (relu) x = fmaxf(x, 0.f);
+            x = cpb::act_fn(x, act);
             Act<T>::st(o + nb + j, x);
           }
       }
@@ -275,7 +275,7 @@ template <typename T, int COUT, int PX, int STRIDE, int KW>
 __global__ void __launch_bounds__(128) stem_kernel(const float *__restrict__ x, T *__restrict__ y,
                                                    const float *__restrict__ w, const float *__restrict__ bias,
                                                    int B, int Cin, int H, int W, int Ho, int Wo,
-                                                   int kh, int pad_h, int pad_w, int relu) {
+                                                   int kh, int pad_h, int pad_w, uint32_t act) {
   extern __shared__ float sw[];                      // kh*KW*cin*COUT
   const int nw = kh * KW * Cin * COUT;
   for (int i = threadIdx.x; i < nw; i += blockDim.x) sw[i] = w[i];
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(128) stem_kernel(const float *__restrict__ x, 
 #pragma unroll
     for (int n = 0; n < COUT; n += 4) {
       float4 v = make_float4(acc[p][n], acc[p][n + 1], acc[p][n + 2], acc[p][n + 3]);
-      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      if (act) { v.x = cpb::act_fn(v.x, act); v.y = cpb::act_fn(v.y, act); v.z = cpb::act_fn(v.z, act); v.w = cpb::act_fn(v.w, act); }
       Act<T>::st4(o + n, v);
     }
   }
@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(256) dwdeconv_add_kernel(const T *__restrict__
 // Thread = 4 channels of one output pixel; f is a power of two (shift).
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_add_kernel(const T *__restrict__ x, const T *__restrict__ skip, T *__restrict__ y,
-                                                           long long total, int H, int W, int C4, int Ho, int Wo, int sh, int relu) {
+                                                           long long total, int H, int W, int C4, int Ho, int Wo, int sh, uint32_t act) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
     long long p = i / C4;
@@ -452,7 +452,95 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(const T *__restrict__
       const float4 s4 = Act<T>::ld4(skip + (size_t)i * 4);
       v.x += s4.x; v.y += s4.y; v.z += s4.z; v.w += s4.w;
     }
-    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (act) { v.x = cpb::act_fn(v.x, act); v.y = cpb::act_fn(v.y, act); v.z = cpb::act_fn(v.z, act); v.w = cpb::act_fn(v.w, act); }
+    Act<T>::st4(y + (size_t)i * 4, v);
+  }
+}
+
+// ---- depthwise k x k conv (stride s, pad k/2) + bias + activation, NHWC   (mobilenetv3.py:124-127 conv2/bn2) ----
+// y[b,ho,wo,c] = act(bias[c] + sum_{r,q} x[b, ho*s-p+r, wo*s-p+q, c] * w[r,q,c]).  Thread = VEC channels of one
+// output pixel (VEC * sizeof(T) = 16 bytes); consecutive threads walk the channels of a pixel, so every tap is
+// a coalesced row read that the neighbouring output pixels re-read from L1.  HBM-bound: 2 bytes in + out per MAC x k^2.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) dwconv_kernel(const T *__restrict__ x, T *__restrict__ y, const float *__restrict__ w,
+                                                     const float *__restrict__ bias, long long total, int H, int W, int C,
+                                                     int Ho, int Wo, int k, int stride, int pad, uint32_t act) {
+  const int CV = C / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long p = i / CV;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const int c0 = cv * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; q += 4) {
+      const float4 b4 = bias ? __ldg(reinterpret_cast<const float4 *>(bias + c0 + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[q] = b4.x; acc[q + 1] = b4.y; acc[q + 2] = b4.z; acc[q + 3] = b4.w;
+    }
+    const int hi0 = ho * stride - pad, wi0 = wo * stride - pad;
+    for (int r = 0; r < k; ++r) {
+      const int hi = hi0 + r;
+      if (hi < 0 || hi >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int wi = wi0 + s;
+        if (wi < 0 || wi >= W) continue;
+        const T *xp = x + (((size_t)b * H + hi) * W + wi) * C + c0;
+        const float *wp = w + (size_t)(r * k + s) * C + c0;
+#pragma unroll
+        for (int q = 0; q < VEC; q += 4) {
+          const float4 v = Act<T>::ld4(xp + q);
+          const float4 ww = __ldg(reinterpret_cast<const float4 *>(wp + q));
+          acc[q] = fmaf(v.x, ww.x, acc[q]); acc[q + 1] = fmaf(v.y, ww.y, acc[q + 1]);
+          acc[q + 2] = fmaf(v.z, ww.z, acc[q + 2]); acc[q + 3] = fmaf(v.w, ww.w, acc[q + 3]);
+        }
+      }
+    }
+    T *o = y + (size_t)i * VEC;
+#pragma unroll
+    for (int q = 0; q < VEC; q += 4)
+      Act<T>::st4(o + q, make_float4(cpb::act_fn(acc[q], act), cpb::act_fn(acc[q + 1], act), cpb::act_fn(acc[q + 2], act),
+                                     cpb::act_fn(acc[q + 3], act)));
+  }
+}
+
+// ---- global average pool (B,H,W,C) -> (B,1,1,C)   (SeModule's AdaptiveAvgPool2d(1), mobilenetv3.py:100) ----
+// CTA = (image b, 64-channel chunk): 16 channel quads x 16 pixel lanes, fp32 partial sums, shared-memory tree.
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_kernel(const T *__restrict__ x, T *__restrict__ y, int HW, int C) {
+  __shared__ float4 part[16][16];
+  const int b = blockIdx.x, cq = blockIdx.y * 16 + (threadIdx.x & 15), lane = threadIdx.x >> 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cq * 4 < C) {
+    const T *xp = x + (size_t)b * HW * C + cq * 4;
+    for (int p = lane; p < HW; p += 16) {
+      const float4 v = Act<T>::ld4(xp + (size_t)p * C);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  part[lane][threadIdx.x & 15] = s;
+  __syncthreads();
+  if (lane == 0 && cq * 4 < C) {
+    for (int l = 1; l < 16; ++l) { const float4 v = part[l][threadIdx.x & 15]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+    const float inv = 1.f / (float)HW;
+    Act<T>::st4(y + (size_t)b * C + cq * 4, make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv));
+  }
+}
+
+// ---- y[b,h,w,c] = x[b,h,w,c] * scale[b,c] (+ skip[b,h,w,c])   (SeModule gate + Block shortcut, mobilenetv3.py:111,146) ----
+template <typename T>
+__global__ void __launch_bounds__(256) scale_add_kernel(const T *__restrict__ x, const T *__restrict__ scale, const T *__restrict__ skip,
+                                                        T *__restrict__ y, long long total, long long per_image, int C4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_image), c4 = (int)(i % C4);
+    float4 v = Act<T>::ld4(x + (size_t)i * 4);
+    const float4 g = Act<T>::ld4(scale + ((size_t)b * C4 + c4) * 4);
+    v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+    if (skip) {
+      const float4 s4 = Act<T>::ld4(skip + (size_t)i * 4);
+      v.x += s4.x; v.y += s4.y; v.z += s4.z; v.w += s4.w;
+    }
     Act<T>::st4(y + (size_t)i * 4, v);
   }
 }
@@ -500,7 +588,7 @@ int run_op_simt(const cpb200_op &op, cudaStream_t st) {
       const int cin = op.cin[0];
       const size_t smem = (size_t)op.kh * op.kw * cin * op.cout * sizeof(float);
       if (cin > 4 || smem > 48 * 1024 || (op.kw != 7 && op.kw != 3)) return cpb::fail(CPB200_ERR_ARG, "stem: unsupported shape");
-      const int relu = (op.flags & CPB200_FLAG_RELU) ? 1 : 0;
+      const uint32_t act = op.flags & CPB_ACT_MASK;
       // (COUT, PX) register tiles: 16 couts x 4 pixels, 64 couts x 1 pixel
 #define STEM_LAUNCH(CO, PX, ST) STEM_LAUNCH_K(CO, PX, ST, 7)
 #define STEM_LAUNCH_K(CO, PX, ST, KW)                                                                            \
@@ -509,10 +597,11 @@ int run_op_simt(const cpb200_op &op, cudaStream_t st) {
     const long long M = (long long)op.B * op.Ho * (op.Wo / PX);                                              \
     stem_kernel<T, CO, PX, ST, KW><<<(unsigned)((M + 127) / 128), 128, smem, st>>>(                           \
         static_cast<const float *>(op.src[0]), static_cast<T *>(op.dst), static_cast<const float *>(op.weight), \
-        op.bias, op.B, cin, op.H, op.W, op.Ho, op.Wo, op.kh, op.pad_h, op.pad_w, relu);                      \
+        op.bias, op.B, cin, op.H, op.W, op.Ho, op.Wo, op.kh, op.pad_h, op.pad_w, act);                      \
   }
       if (op.kw == 3) {                               // HRNet conv1 (pose_higher_hrnet.py:243-244)
         if (op.cout == 64 && op.stride == 2) STEM_LAUNCH_K(64, 1, 2, 3)
+        else if (op.cout == 16 && op.stride == 2) STEM_LAUNCH_K(16, 4, 2, 3)      // MobileNetV3 conv1 (mobilenetv3.py:165)
         else return cpb::fail(CPB200_ERR_ARG, "stem 3x3: cout %d / stride %d unsupported", op.cout, op.stride);
       } else if (op.cout == 16 && op.stride == 1) STEM_LAUNCH(16, 4, 1)
       else if (op.cout == 16 && op.stride == 2) STEM_LAUNCH(16, 4, 2)
@@ -544,11 +633,41 @@ int run_op_simt(const cpb200_op &op, cudaStream_t st) {
       constexpr int VEC = sizeof(T) == 2 ? 8 : 4;
       if (op.cin[0] % VEC) return cpb::fail(CPB200_ERR_ARG, "dwdeconv: C %% %d != 0", VEC);
       const size_t smem = (size_t)op.kh * op.kh * op.cin[0] * sizeof(float);
-      if (smem > 48 * 1024) return cpb::fail(CPB200_ERR_ARG, "dwdeconv: filter does not fit shared memory");
+      if (smem > 160 * 1024) return cpb::fail(CPB200_ERR_ARG, "dwdeconv: filter does not fit shared memory");
+      if (smem > 48 * 1024 &&
+          cudaFuncSetAttribute(dwdeconv_add_kernel<T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return cpb::fail(CPB200_ERR_CUDA, "dwdeconv: cannot raise the shared-memory limit to %zu bytes", smem);
       dwdeconv_add_kernel<T, VEC><<<(unsigned)(op.B * op.Ho), 256, smem, st>>>(static_cast<const T *>(op.src[0]),
           static_cast<const T *>(op.aux), static_cast<T *>(op.dst), static_cast<const float *>(op.weight),
           op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h);
       return cpb::check_launch("dwdeconv_add_kernel");
+    }
+    case CPB200_OP_DWCONV: {
+      constexpr int VEC = sizeof(T) == 2 ? 8 : 4;
+      const int C = op.cin[0];
+      if (C % VEC || op.kh != op.kw || op.cout != C) return cpb::fail(CPB200_ERR_ARG, "dwconv: C %% %d != 0 or non-square kernel", VEC);
+      const long long total = (long long)op.B * op.Ho * op.Wo * (C / VEC);
+      const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 32);
+      dwconv_kernel<T, VEC><<<grid, 256, 0, st>>>(static_cast<const T *>(op.src[0]), static_cast<T *>(op.dst),
+          static_cast<const float *>(op.weight), op.bias, total, op.H, op.W, C, op.Ho, op.Wo, op.kh, op.stride, op.pad_h,
+          op.flags & CPB_ACT_MASK);
+      return cpb::check_launch("dwconv_kernel");
+    }
+    case CPB200_OP_AVGPOOL: {
+      const int C = op.cin[0];
+      if (C % 4 || op.Ho != 1 || op.Wo != 1) return cpb::fail(CPB200_ERR_ARG, "avgpool: C %% 4 != 0 or output not 1x1");
+      avgpool_kernel<T><<<dim3((unsigned)op.B, (unsigned)((C + 63) / 64)), 256, 0, st>>>(static_cast<const T *>(op.src[0]),
+          static_cast<T *>(op.dst), op.H * op.W, C);
+      return cpb::check_launch("avgpool_kernel");
+    }
+    case CPB200_OP_SCALE_ADD: {
+      const int C = op.cin[0];
+      if (C % 4 || !op.res) return cpb::fail(CPB200_ERR_ARG, "scale_add: C %% 4 != 0 or missing scale vector");
+      const long long per_image = (long long)op.H * op.W * (C / 4), total = per_image * op.B;
+      const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
+      scale_add_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(op.src[0]), static_cast<const T *>(op.res),
+          static_cast<const T *>(op.aux), static_cast<T *>(op.dst), total, per_image, C / 4);
+      return cpb::check_launch("scale_add_kernel");
     }
     case CPB200_OP_UPSAMPLE_ADD: {
       const int f = op.stride;
@@ -559,7 +678,7 @@ int run_op_simt(const cpb200_op &op, cudaStream_t st) {
       const long long total = (long long)op.B * op.Ho * op.Wo * (op.cin[0] / 4);
       const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
       upsample_add_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T *>(op.src[0]), static_cast<const T *>(op.aux),
-          static_cast<T *>(op.dst), total, op.H, op.W, op.cin[0] / 4, op.Ho, op.Wo, sh, (op.flags & CPB200_FLAG_RELU) ? 1 : 0);
+          static_cast<T *>(op.dst), total, op.H, op.W, op.cin[0] / 4, op.Ho, op.Wo, sh, op.flags & CPB_ACT_MASK);
       return cpb::check_launch("upsample_add_kernel");
     }
     default: return cpb::fail(CPB200_ERR_ARG, "unknown op type %d", op.type);

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;
-    const bool relu = a.flags & CPB200_FLAG_RELU;
+    const uint32_t act = a.flags & CPB_ACT_MASK;
     const bool out_f32 = a.flags & CPB200_FLAG_OUT_F32;
     int acc = 0; uint32_t accphase = 0;
     bool bias_loaded = false;
@@ -245,13 +245,13 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
                 float4 v4 = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                if (relu) { v4.x = fmaxf(v4.x, 0.f); v4.y = fmaxf(v4.y, 0.f); v4.z = fmaxf(v4.z, 0.f); v4.w = fmaxf(v4.w, 0.f); }
+                if (act) { v4.x = cpb::act_fn(v4.x, act); v4.y = cpb::act_fn(v4.y, act); v4.z = cpb::act_fn(v4.z, act); v4.w = cpb::act_fn(v4.w, act); }
                 *reinterpret_cast<float4 *>(o + j) = v4;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (nb + j < a.cout) o[j] = relu ? fmaxf(f[j], 0.f) : f[j];
+                if (nb + j < a.cout) o[j] = cpb::act_fn(f[j], act);
             }
           } else {
             __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(a.dst) + pix * a.cout_store + nb;
@@ -266,9 +266,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
                 f[2 * j] += x0.x; f[2 * j + 1] += x0.y; f[8 + 2 * j] += x1.x; f[8 + 2 * j + 1] += x1.y;
               }
             }
-            if (relu) {
+            if (act) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+              for (int j = 0; j < 16; ++j) f[j] = cpb::act_fn(f[j], act);
             }
             uint4 o0, o1;
             __nv_bfloat162 *ob0 = reinterpret_cast<__nv_bfloat162 *>(&o0), *ob1 = reinterpret_cast<__nv_bfloat162 *>(&o1);

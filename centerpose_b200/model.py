@@ -24,6 +24,11 @@ def _res_arch():
     return _res
 
 
+def _mobilenet_arch():
+    from .archs import mobilenet as _mb
+    return _mb
+
+
 def _hrnet_arch():
     from .archs import hrnet as _hr
     return _hr
@@ -34,6 +39,7 @@ _backbone_factory = {
     "dla": lambda n: (_dla, 64) if n == 34 else None,
     "res": lambda n: (_res_arch(), 256) if n == 50 else None,
     "hrnet": lambda n: (_hrnet_arch(), None),
+    "mobilenetv3": lambda n: (_mobilenet_arch(), 24),
 }
 
 
@@ -62,7 +68,7 @@ class BackBoneWithHead(nn.Module):
         arch_name = arch[:arch.find("_")] if "_" in arch else arch
         if arch_name not in _backbone_factory or _backbone_factory[arch_name](num_layers) is None:
             raise KeyError(f"centerpose_b200: backbone {arch!r} is not implemented "
-                           f"(available: dla_34, res_50, hrnet)")
+                           f"(available: dla_34, res_50, hrnet, mobilenetv3)")
         self._arch_mod, feat_c = _backbone_factory[arch_name](num_layers)
         if feat_c is None:
             feat_c = self._arch_mod.feature_channels(cfg)
@@ -114,8 +120,10 @@ class BackBoneWithHead(nn.Module):
             P = StateView(sd, "head_model.", device)
             for name, c in HEADS:
                 dst = pb.output(c, feat.H, feat.W, name)
-                t = pb.conv([feat], P(f"{name}.0.weight").float(), P(f"{name}.0.bias").float(),
-                            stride=1, pad=1, relu=True)
+                w0 = P(f"{name}.0.weight").float()
+                if feat.C > w0.shape[1]:                 # backbone carries zero-padded channels (archs/mobilenet.py)
+                    w0 = torch.nn.functional.pad(w0, (0, 0, 0, 0, 0, feat.C - w0.shape[1]))
+                t = pb.conv([feat], w0, P(f"{name}.0.bias").float(), stride=1, pad=1, relu=True)
                 pb.conv([t], P(f"{name}.2.weight").float(), P(f"{name}.2.bias").float(),
                         stride=1, pad=0, relu=False, out="nchw", dst=dst)
             plan = pb.build()

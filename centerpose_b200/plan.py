@@ -25,7 +25,9 @@ import torch
 from . import _lib
 
 OP_CONV, OP_STEM, OP_MAXPOOL, OP_DWDECONV_ADD, OP_DCN, OP_IM2COL_W, OP_UPSAMPLE_ADD = 1, 2, 3, 4, 5, 6, 7
-FLAG_RELU, FLAG_OUT_NCHW_F32, FLAG_OUT_F32, FLAG_TC = 1, 2, 4, 8
+OP_DWCONV, OP_AVGPOOL, OP_SCALE_ADD = 8, 9, 10
+FLAG_RELU, FLAG_OUT_NCHW_F32, FLAG_OUT_F32, FLAG_TC, FLAG_HSWISH, FLAG_HSIGMOID = 1, 2, 4, 8, 16, 32
+_ACT_FLAG = {None: 0, "relu": FLAG_RELU, "hswish": FLAG_HSWISH, "hsigmoid": FLAG_HSIGMOID}
 F32, BF16 = 0, 1
 BN_EPS = 1e-5
 
@@ -156,7 +158,7 @@ class PlanBuilder:
                 and (co % 16 == 0 or out in ("f32", "nchw")) and kh * kw <= 49)
 
     # ---- ops -------------------------------------------------------------------------------
-    def stem(self, x: Sym, w, b, k, stride, pad, relu=True):
+    def stem(self, x: Sym, w, b, k, stride, pad, relu=True, act=None):
         co, ci = w.shape[0], w.shape[1]
         if (self.use_tc and stride == 1 and k * ci <= 32 and co % 16 == 0 and pad == k // 2
                 and os.environ.get("CPB200_TC_STEM", "0") == "1"):
@@ -174,13 +176,13 @@ class PlanBuilder:
         Ho = (x.H + 2 * pad - k) // stride + 1; Wo = (x.W + 2 * pad - k) // stride + 1
         y = self._sym(co, Ho, Wo)
         wp = self._dev(w.permute(2, 3, 1, 0).reshape(k * k * ci, co))
-        self._emit(_PendingOp(type=OP_STEM, flags=FLAG_RELU if relu else 0, k=(k, k), stride=stride,
+        self._emit(_PendingOp(type=OP_STEM, flags=_ACT_FLAG[act] if act else (FLAG_RELU if relu else 0), k=(k, k), stride=stride,
                               pad=(pad, pad), weight=wp, bias=self._dev(b), cout=co), [x], y)
         return y
 
     def conv(self, srcs: Sequence[Sym], w, b, stride=1, pad=0, relu=False, res: Optional[Sym] = None,
              out: str = "act", dst: Optional[Sym] = None, ch_off: int = 0, pad_hw=None,
-             out_map=None):
+             out_map=None, act=None):
         """w (Co, sum(Ci), kh, kw) already BN-folded; b (Co).  out: 'act' | 'f32' | 'nchw'.
         pad_hw=(top,left) overrides symmetric padding; out_map=(Hd,Wd,sy,sx,oy,ox,Ho,Wo) writes a
         strided sub-lattice of a larger dst (used to lower dense ConvTranspose2d)."""
@@ -193,7 +195,7 @@ class PlanBuilder:
             Hd, Wd, sy, sx, oy, ox = Ho, Wo, 1, 1, 0, 0
         else:
             Hd, Wd, sy, sx, oy, ox, Ho, Wo = out_map
-        flags = FLAG_RELU if relu else 0
+        flags = _ACT_FLAG[act] if act else (FLAG_RELU if relu else 0)     # act: 'relu' | 'hswish' | 'hsigmoid'
         if out == "nchw":
             assert dst is not None
             flags |= FLAG_OUT_NCHW_F32
@@ -230,6 +232,32 @@ class PlanBuilder:
                               weight=wp, bias=None, cout=C), [x], y, [skip])
         return y
 
+    def dwconv(self, x: Sym, w, b, stride=1, act=None):
+        """depthwise conv, w (C,1,k,k) BN-folded, pad k//2   (mobilenetv3.py:124-127)."""
+        C, _, k, _ = w.shape
+        assert C == x.C
+        Ho = (x.H + 2 * (k // 2) - k) // stride + 1; Wo = (x.W + 2 * (k // 2) - k) // stride + 1
+        y = self._sym(C, Ho, Wo)
+        wp = self._dev(w.float().reshape(C, k * k).t())          # [k*k][C]
+        self._emit(_PendingOp(type=OP_DWCONV, flags=_ACT_FLAG[act], k=(k, k), stride=stride, pad=(k // 2, k // 2),
+                              weight=wp, bias=self._dev(b), cout=C), [x], y)
+        return y
+
+    def avgpool(self, x: Sym):
+        """global average pool -> (C, 1, 1)   (mobilenetv3.py:100)."""
+        y = self._sym(x.C, 1, 1)
+        self._emit(_PendingOp(type=OP_AVGPOOL, flags=0, k=(x.H, x.W), stride=1, pad=(0, 0), weight=None, bias=None,
+                              cout=x.C), [x], y)
+        return y
+
+    def scale_add(self, x: Sym, gate: Sym, skip: Optional[Sym] = None):
+        """x * gate[b, c] (+ skip)   (mobilenetv3.py:111,146)."""
+        assert gate.C == x.C and gate.H == 1 and gate.W == 1
+        y = self._sym(x.C, x.H, x.W)
+        self._emit(_PendingOp(type=OP_SCALE_ADD, flags=0, k=(1, 1), stride=1, pad=(0, 0), weight=None, bias=None,
+                              cout=x.C), [x], y, [gate, skip])
+        return y
+
     def upsample_add(self, x: Sym, skip: Optional[Sym], f: int, relu=False):
         """nearest-neighbour upsample x f of ``x`` (+ skip)(+ReLU)   (pose_higher_hrnet.py:186-187,224-232)."""
         y = self._sym(x.C, x.H * f, x.W * f)
@@ -245,7 +273,7 @@ class PlanBuilder:
         om = self.conv([x], om_w32, om_b32, stride=1, pad=1, relu=False, out="f32")
         co = w.shape[0]
         y = self._sym(co, x.H, x.W)
-        tc = (self.use_tc and x.kind == "act" and x.C % 64 == 0 and co % 16 == 0 and 64 <= co and x.W >= 8
+        tc = (self.use_tc and x.kind == "act" and x.C % 64 == 0 and co % 16 == 0 and 32 <= co and x.W >= 8
               and os.environ.get("CPB200_TC_DCN", "1") != "0")
         self._emit(_PendingOp(type=OP_DCN, flags=(FLAG_RELU if relu else 0) | (FLAG_TC if tc else 0), k=(3, 3),
                               stride=1, pad=(1, 1), weight=self._pack_conv_tc(w) if tc else self._pack_conv(w),
@@ -301,6 +329,10 @@ class Plan:
             if po.type in (OP_DCN, OP_DWDECONV_ADD, OP_UPSAMPLE_ADD) and ex and ex[0] is not None:
                 o.aux = ex[0].buf.data_ptr()
                 o.aux_pitch = ex[0].C
+            if po.type == OP_SCALE_ADD:
+                o.res = ex[0].buf.data_ptr()
+                if ex[1] is not None:
+                    o.aux = ex[1].buf.data_ptr()
             if po.weight is not None:
                 o.weight = po.weight.data_ptr()
             if po.bias is not None:

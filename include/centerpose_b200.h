@@ -114,8 +114,13 @@ enum cpb200_op_type {
   CPB200_OP_DCN = 5,         /* modulated deformable 3x3 conv (DCNv2 forward) (+bias)(+ReLU)                */
   CPB200_OP_IM2COL_W = 6,    /* NCHW fp32 image -> NHWC act: channel s*cin+c = x[c, h, w+s-pad_w], s < kw, zero-padded
                                 to `cout` channels.  Turns the 7x7 stem into a 7x1 tensor-core conv (K = 7 x 32).   */
-  CPB200_OP_UPSAMPLE_ADD = 7 /* nearest-neighbour upsample x `stride` (power of two) of src[0] (+ aux skip add)(+ReLU),
+  CPB200_OP_UPSAMPLE_ADD = 7,/* nearest-neighbour upsample x `stride` (power of two) of src[0] (+ aux skip add)(+ReLU),
                                 NHWC  (HRNet fuse_layers, pose_higher_hrnet.py:186-187,224-232)                     */
+  CPB200_OP_DWCONV = 8,      /* depthwise k x k conv, stride s, pad k/2 (+bias)(+activation); weight fp32 [k*k][C]
+                                (MobileNetV3 Block.conv2, mobilenetv3.py:124-127)                                   */
+  CPB200_OP_AVGPOOL = 9,     /* global average pool (B,H,W,C) -> (B,1,1,C)  (SeModule, mobilenetv3.py:100)           */
+  CPB200_OP_SCALE_ADD = 10   /* dst = src[0] * res[b,c] (+ aux skip): SE gate + block shortcut (mobilenetv3.py:111,146);
+                                `res` is the (B,1,1,C) gate vector                                                  */
 };
 /* A dense ConvTranspose2d(k4,s2,p1) (msra_resnet.py:168-193) is lowered by the host into four
  * 2x2 CONV ops, one per output parity, using pad_h/pad_w and the strided-output fields below. */
@@ -124,6 +129,8 @@ enum cpb200_op_type {
 #define CPB200_FLAG_OUT_NCHW_F32 2u  /* write fp32 NCHW into dst (channel slice out_ch_off..)    */
 #define CPB200_FLAG_OUT_F32 4u       /* write fp32 NHWC regardless of act_dtype (DCN offsets)    */
 #define CPB200_FLAG_TC 8u            /* run on the tcgen05 tensor-core path (bf16 only)          */
+#define CPB200_FLAG_HSWISH 16u       /* x * relu6(x + 3) / 6 in the epilogue (mobilenetv3.py:84-87)   */
+#define CPB200_FLAG_HSIGMOID 32u     /* relu6(x + 3) / 6 in the epilogue     (mobilenetv3.py:90-93)   */
 
 typedef struct cpb200_op {
   int32_t type;              /* enum cpb200_op_type */

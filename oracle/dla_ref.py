@@ -129,6 +129,9 @@ def forward(sd, x, arch="dla_34"):
     elif arch == "res_50":
         from .resnet_ref import resnet50_backbone
         feat = resnet50_backbone(sd, x)
+    elif arch == "mobilenetv3":
+        from .mobilenet_ref import mobilenetv3_backbone
+        feat = mobilenetv3_backbone(sd, x)
     elif arch == "hrnet":
         from .hrnet_ref import hrnet_backbone
         feat = hrnet_backbone(sd, x)

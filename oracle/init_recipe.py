@@ -22,7 +22,8 @@ exercised.  This recipe keeps the architecture and shapes and only changes the V
                                  offsets (gain 1.5, many samples out of bounds) are covered at op level
                                  (tests/test_net_gpu.py::test_dcn_op_matches_oracle).
   * BatchNorm                    weight ~ U(0.5,1.5) (U(0.1,0.3) for a bottleneck's last ``bn3`` and an HRNet branch
-                                 block's last ``bn2``; U(0.2,0.6) inside HRNet ``fuse_layers``), bias ~ N(0,0.1),
+                                 block's last ``bn2``; U(0.2,0.6) inside HRNet ``fuse_layers``; U(0.4,0.8) for a
+                                 MobileNetV3 block's projection ``bn3``), bias ~ N(0,0.1),
                                  mean ~ N(0,0.1), var ~ U(0.5,1.5)
   * conv / DCN biases            ~ N(0, 0.1)
   * head final 1x1 (``.2``)      per-head gain so logits/regressions have realistic spread;
@@ -74,7 +75,11 @@ def conditioned_state_dict(template: "OrderedDict[str, torch.Tensor]", seed: int
             if leaf == "weight":
                 # the last BN of a bottleneck residual branch is damped (cf. zero-gamma init) so that 16
                 # stacked blocks keep activations O(1..10) instead of growing by ~sqrt(2) per block
-                if k.endswith(".bn3.weight") or (".branches." in k and k.endswith(".bn2.weight")):
+                if ".bneck" in k:
+                    # MobileNetV3 blocks: bn3 is the linear-bottleneck projection, not a damped residual branch;
+                    # U(0.4,0.8) keeps the 15 blocks' activations O(1..25) (0.3-0.6 decays to 1e-1, 0.5-1.0 explodes)
+                    new[k] = rand(shape, 0.4, 0.8) if k.endswith(".bn3.weight") else rand(shape, 0.5, 1.5)
+                elif k.endswith(".bn3.weight") or (".branches." in k and k.endswith(".bn2.weight")):
                     new[k] = rand(shape, 0.1, 0.3)
                 elif ".fuse_layers." in k:                         # HRNet cross-resolution terms: y_i = sum_j f_ij(x_j)
                     new[k] = rand(shape, 0.2, 0.6)

@@ -164,6 +164,25 @@ def gen_hrnet(ns):
         print(f"hrnet_w32 {tag}: oracle max abs err {err:.2e} (scale {scale:.1f})")
 
 
+def gen_mbv3(ns):
+    model, cfg = ref_create_model("mobilenetv3_512x512")
+    sd = conditioned_state_dict(model.state_dict(), 317)
+    model.load_state_dict(sd)
+    sd_sha = sha(*[sd[k].numpy() for k in sorted(sd) if sd[k].is_floating_point()])
+    for tag, B, H, W, stride in (("128x160", 2, 128, 160, 1), ("512", 1, 512, 512, 4)):
+        x = synth_images(B, H, W, seed=317)
+        with torch.no_grad():
+            ref = model(x)
+            mine = dla_ref.forward(sd, x, arch="mobilenetv3")
+        err = max(float((a - b).abs().max()) for a, b in zip(ref, mine))
+        scale = max(float(a.abs().max()) for a in ref)
+        assert err <= 1e-4 * scale, f"mobilenetv3 oracle != reference ({err})"
+        maps = torch.cat(ref, dim=1).numpy()[:, :, ::stride, ::stride]
+        np.savez_compressed(os.path.join(GOLD, f"mbv3_{tag}.npz"), maps=maps.astype(np.float32), stride=np.array(stride),
+                            shape=np.array([B, H, W]), sd_sha=np.array(sd_sha), x_sha=np.array(sha(x.numpy())))
+        print(f"mobilenetv3 {tag}: oracle max abs err {err:.2e} (scale {scale:.1f})")
+
+
 def gen_post(ns):
     rng = np.random.RandomState(3)
     dets = rng.uniform(0, 128, size=(1, 100, 56)).astype(np.float32)
@@ -205,6 +224,7 @@ def main():
     gen_dla(ns)
     gen_res50(ns)
     gen_hrnet(ns)
+    gen_mbv3(ns)
     print("golden fixtures written to", GOLD)
 
 

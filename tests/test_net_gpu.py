@@ -432,6 +432,57 @@ def test_upsample_add_op_matches_torch(precision):
     _check(_nchw(plan.tensor(y)), F.relu(F.conv2d(img, w, b, stride=2, padding=1)), precision)
 
 
+def test_mobilenetv3_matches_reference_golden_and_oracle():
+    """BASELINE config 5 backbone: MobileNetV3-Large + DCN IDAUp (mobilenet/mobilenetv3.py) + heads, lowered on
+    zero-padded channels (archs/mobilenet.py)."""
+    from oracle import dla_ref
+    from oracle.init_recipe import synth_images
+    g = np.load(os.path.join(GOLD, "mbv3_128x160.npz"))
+    B, H, W = [int(v) for v in g["shape"]]
+    m, sd = _model("fp32", "mobilenetv3")
+    x = synth_images(B, H, W, 317)
+    _net_close(torch.cat(m(x.to(DEV)), dim=1).cpu().numpy(), g["maps"])
+    ref = torch.cat(dla_ref.forward(sd, x, arch="mobilenetv3"), dim=1)
+    for tc in (False, True):
+        m.set_precision("bf16", tc=tc)
+        got16 = torch.cat(m(x.to(DEV)), dim=1).cpu()
+        rel = ((got16 - ref).norm() / ref.norm()).item()
+        assert rel <= 4e-2, (tc, rel)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_mobilenet_ops_match_torch(precision):
+    """CPB200_OP_DWCONV / AVGPOOL / SCALE_ADD and the h-swish / h-sigmoid epilogues (mobilenetv3.py:84-147)."""
+    from oracle.mobilenet_ref import hsigmoid, hswish
+    g = torch.Generator().manual_seed(11)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    B, C, H, W = 2, 48, 13, 18
+    x = (torch.randn(B, C, H, W, generator=g) * 2).bfloat16().float()
+    for k, stride, act, fn in ((3, 1, "relu", F.relu), (5, 2, "hswish", hswish), (5, 1, None, lambda t: t), (3, 2, "hswish", hswish)):
+        w = torch.randn(C, 1, k, k, generator=g) * 0.3; b = torch.randn(C, generator=g)
+        pb = _builder(B, precision)
+        y = pb.dwconv(pb.external(_nhwc(x, dt)), w.to(DEV), b.to(DEV), stride=stride, act=act)
+        _check(_nchw(_run(pb, y)), fn(F.conv2d(x, w, b, stride=stride, padding=k // 2, groups=C)), precision)
+    # global average pool + gate * x + skip
+    gate = torch.rand(B, C, 1, 1, generator=g).bfloat16().float(); skip = torch.randn(B, C, H, W, generator=g).bfloat16().float()
+    pb = _builder(B, precision)
+    sx = pb.external(_nhwc(x, dt))
+    pooled = pb.avgpool(sx)
+    y = pb.scale_add(sx, pb.external(_nhwc(gate, dt)), pb.external(_nhwc(skip, dt)))
+    plan = pb.build(); plan.bind(torch.zeros(1, device=DEV), {})
+    plan.run(torch.cuda.current_stream().cuda_stream); torch.cuda.synchronize()
+    _check(_nchw(plan.tensor(pooled)), x.mean(dim=(2, 3), keepdim=True), precision)
+    _check(_nchw(plan.tensor(y)), x * gate + skip, precision)
+    # h-swish / h-sigmoid epilogues of the 1x1 conv (CUDA-core and, in bf16, tensor-core kernels)
+    w = torch.randn(32, C, 1, 1, generator=g) * 0.3; b = torch.randn(32, generator=g)
+    for act, fn in (("hswish", hswish), ("hsigmoid", hsigmoid)):
+        for tc in ((False, True) if precision == "bf16" else (False,)):
+            pb = _builder(B, precision, tc=tc)
+            y = pb.conv([pb.external(_nhwc(x, dt))], w.to(DEV), b.to(DEV), act=act)
+            assert bool(pb.ops[-1].flags & 8) == tc
+            _check(_nchw(_run(pb, y)), fn(F.conv2d(x, w, b)), precision, 2e-2 if tc else None)
+
+
 def test_forward_rejects_cpu_and_training():
     m, _ = _model("bf16")
     with pytest.raises(RuntimeError):

@@ -142,3 +142,18 @@ def test_hrnet_oracle_matches_golden():
     x = synth_images(B, H, W, seed=317)
     maps = torch.cat(dla_ref.forward(sd, x, arch="hrnet"), dim=1).numpy()
     assert np.abs(maps - g["maps"]).max() <= 1e-4 * np.abs(g["maps"]).max()
+
+
+def test_mobilenetv3_oracle_matches_golden():
+    """MobileNetV3 + DCN IDAUp (BASELINE config 5): oracle restatement vs the reference module's golden maps."""
+    g = np.load(os.path.join(GOLD, "mbv3_128x160.npz"))
+    B, H, W = [int(v) for v in g["shape"]]
+    from centerpose_b200.model import create_model
+    from centerpose_b200.config import default_cfg
+    cfg = default_cfg("mobilenetv3")
+    sd = conditioned_state_dict(create_model(cfg.MODEL.NAME, cfg.MODEL.HEAD_CONV, cfg).state_dict(), 317)
+    assert len(sd) == 471
+    assert _sha(*[sd[k].numpy() for k in sorted(sd) if sd[k].is_floating_point()]) == str(g["sd_sha"])
+    x = synth_images(B, H, W, seed=317)
+    maps = torch.cat(dla_ref.forward(sd, x, arch="mobilenetv3"), dim=1).numpy()
+    assert np.abs(maps - g["maps"]).max() <= 1e-4 * np.abs(g["maps"]).max()
