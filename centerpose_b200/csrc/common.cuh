@@ -47,5 +47,19 @@ __device__ __forceinline__ float act_fn(float v, uint32_t act) {
   const float r = fminf(fmaxf(v + 3.f, 0.f), 6.f);
   return act == CPB200_FLAG_HSWISH ? v * r / 6.f : r / 6.f;
 }
+// bf16-output variant: multiply by 1/6 instead of the IEEE division (differs from act_fn by <= 1 ulp of fp32,
+// far below the bf16 rounding that follows).  The division cost 20+ instructions per element and made the
+// MobileNetV3 expand convs and depthwise convs instruction-bound (profiles/r01_launches_mbv3_v1_summary.txt).
+template <typename T>
+__device__ __forceinline__ float act_out(float v, uint32_t act) {
+  if constexpr (sizeof(T) == 4) {
+    return act_fn(v, act);
+  } else {
+    if (act == CPB200_FLAG_RELU) return fmaxf(v, 0.f);
+    if (act == 0u) return v;
+    const float r = fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+    return act == CPB200_FLAG_HSWISH ? v * r : r;
+  }
+}
 
 }  // namespace cpb

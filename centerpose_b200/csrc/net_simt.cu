@@ -237,21 +237,21 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
 #pragma unroll
       for (int j = 0; j < TN; ++j)
         if (nb + j < a.cout) {
-          float x = v[j]; x = cpb::act_fn(x, act);
+          float x = v[j]; x = cpb::act_out<T>(x, act);
           o[(((size_t)b * a.out_ch_total + a.out_ch_off + nb + j) * a.Hd + hd) * a.Wd + wd] = x;
         }
     } else if (a.flags & CPB200_FLAG_OUT_F32) {
       float *o = static_cast<float *>(a.dst) + pix * a.cout;
 #pragma unroll
       for (int j = 0; j < TN; ++j)
-        if (nb + j < a.cout) { float x = v[j]; x = cpb::act_fn(x, act); o[nb + j] = x; }
+        if (nb + j < a.cout) { float x = v[j]; x = cpb::act_out<T>(x, act); o[nb + j] = x; }
     } else {
       T *o = static_cast<T *>(a.dst) + pix * a.cout;
       const T *rs = a.res ? static_cast<const T *>(a.res) + pix * a.cout : nullptr;
       if (nb + TN <= a.cout && (a.cout & 3) == 0) {
         float4 x = make_float4(v[0], v[1], v[2], v[3]);
         if (rs) { float4 r4 = Act<T>::ld4(rs + nb); x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w; }
-        if (act) { x.x = cpb::act_fn(x.x, act); x.y = cpb::act_fn(x.y, act); x.z = cpb::act_fn(x.z, act); x.w = cpb::act_fn(x.w, act); }
+        if (act) { x.x = cpb::act_out<T>(x.x, act); x.y = cpb::act_out<T>(x.y, act); x.z = cpb::act_out<T>(x.z, act); x.w = cpb::act_out<T>(x.w, act); }
         Act<T>::st4(o + nb, x);
       } else {
 #pragma unroll
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
           if (nb + j < a.cout) {
             float x = v[j];
             if (rs) x += Act<T>::ld(rs + nb + j);
-            x = cpb::act_fn(x, act);
+            x = cpb::act_out<T>(x, act);
             Act<T>::st(o + nb + j, x);
           }
       }
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(128) stem_kernel(const float *__restrict__ x, 
 #pragma unroll
     for (int n = 0; n < COUT; n += 4) {
       float4 v = make_float4(acc[p][n], acc[p][n + 1], acc[p][n + 2], acc[p][n + 3]);
-      if (act) { v.x = cpb::act_fn(v.x, act); v.y = cpb::act_fn(v.y, act); v.z = cpb::act_fn(v.z, act); v.w = cpb::act_fn(v.w, act); }
+      if (act) { v.x = cpb::act_out<T>(v.x, act); v.y = cpb::act_out<T>(v.y, act); v.z = cpb::act_out<T>(v.z, act); v.w = cpb::act_out<T>(v.w, act); }
       Act<T>::st4(o + n, v);
     }
   }
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(const T *__restrict__
       const float4 s4 = Act<T>::ld4(skip + (size_t)i * 4);
       v.x += s4.x; v.y += s4.y; v.z += s4.z; v.w += s4.w;
     }
-    if (act) { v.x = cpb::act_fn(v.x, act); v.y = cpb::act_fn(v.y, act); v.z = cpb::act_fn(v.z, act); v.w = cpb::act_fn(v.w, act); }
+    if (act) { v.x = cpb::act_out<T>(v.x, act); v.y = cpb::act_out<T>(v.y, act); v.z = cpb::act_out<T>(v.z, act); v.w = cpb::act_out<T>(v.w, act); }
     Act<T>::st4(y + (size_t)i * 4, v);
   }
 }
@@ -500,8 +500,76 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T *__restrict__ x, T 
     T *o = y + (size_t)i * VEC;
 #pragma unroll
     for (int q = 0; q < VEC; q += 4)
-      Act<T>::st4(o + q, make_float4(cpb::act_fn(acc[q], act), cpb::act_fn(acc[q + 1], act), cpb::act_fn(acc[q + 2], act),
-                                     cpb::act_fn(acc[q + 3], act)));
+      Act<T>::st4(o + q, make_float4(cpb::act_out<T>(acc[q], act), cpb::act_out<T>(acc[q + 1], act), cpb::act_out<T>(acc[q + 2], act),
+                                     cpb::act_out<T>(acc[q + 3], act)));
+  }
+}
+
+// Register-tiled variant for the shapes MobileNetV3 uses (k in {3,5}, stride in {1,2}): a thread produces PXW
+// adjacent output pixels of one row for VEC channels, so each input vector of the row segment is loaded once and
+// each tap's weight vector feeds PXW pixels (the generic kernel above issues 3 loads per tap per pixel).
+template <typename T, int VEC, int K, int S, int PXW>
+__global__ void __launch_bounds__(256) dwconv_tiled_kernel(const T *__restrict__ x, T *__restrict__ y, const float *__restrict__ w,
+                                                           const float *__restrict__ bias, long long total, int H, int W, int C,
+                                                           int Ho, int Wo, uint32_t act) {
+  constexpr int NIN = (PXW - 1) * S + K, PAD = K / 2;
+  const int CV = C / VEC, WG = (Wo + PXW - 1) / PXW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long p = i / CV;
+    const int wg = (int)(p % WG); p /= WG;
+    const int ho = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const int c0 = cv * VEC, wo0 = wg * PXW;
+    float acc[PXW][VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; q += 4) {
+      const float4 b4 = bias ? __ldg(reinterpret_cast<const float4 *>(bias + c0 + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int px = 0; px < PXW; ++px) { acc[px][q] = b4.x; acc[px][q + 1] = b4.y; acc[px][q + 2] = b4.z; acc[px][q + 3] = b4.w; }
+    }
+    const int wi0 = wo0 * S - PAD;
+#pragma unroll 1
+    for (int r = 0; r < K; ++r) {
+      const int hi = ho * S - PAD + r;
+      if (hi < 0 || hi >= H) continue;
+      const T *xr = x + (((size_t)b * H + hi) * W) * C + c0;
+      float in[NIN][VEC];
+#pragma unroll
+      for (int j = 0; j < NIN; ++j) {
+        const int wi = wi0 + j;
+        const bool okw = wi >= 0 && wi < W;
+#pragma unroll
+        for (int q = 0; q < VEC; q += 4) {
+          const float4 v = okw ? Act<T>::ld4(xr + (size_t)wi * C + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          in[j][q] = v.x; in[j][q + 1] = v.y; in[j][q + 2] = v.z; in[j][q + 3] = v.w;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < K; ++t) {
+        const float *wp = w + (size_t)(r * K + t) * C + c0;
+#pragma unroll
+        for (int q = 0; q < VEC; q += 4) {
+          const float4 ww = __ldg(reinterpret_cast<const float4 *>(wp + q));
+#pragma unroll
+          for (int px = 0; px < PXW; ++px) {
+            acc[px][q] = fmaf(in[px * S + t][q], ww.x, acc[px][q]);
+            acc[px][q + 1] = fmaf(in[px * S + t][q + 1], ww.y, acc[px][q + 1]);
+            acc[px][q + 2] = fmaf(in[px * S + t][q + 2], ww.z, acc[px][q + 2]);
+            acc[px][q + 3] = fmaf(in[px * S + t][q + 3], ww.w, acc[px][q + 3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int px = 0; px < PXW; ++px) {
+      if (wo0 + px >= Wo) break;
+      T *o = y + ((((size_t)b * Ho + ho) * Wo) + wo0 + px) * C + c0;
+#pragma unroll
+      for (int q = 0; q < VEC; q += 4)
+        Act<T>::st4(o + q, make_float4(cpb::act_out<T>(acc[px][q], act), cpb::act_out<T>(acc[px][q + 1], act),
+                                       cpb::act_out<T>(acc[px][q + 2], act), cpb::act_out<T>(acc[px][q + 3], act)));
+    }
   }
 }
 
@@ -646,6 +714,17 @@ int run_op_simt(const cpb200_op &op, cudaStream_t st) {
       constexpr int VEC = sizeof(T) == 2 ? 8 : 4;
       const int C = op.cin[0];
       if (C % VEC || op.kh != op.kw || op.cout != C) return cpb::fail(CPB200_ERR_ARG, "dwconv: C %% %d != 0 or non-square kernel", VEC);
+#define DW_TILED(KK, SS, PX)                                                                                   \
+  if (op.kh == KK && op.stride == SS && op.pad_h == KK / 2) {                                                    \
+    const long long tot = (long long)op.B * op.Ho * ((op.Wo + PX - 1) / PX) * (C / VEC);                         \
+    const unsigned g = (unsigned)std::min<long long>((tot + 255) / 256, 148LL * 32);                            \
+    dwconv_tiled_kernel<T, VEC, KK, SS, PX><<<g, 256, 0, st>>>(static_cast<const T *>(op.src[0]),                \
+        static_cast<T *>(op.dst), static_cast<const float *>(op.weight), op.bias, tot, op.H, op.W, C, op.Ho,     \
+        op.Wo, op.flags & CPB_ACT_MASK);                                                                        \
+    return cpb::check_launch("dwconv_tiled_kernel");                                                            \
+  }
+      DW_TILED(3, 1, 4) DW_TILED(5, 1, 4) DW_TILED(3, 2, 2) DW_TILED(5, 2, 2)
+#undef DW_TILED
       const long long total = (long long)op.B * op.Ho * op.Wo * (C / VEC);
       const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 32);
       dwconv_kernel<T, VEC><<<grid, 256, 0, st>>>(static_cast<const T *>(op.src[0]), static_cast<T *>(op.dst),

@@ -245,13 +245,13 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
                 float4 v4 = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                if (act) { v4.x = cpb::act_fn(v4.x, act); v4.y = cpb::act_fn(v4.y, act); v4.z = cpb::act_fn(v4.z, act); v4.w = cpb::act_fn(v4.w, act); }
+                if (act) { v4.x = cpb::act_out<__nv_bfloat16>(v4.x, act); v4.y = cpb::act_out<__nv_bfloat16>(v4.y, act); v4.z = cpb::act_out<__nv_bfloat16>(v4.z, act); v4.w = cpb::act_out<__nv_bfloat16>(v4.w, act); }
                 *reinterpret_cast<float4 *>(o + j) = v4;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (nb + j < a.cout) o[j] = cpb::act_fn(f[j], act);
+                if (nb + j < a.cout) o[j] = cpb::act_out<__nv_bfloat16>(f[j], act);
             }
           } else {
             __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(a.dst) + pix * a.cout_store + nb;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
             }
             if (act) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = cpb::act_fn(f[j], act);
+              for (int j = 0; j < 16; ++j) f[j] = cpb::act_out<__nv_bfloat16>(f[j], act);
             }
             uint4 o0, o1;
             __nv_bfloat162 *ob0 = reinterpret_cast<__nv_bfloat162 *>(&o0), *ob1 = reinterpret_cast<__nv_bfloat162 *>(&o1);

@@ -183,6 +183,35 @@ def gen_mbv3(ns):
         print(f"mobilenetv3 {tag}: oracle max abs err {err:.2e} (scale {scale:.1f})")
 
 
+def gen_soft_nms(ns=None):
+    """Golden vectors of the reference's own Cython ``soft_nms_39`` compiled here (oracle/build_ref.py)."""
+    from oracle.build_ref import load
+    from centerpose_b200.soft_nms import soft_nms_39
+    nms = load()
+    assert nms is not None, "reference tree absent"
+    rng = np.random.RandomState(39)
+    ins, outs, keeps, params = [], [], [], []
+    for trial in range(24):
+        N = int(rng.randint(1, 100))
+        c = rng.uniform(0, 400, size=(N, 2)); wh = rng.uniform(5, 200, size=(N, 2))
+        rows = np.zeros((100, 56), np.float32)
+        rows[:N, 0:2] = c - wh / 2; rows[:N, 2:4] = c + wh / 2; rows[:N, 4] = rng.uniform(0, 1, N)
+        if trial % 4 == 0:
+            rows[:N, 4] = np.round(rows[:N, 4], 1)                         # score ties
+        rows[:N, 5:] = rng.uniform(0, 400, size=(N, 51))
+        method, Nt, thr = trial % 3, (0.3, 0.5, 0.7)[trial % 3], (0.001, 0.05)[trial % 2]
+        a = rows[:N].copy(); b = rows[:N].copy()
+        ka = nms.soft_nms_39(a, sigma=0.5, Nt=Nt, threshold=thr, method=method)
+        kb = soft_nms_39(b, sigma=0.5, Nt=Nt, threshold=thr, method=method)
+        assert list(ka) == list(kb), (trial, len(ka), len(kb))
+        assert np.abs(a - b).max() <= 2e-7, float(np.abs(a - b).max())     # 1 ulp of a score in (0,1]: see test
+        out = np.zeros((100, 56), np.float32); out[:N] = a
+        ins.append(rows); outs.append(out); keeps.append(len(ka)); params.append([N, method, Nt, thr])
+    np.savez_compressed(os.path.join(GOLD, "soft_nms.npz"), boxes=np.stack(ins), out=np.stack(outs),
+                        keep=np.array(keeps), params=np.array(params, np.float64))
+    print("soft_nms_39: port == compiled reference on 24 cases (keep lists equal, scores within 1 ulp)")
+
+
 def gen_post(ns):
     rng = np.random.RandomState(3)
     dets = rng.uniform(0, 128, size=(1, 100, 56)).astype(np.float32)
@@ -225,6 +254,7 @@ def main():
     gen_res50(ns)
     gen_hrnet(ns)
     gen_mbv3(ns)
+    gen_soft_nms(ns)
     print("golden fixtures written to", GOLD)
 
 

@@ -458,7 +458,8 @@ def test_mobilenet_ops_match_torch(precision):
     dt = torch.float32 if precision == "fp32" else torch.bfloat16
     B, C, H, W = 2, 48, 13, 18
     x = (torch.randn(B, C, H, W, generator=g) * 2).bfloat16().float()
-    for k, stride, act, fn in ((3, 1, "relu", F.relu), (5, 2, "hswish", hswish), (5, 1, None, lambda t: t), (3, 2, "hswish", hswish)):
+    for k, stride, act, fn in ((3, 1, "relu", F.relu), (5, 2, "hswish", hswish), (5, 1, None, lambda t: t), (3, 2, "hswish", hswish),
+                                (7, 1, "relu", F.relu)):          # 7x7 takes the generic (untiled) kernel
         w = torch.randn(C, 1, k, k, generator=g) * 0.3; b = torch.randn(C, generator=g)
         pb = _builder(B, precision)
         y = pb.dwconv(pb.external(_nhwc(x, dt)), w.to(DEV), b.to(DEV), stride=stride, act=act)
