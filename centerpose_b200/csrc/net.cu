@@ -6,6 +6,8 @@ int run_op_simt_dispatch(const cpb200_op &op, cudaStream_t st);
 int tc_prepare_op(cpb200_op &op);
 int tc_release_op(cpb200_op &op);
 int tc_run_op(const cpb200_op &op, cudaStream_t st);
+bool stem_tc_eligible(const cpb200_op &op);
+int stem_tc_run(const cpb200_op &op, cudaStream_t st);
 }  // namespace cpb
 
 static int validate(const cpb200_op &op, int i) {
@@ -31,7 +33,9 @@ extern "C" int cpb200_prepare_ops(cpb200_op *ops, int n) {
   for (int i = 0; i < n; ++i) {
     int rc = validate(ops[i], i);
     if (rc) return rc;
-    if (ops[i].flags & CPB200_FLAG_TC) {
+    if (ops[i].type == CPB200_OP_STEM && (ops[i].flags & CPB200_FLAG_TC)) {
+      if (!cpb::stem_tc_eligible(ops[i])) return cpb::fail(CPB200_ERR_ARG, "op %d: shape not supported by the tensor-core stem", i);
+    } else if (ops[i].flags & CPB200_FLAG_TC) {
       rc = cpb::tc_prepare_op(ops[i]);
       if (rc) return rc;
     }
@@ -50,7 +54,10 @@ extern "C" int cpb200_run_ops(const cpb200_op *ops, int n, void *stream) {
   if (!ops || n < 0) return cpb::fail(CPB200_ERR_ARG, "run_ops: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int i = 0; i < n; ++i) {
-    int rc = (ops[i].flags & CPB200_FLAG_TC) ? cpb::tc_run_op(ops[i], st) : cpb::run_op_simt_dispatch(ops[i], st);
+    int rc;
+    if (!(ops[i].flags & CPB200_FLAG_TC)) rc = cpb::run_op_simt_dispatch(ops[i], st);
+    else if (ops[i].type == CPB200_OP_STEM) rc = cpb::stem_tc_run(ops[i], st);
+    else rc = cpb::tc_run_op(ops[i], st);
     if (rc) return rc;
   }
   return CPB200_OK;

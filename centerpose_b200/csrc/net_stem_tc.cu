@@ -1,0 +1,260 @@
+// Tensor-core stem: 7x7 (stride 1 or 2, pad 3) convolution of the NCHW fp32 network input with Cin = 3,
+// + folded BatchNorm bias + activation, NHWC bf16 output          (pose_dla_dcn.py:246-250 base_layer,
+// msra_resnet.py:112-116 conv1/bn1/relu).
+//
+// Why: on CUDA cores the 7x7x3 -> 16 stem costs 37 632 FMAs per output pixel (1.07 ms for 32 x 512^2,
+// 13 % of the DLA-34 step at half the fp32 FMA peak).  Here the im2col happens IN SHARED MEMORY: producer
+// threads build the K-major bf16 operand tile straight from a staged input patch, one tcgen05.mma chain
+// per 128-pixel tile does the arithmetic, and HBM only sees the image once and the output once.  (A first
+// attempt that materialised a 32-channel im2col tensor in HBM was slower than the CUDA-core kernel.)
+//
+//   K index  k = (c * 7 + r) * 8 + s   (s = 0..7; the 8th column has a zero weight), 168 real + 24 zero = 192
+//            => every 16-byte chunk of an operand row is 8 CONSECUTIVE input pixels of one (channel, row).
+//   A tile   128 pixels (8 rows x 16 cols) x 192, three 64-wide slabs in the 128-byte-swizzled UMMA layout
+//            (chunk j of row m at (j ^ (m & 7)) * 16), written with st.shared.v4 + fence.proxy.async.
+//   B tile   weights, pre-swizzled by the host (plan.py::_pack_stem_tc), copied to shared memory once per CTA.
+//   warps    0-3 producers (thread m builds row m), 4 MMA issuer + TMEM owner, 5-8 epilogue.
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int ST_THREADS = 288;
+constexpr int TH = 8, TW = 16;                 // output tile (M = 128)
+constexpr int KW8 = 8, KH = 7, CIN = 3;
+constexpr int NCHUNK = CIN * KH;               // 21 real 16-byte chunks per operand row
+constexpr int SLABS = 3;                       // K = 192
+constexpr int A_SLAB_BYTES = 128 * 128;        // 128 rows x 128 B
+constexpr int A_STAGE_BYTES = SLABS * A_SLAB_BYTES;
+constexpr int NSTAGE = 3;
+constexpr int NACC = 4;
+
+struct StemArgs {
+  const float *x;            // (B,3,H,W) fp32
+  __nv_bfloat16 *y;          // (B,Ho,Wo,N) bf16
+  const uint4 *wimg;         // pre-swizzled B operand image: SLABS x (N x 128 B)
+  const float *bias;
+  int B, H, W, Ho, Wo;
+  int tiles_h, tiles_w, total_tiles;
+  uint32_t act;
+};
+
+template <int N, int S>
+__global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const StemArgs a) {
+  constexpr int PH = (TH - 1) * S + KH;                   // staged input rows per tile
+  constexpr int PW = (TW - 1) * S + KW8;                  // staged input columns per tile
+  constexpr int PP = (S == 1) ? 48 : PW + 1;              // row pitch (words): S=1 keeps the two half-warps on disjoint banks
+  constexpr int B_SLAB_BYTES = N * 128;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + NSTAGE * A_STAGE_BYTES;
+  float *patch = reinterpret_cast<float *>(smem_raw + (smem_base - smem_u32(smem_raw)) + NSTAGE * A_STAGE_BYTES + SLABS * B_SLAB_BYTES);
+  __shared__ __align__(8) uint64_t bars[2 * NSTAGE + 2 * NACC];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_bias[N];
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[NSTAGE]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * NSTAGE]), tempty0 = smem_u32(&bars[2 * NSTAGE + NACC]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = (NACC * N) < 32 ? 32u : (uint32_t)(NACC * N);
+
+  // ---- one-time setup: barriers, TMEM, zeroed A stages (the 3 pad chunks stay zero), weights, bias ----
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 128); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < NSTAGE * A_STAGE_BYTES / 16; i += ST_THREADS)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a_base + i * 16), "r"(0u) : "memory");
+  for (int i = threadIdx.x; i < SLABS * B_SLAB_BYTES / 16; i += ST_THREADS) {
+    const uint4 v = __ldg(a.wimg + i);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(b_base + i * 16), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+  for (int i = threadIdx.x; i < N; i += ST_THREADS) s_bias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  auto decode_tile = [&](int t, int &n, int &h0, int &w0) {
+    const int tw = t % a.tiles_w; t /= a.tiles_w;
+    const int th = t % a.tiles_h; n = t / a.tiles_h;
+    h0 = th * TH; w0 = tw * TW;
+  };
+
+  if (warp < 4) {
+    // =============================== producers: patch -> swizzled K-major operand rows ===============================
+    const int m = threadIdx.x;                             // operand row = tile pixel (ty, tx)
+    const int ty = m >> 4, tx = m & 15;
+    int stage = 0; uint32_t phase = 0;
+    int pb = 0;                                            // patch double buffer
+    constexpr int NLD = (CIN * PH * PW + 127) / 128;       // patch elements per producer thread
+    float pre[NLD];
+    // The patch of tile i+1 is requested from global memory BEFORE tile i's operand rows are built and parked in
+    // registers meanwhile: without this every tile paid a full exposed DRAM/L2 round trip (2.7 us per tile).
+    auto fetch = [&](int t) {
+      int n, h0, w0; decode_tile(t, n, h0, w0);
+      const int hi0 = h0 * S - 3, wi0 = w0 * S - 3;
+      const float *xin = a.x + (size_t)n * CIN * a.H * a.W;
+#pragma unroll
+      for (int j = 0; j < NLD; ++j) {
+        const int i = m + j * 128;
+        const int col = i % PW, rr = i / PW;               // rr = c * PH + row
+        const int row = rr % PH, c = rr / PH;
+        const int hi = hi0 + row, wi = wi0 + col;
+        const bool okl = i < CIN * PH * PW && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
+        pre[j] = okl ? __ldg(xin + ((size_t)c * a.H + hi) * a.W + wi) : 0.f;
+      }
+    };
+    if ((int)blockIdx.x < a.total_tiles) fetch(blockIdx.x);
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      float *pbuf = patch + pb * (CIN * PH * PP);
+#pragma unroll
+      for (int j = 0; j < NLD; ++j) {
+        const int i = m + j * 128;
+        if (i < CIN * PH * PW) pbuf[(i / PW) * PP + (i % PW)] = pre[j];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // patch complete (the other buffer is free: see below)
+      if (t + (int)gridDim.x < a.total_tiles) fetch(t + gridDim.x);
+      mbar_wait(empty0 + 8 * stage, phase ^ 1);
+      const uint32_t sa = a_base + stage * A_STAGE_BYTES + m * 128;
+      const float *prow = pbuf + (ty * S) * PP + tx * S;
+#pragma unroll
+      for (int q = 0; q < NCHUNK; ++q) {
+        const int c = q / KH, r = q % KH;
+        const float *p = prow + (c * PH + r) * PP;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(p[0], p[1]), h1 = __floats2bfloat162_rn(p[2], p[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(p[4], p[5]), h3 = __floats2bfloat162_rn(p[6], p[7]);
+        const uint32_t dst = sa + (q >> 3) * A_SLAB_BYTES + (((q & 7) ^ (m & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(*reinterpret_cast<uint32_t *>(&h0)),
+                     "r"(*reinterpret_cast<uint32_t *>(&h1)), "r"(*reinterpret_cast<uint32_t *>(&h2)),
+                     "r"(*reinterpret_cast<uint32_t *>(&h3)) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(full0 + 8 * stage);
+      if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      // the next tile fills the OTHER patch buffer; by the time a thread returns to this one it has passed the
+      // next tile's bar.sync, i.e. every producer has finished reading this buffer.
+      pb ^= 1;
+    }
+  } else if (warp == 4) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t accphase = 0;
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
+      mbar_wait(full0 + 8 * stage, phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + acc * N;
+        const uint64_t ad0 = make_desc(a_base + stage * A_STAGE_BYTES, 128, 2);
+        const uint64_t bd0 = make_desc(b_base, 128, 2);
+#pragma unroll
+        for (int sl = 0; sl < SLABS; ++sl) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, ad0 + (uint32_t)(sl * (A_SLAB_BYTES >> 4) + 2 * k), bd0 + (uint32_t)(sl * (B_SLAB_BYTES >> 4) + 2 * k),
+                      idesc, (sl > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * stage);
+        umma_commit(tfull0 + 8 * acc);
+      }
+      __syncwarp();
+      if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      if (++acc == NACC) { acc = 0; accphase ^= 1; }
+    }
+  } else {
+    // =============================== epilogue (warps 5..8) ===============================
+    const int q = warp & 3;                                // TMEM lane quadrant this warp may read
+    const int m = q * 32 + lane;
+    const int ty = m >> 4, tx = m & 15;
+    int acc = 0; uint32_t accphase = 0;
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      int n, h0, w0; decode_tile(t, n, h0, w0);
+      const int ho = h0 + ty, wo = w0 + tx;
+      const bool ok = ho < a.Ho && wo < a.Wo;
+      __nv_bfloat16 *o = a.y + (((size_t)n * a.Ho + ho) * a.Wo + wo) * N;
+      mbar_wait(tfull0 + 8 * acc, accphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N;
+#pragma unroll
+      for (int c = 0; c < N / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c * 16, v);
+        tmem_ld_wait();
+        if (ok) {
+          uint4 o0, o1;
+          __nv_bfloat162 *ob0 = reinterpret_cast<__nv_bfloat162 *>(&o0), *ob1 = reinterpret_cast<__nv_bfloat162 *>(&o1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ob0[j] = __floats2bfloat162_rn(cpb::act_out<__nv_bfloat16>(__uint_as_float(v[2 * j]) + s_bias[c * 16 + 2 * j], a.act),
+                                           cpb::act_out<__nv_bfloat16>(__uint_as_float(v[2 * j + 1]) + s_bias[c * 16 + 2 * j + 1], a.act));
+            ob1[j] = __floats2bfloat162_rn(cpb::act_out<__nv_bfloat16>(__uint_as_float(v[8 + 2 * j]) + s_bias[c * 16 + 8 + 2 * j], a.act),
+                                           cpb::act_out<__nv_bfloat16>(__uint_as_float(v[8 + 2 * j + 1]) + s_bias[c * 16 + 8 + 2 * j + 1], a.act));
+          }
+          reinterpret_cast<uint4 *>(o + c * 16)[0] = o0;
+          reinterpret_cast<uint4 *>(o + c * 16)[1] = o1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (++acc == NACC) { acc = 0; accphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int N, int S>
+int launch_stem(const cpb200_op &op, cudaStream_t st) {
+  constexpr int PH = (TH - 1) * S + KH, PW = (TW - 1) * S + KW8, PP = (S == 1) ? 48 : PW + 1;
+  StemArgs a;
+  a.x = static_cast<const float *>(op.src[0]); a.y = static_cast<__nv_bfloat16 *>(op.dst);
+  a.wimg = static_cast<const uint4 *>(op.weight); a.bias = op.bias;
+  a.B = op.B; a.H = op.H; a.W = op.W; a.Ho = op.Ho; a.Wo = op.Wo;
+  a.tiles_h = (op.Ho + TH - 1) / TH; a.tiles_w = (op.Wo + TW - 1) / TW;
+  a.total_tiles = op.B * a.tiles_h * a.tiles_w;
+  a.act = op.flags & CPB_ACT_MASK;
+  const size_t smem = 1024 + (size_t)NSTAGE * A_STAGE_BYTES + (size_t)SLABS * N * 128 + 2 * (size_t)CIN * PH * PP * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CPB_CUDA(cudaFuncSetAttribute(stem_tc_kernel<N, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int sms = tc::num_sms();
+  const int grid = a.total_tiles < sms ? a.total_tiles : sms;
+  stem_tc_kernel<N, S><<<grid, ST_THREADS, smem, st>>>(a);
+  return cpb::check_launch("stem_tc_kernel");
+}
+
+}  // namespace
+
+namespace cpb {
+
+bool stem_tc_eligible(const cpb200_op &op) {
+  return op.type == CPB200_OP_STEM && op.act_dtype == CPB200_BF16 && op.cin[0] == 3 && op.kh == 7 && op.kw == 7 &&
+         op.pad_h == 3 && op.pad_w == 3 && (op.stride == 1 || op.stride == 2) && (op.cout == 16 || op.cout == 64) &&
+         op.Ho == (op.H + 6 - 7) / op.stride + 1 && op.Wo == (op.W + 6 - 7) / op.stride + 1;
+}
+
+int stem_tc_run(const cpb200_op &op, cudaStream_t st) {
+  if (!stem_tc_eligible(op)) return fail(CPB200_ERR_ARG, "stem_tc: unsupported shape (needs 7x7, Cin 3, stride 1/2, cout 16/64, bf16)");
+  if (op.cout == 16 && op.stride == 1) return launch_stem<16, 1>(op, st);
+  if (op.cout == 16 && op.stride == 2) return launch_stem<16, 2>(op, st);
+  if (op.cout == 64 && op.stride == 1) return launch_stem<64, 1>(op, st);
+  return launch_stem<64, 2>(op, st);
+}
+
+}  // namespace cpb

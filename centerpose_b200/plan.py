@@ -152,6 +152,21 @@ class PlanBuilder:
         p[:, :co, :] = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
         return self._dev(p, torch.bfloat16)
 
+    def _pack_stem_tc(self, w: torch.Tensor):
+        """(N,3,7,7) fp32 -> the 128-byte-swizzled K-major B operand image of csrc/net_stem_tc.cu:
+        k = (c*7 + r)*8 + s (s = 7 and k >= 168 are zero), three 64-wide slabs of N rows x 128 bytes,
+        16-byte chunk j of row n stored at chunk j ^ (n & 7)."""
+        N = w.shape[0]
+        wk = torch.zeros(N, 3, 7, 8, dtype=torch.float32, device=w.device)
+        wk[..., :7] = w.float()
+        wk = torch.nn.functional.pad(wk.reshape(N, 168), (0, 24))                   # (N, 192)
+        blk = wk.reshape(N, 3, 8, 8).permute(1, 0, 2, 3)                            # [slab][n][chunk j][e]
+        n_idx = torch.arange(N, device=w.device).view(1, N, 1, 1).expand(3, N, 8, 8)
+        j_idx = torch.arange(8, device=w.device).view(1, 1, 8, 1).expand(3, N, 8, 8)
+        img = torch.zeros(3, N, 8, 8, dtype=torch.float32, device=w.device)
+        img.scatter_(2, (j_idx ^ (n_idx & 7)), blk.contiguous())
+        return self._dev(img, torch.bfloat16)
+
     def _tc_ok(self, srcs, co, kh, kw, stride, out, out_map, Wo):
         return (self.use_tc and stride in (1, 2) and Wo >= 8
                 and all(s.C % 16 == 0 and s.kind == "act" for s in srcs)
@@ -160,12 +175,12 @@ class PlanBuilder:
     # ---- ops -------------------------------------------------------------------------------
     def stem(self, x: Sym, w, b, k, stride, pad, relu=True, act=None):
         co, ci = w.shape[0], w.shape[1]
-        if (self.use_tc and stride == 1 and k * ci <= 32 and co % 16 == 0 and pad == k // 2
-                and os.environ.get("CPB200_TC_STEM", "0") == "1"):
-            # tensor-core stem (opt-in, CPB200_TC_STEM=1): gather the k horizontal taps of every pixel into 32
-            # channels, then a k x 1 conv with K = k * 32 runs on the halo-reuse tcgen05 kernel.  Correct
-            # (tests/test_net_gpu.py::test_stem_tensor_core_path) but measured SLOWER than the register-tiled
-            # CUDA-core stem at B=32 512x512 (1430 us vs 1045 us: 537 MB intermediate + 65 536 N=16 tiles), so off.
+        mode = os.environ.get("CPB200_TC_STEM", "1")
+        if (self.use_tc and mode == "im2col" and stride == 1 and k * ci <= 32 and co % 16 == 0 and pad == k // 2):
+            # first tensor-core stem (kept for the record, CPB200_TC_STEM=im2col): gather the k horizontal taps of
+            # every pixel into 32 channels IN HBM, then a k x 1 conv with K = k * 32 on the halo-reuse kernel.
+            # Correct (tests/test_net_gpu.py::test_stem_im2col_path) but measured SLOWER than the CUDA-core stem at
+            # B=32 512x512 (1430 us vs 1045 us: 537 MB intermediate + 65 536 N=16 tiles).
             t = self._sym(32, x.H, x.W)
             self._emit(_PendingOp(type=OP_IM2COL_W, flags=0, k=(1, k), stride=1, pad=(0, pad), weight=None,
                                   bias=None, cout=32), [x], t)
@@ -173,10 +188,18 @@ class PlanBuilder:
             # w2[o, s*ci + c, r, 0] = w[o, c, r, s]
             w2[:, :k * ci, :, 0] = w.float().permute(0, 3, 1, 2).reshape(co, k * ci, k)
             return self.conv([t], w2, b.float(), stride=1, relu=relu, pad_hw=(pad, 0))
+        flags = _ACT_FLAG[act] if act else (FLAG_RELU if relu else 0)
+        if (self.use_tc and mode != "0" and k == 7 and ci == 3 and pad == 3 and stride in (1, 2) and co in (16, 64)):
+            # tensor-core stem with the im2col done in shared memory (csrc/net_stem_tc.cu)
+            Ho = (x.H + 2 * pad - k) // stride + 1; Wo = (x.W + 2 * pad - k) // stride + 1
+            y = self._sym(co, Ho, Wo)
+            self._emit(_PendingOp(type=OP_STEM, flags=flags | FLAG_TC, k=(k, k), stride=stride, pad=(pad, pad),
+                                  weight=self._pack_stem_tc(w), bias=self._dev(b), cout=co), [x], y)
+            return y
         Ho = (x.H + 2 * pad - k) // stride + 1; Wo = (x.W + 2 * pad - k) // stride + 1
         y = self._sym(co, Ho, Wo)
         wp = self._dev(w.permute(2, 3, 1, 0).reshape(k * k * ci, co))
-        self._emit(_PendingOp(type=OP_STEM, flags=_ACT_FLAG[act] if act else (FLAG_RELU if relu else 0), k=(k, k), stride=stride,
+        self._emit(_PendingOp(type=OP_STEM, flags=flags, k=(k, k), stride=stride,
                               pad=(pad, pad), weight=wp, bias=self._dev(b), cout=co), [x], y)
         return y
 

@@ -108,7 +108,9 @@ int cpb200_sigmoid_inplace(float *x, size_t n, void *stream);
 
 enum cpb200_op_type {
   CPB200_OP_CONV = 1,        /* k x k conv (+bias)(+residual)(+ReLU); up to 4 channel-concatenated inputs */
-  CPB200_OP_STEM = 2,        /* NCHW fp32 image -> NHWC, small-Cin direct conv (+bias+ReLU)                */
+  CPB200_OP_STEM = 2,        /* NCHW fp32 image -> NHWC, small-Cin direct conv (+bias+activation); with CPB200_FLAG_TC
+                                (7x7, Cin 3, stride 1/2, cout 16/64, bf16) the im2col is built in shared memory and
+                                the arithmetic runs on tcgen05 (weight = pre-swizzled operand image, plan.py)   */
   CPB200_OP_MAXPOOL = 3,     /* k x k / stride s / pad p max-pool, NHWC                                     */
   CPB200_OP_DWDECONV_ADD = 4,/* depthwise ConvTranspose2d(k=2f,s=f,p=f/2) (+ skip add), NHWC  (IDAUp up_*) */
   CPB200_OP_DCN = 5,         /* modulated deformable 3x3 conv (DCNv2 forward) (+bias)(+ReLU)                */

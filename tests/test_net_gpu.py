@@ -265,14 +265,35 @@ def test_dcn_zero_offset_identity():
     assert (2 * out - x).abs().max().item() < 1e-6
 
 
-def test_stem_tensor_core_path():
+@pytest.mark.parametrize("co,stride,H,W", [(16, 1, 48, 40), (16, 1, 21, 37), (64, 2, 64, 96), (64, 2, 38, 50), (16, 2, 32, 32),
+                                           (64, 1, 16, 24)])
+def test_stem_tensor_core_kernel(co, stride, H, W):
+    """csrc/net_stem_tc.cu: 7x7 Cin-3 stem with the im2col built in shared memory + tcgen05, vs torch fp32 on
+    bf16-rounded image and weights (partial tiles, both strides, both output widths)."""
+    B = 3
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, 3, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(co, 3, 7, 7, generator=g) * 0.1).bfloat16().float(); b = torch.randn(co, generator=g)
+    ref = F.relu(F.conv2d(x, w, b, stride=stride, padding=3))
+    pb = _builder(B, "bf16", tc=True); pb.H, pb.W = H, W
+    y = pb.stem(pb.input(3), w.to(DEV), b.to(DEV), 7, stride, 3, relu=True)
+    assert [o.type for o in pb.ops] == [2] and pb.ops[0].flags & 8
+    plan = pb.build(); plan.bind(x.to(DEV), {}); plan.run(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = _nchw(plan.tensor(y))
+    assert got.shape == ref.shape
+    err = (got - ref).abs().max().item()
+    assert err <= 1e-2 * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+def test_stem_im2col_path():
     """7x7 stem lowered to im2col-W (32 ch) + 7x1 tcgen05 halo conv vs torch fp32 on bf16-rounded data."""
     B, H, W = 2, 48, 40
     g = torch.Generator().manual_seed(4)
     x = torch.randn(B, 3, H, W, generator=g).bfloat16().float()
     w = (torch.randn(16, 3, 7, 7, generator=g) * 0.1).bfloat16().float(); b = torch.randn(16, generator=g)
     ref = F.relu(F.conv2d(x, w, b, padding=3))
-    os.environ["CPB200_TC_STEM"] = "1"
+    os.environ["CPB200_TC_STEM"] = "im2col"
     try:
         pb = _builder(B, "bf16", tc=True); pb.H, pb.W = H, W
         y = pb.stem(pb.input(3), w.to(DEV), b.to(DEV), 7, 1, 3, relu=True)

@@ -32,7 +32,7 @@ def main():
         x = torch.randn(B, 3, 512, 512, generator=g).to(dev)
         y = pb.stem(pb.input(3), torch.randn(16, 3, 7, 7, generator=g).to(dev) * 0.1, torch.zeros(16, device=dev), 7, 1, 3)
         flops = 2.0 * B * 512 * 512 * 16 * 147
-        name = name + ("(tc)" if len(pb.ops) == 2 else "(simt)")
+        name = name + ("(tc)" if (pb.ops[0].flags & 8 or len(pb.ops) == 2) else "(simt)")
     elif spec[0] == "dcn":
         _, ci, co, hw = spec
         xin = torch.randn(B, hw, hw, ci, generator=g).to(dev, torch.bfloat16)
