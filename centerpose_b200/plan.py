@@ -167,6 +167,20 @@ class PlanBuilder:
         img.scatter_(2, (j_idx ^ (n_idx & 7)), blk.contiguous())
         return self._dev(img, torch.bfloat16)
 
+    def _pack_stem_tc_h(self, w: torch.Tensor):
+        """(N,3,7,7) fp32 -> B operand image of the stride-1 tensor-core stem (stem_tc_h_kernel): one block per
+        horizontal tap s of N rows x 64 bytes, k = c*7 + r (21 real of 32), 64-byte swizzle: 16-byte chunk j of
+        row n stored at chunk j ^ ((n >> 1) & 3) (tap blocks are multiples of 1024 bytes)."""
+        N = w.shape[0]
+        wk = torch.zeros(7, N, 32, dtype=torch.float32, device=w.device)                # [s][n][k]
+        wk[:, :, :21] = w.float().permute(3, 0, 1, 2).reshape(7, N, 21)
+        blk = wk.reshape(7, N, 4, 8)                                                     # [s][n][chunk j][e]
+        n_idx = torch.arange(N, device=w.device).view(1, N, 1, 1).expand(7, N, 4, 8)
+        j_idx = torch.arange(4, device=w.device).view(1, 1, 4, 1).expand(7, N, 4, 8)
+        img = torch.zeros(7, N, 4, 8, dtype=torch.float32, device=w.device)
+        img.scatter_(2, (j_idx ^ ((n_idx >> 1) & 3)), blk.contiguous())
+        return self._dev(img, torch.bfloat16)
+
     def _tc_ok(self, srcs, co, kh, kw, stride, out, out_map, Wo):
         return (self.use_tc and stride in (1, 2) and Wo >= 8
                 and all(s.C % 16 == 0 and s.kind == "act" for s in srcs)
@@ -194,7 +208,8 @@ class PlanBuilder:
             Ho = (x.H + 2 * pad - k) // stride + 1; Wo = (x.W + 2 * pad - k) // stride + 1
             y = self._sym(co, Ho, Wo)
             self._emit(_PendingOp(type=OP_STEM, flags=flags | FLAG_TC, k=(k, k), stride=stride, pad=(pad, pad),
-                                  weight=self._pack_stem_tc(w), bias=self._dev(b), cout=co), [x], y)
+                                  weight=self._pack_stem_tc_h(w) if stride == 1 else self._pack_stem_tc(w),
+                                  bias=self._dev(b), cout=co), [x], y)
             return y
         Ho = (x.H + 2 * pad - k) // stride + 1; Wo = (x.W + 2 * pad - k) // stride + 1
         y = self._sym(co, Ho, Wo)
