@@ -6,6 +6,8 @@ int run_op_simt_dispatch(const cpb200_op &op, cudaStream_t st);
 int tc_prepare_op(cpb200_op &op);
 int tc_release_op(cpb200_op &op);
 int tc_run_op(const cpb200_op &op, cudaStream_t st);
+bool sp_eligible(const cpb200_op &op);
+int sp_run(const cpb200_op &op, cudaStream_t st);
 bool stem_tc_eligible(const cpb200_op &op);
 int stem_tc_run(const cpb200_op &op, cudaStream_t st);
 }  // namespace cpb
@@ -35,6 +37,8 @@ extern "C" int cpb200_prepare_ops(cpb200_op *ops, int n) {
     if (rc) return rc;
     if (ops[i].type == CPB200_OP_STEM && (ops[i].flags & CPB200_FLAG_TC)) {
       if (!cpb::stem_tc_eligible(ops[i])) return cpb::fail(CPB200_ERR_ARG, "op %d: shape not supported by the tensor-core stem", i);
+    } else if (cpb::sp_eligible(ops[i])) {
+      // small-channel 3x3 conv: SIMT-fed tcgen05 kernel, nothing to prepare (csrc/net_tc_sp.cu)
     } else if (ops[i].flags & CPB200_FLAG_TC) {
       rc = cpb::tc_prepare_op(ops[i]);
       if (rc) return rc;
@@ -57,6 +61,7 @@ extern "C" int cpb200_run_ops(const cpb200_op *ops, int n, void *stream) {
     int rc;
     if (!(ops[i].flags & CPB200_FLAG_TC)) rc = cpb::run_op_simt_dispatch(ops[i], st);
     else if (ops[i].type == CPB200_OP_STEM) rc = cpb::stem_tc_run(ops[i], st);
+    else if (!ops[i].tc && cpb::sp_eligible(ops[i])) rc = cpb::sp_run(ops[i], st);
     else rc = cpb::tc_run_op(ops[i], st);
     if (rc) return rc;
   }

@@ -1,0 +1,323 @@
+// Small-channel 3x3 convolutions (Cin = 16 or 32, stride 1 or 2, pad 1) on tcgen05 with SIMT-fed operands.
+//
+// Why not TMA here: a tiled TMA box is fetched row by row, one request per (pixel row of the box) — measured
+// ~2.5-3 ns per request per SM whatever its width.  With 16 or 32 channels a request is only 32 / 64 bytes, so
+// the halo-reuse kernel (csrc/net_tc3.cu, 180 requests per tile) and the tap-per-stage kernel (csrc/net_tc.cu,
+// 9 x 128 requests per tile for stride 2) spend 0.5-3.7 us per 128-pixel tile waiting for the copy engine:
+// DLA-34 level0 (16->16 @512^2) 437 us and level1 (16->32 /2) 410 us against a ~100 us HBM floor.  Here producer
+// THREADS fetch the halo with coalesced 16-byte loads (a tile row is one contiguous 320..1088-byte segment of the
+// NHWC tensor) and store it straight into the swizzled K-major layout the UMMA descriptors read — the same
+// scheme as the stem (csrc/net_stem_tc.cu): next tile's loads in flight while this tile is stored, several
+// producer groups on alternate tiles, no CTA-wide barrier.
+//
+//   halo     stride 1: 18 x 10 pixels, row R = hy*10 + hx;  tap (r,s) = window starting (r*10 + s) rows later,
+//            8-row-group stride 10 rows (as in net_tc3.cu).
+//            stride 2: 33 x 17 pixels split into four parity planes of 17 x 9 (R = plane*153 + (hy/2)*9 + hx/2)
+//            so that the 8 pixels of an output row are again 8 CONSECUTIVE operand rows: tap (r,s) = plane
+//            (r&1, s&1), window offset ((r/2)*9 + s/2) rows, group stride 9 rows.
+//   swizzle  32-byte (C=16) / 64-byte (C=32) pattern applied on absolute shared-memory address bits
+//            (chunk bit(s) [4..] ^= address bits [7..]); stage bases are 1024-aligned.
+//   weights  the ordinary tensor-core packing [tap][N][C] bf16 (plan.py::_pack_conv_tc), swizzled while being
+//            copied to shared memory once per CTA.
+#include "tc_common.cuh"
+
+#include <cstdlib>
+
+namespace {
+
+using namespace tc;
+
+constexpr int SP_TH = 16, SP_TW = 8;
+constexpr int SP_GROUPS = 2;
+constexpr int SP_PT = 256;                                // producer threads per group
+constexpr int SP_THREADS = SP_GROUPS * SP_PT + 5 * 32;    // + MMA warp + 4 epilogue warps
+constexpr int SP_NACC = 4;
+
+struct SpArgs {
+  const __nv_bfloat16 *x;      // (B,H,W,C)
+  const __nv_bfloat16 *w;      // [9][N][C]
+  const __nv_bfloat16 *res;    // optional (B,Ho,Wo,N)
+  __nv_bfloat16 *y;            // (B,Ho,Wo,N)
+  const float *bias;
+  int B, H, W, Ho, Wo;
+  int tiles_h, tiles_w, total_tiles;
+  uint32_t act;
+};
+
+template <int C, int S>
+struct SpGeom {
+  static constexpr int PIX_B = C * 2;                     // bytes per pixel row of the operand
+  static constexpr int CH = PIX_B / 16;                   // 16-byte chunks per pixel
+  static constexpr int HH = (SP_TH - 1) * S + 3, HW = (SP_TW - 1) * S + 3;       // halo extent in input pixels
+  static constexpr int PLANE_W = (S == 1) ? HW : (HW + 1) / 2;                   // operand rows per halo row (per plane)
+  static constexpr int PLANE_H = (S == 1) ? HH : (HH + 1) / 2;
+  static constexpr int PLANE_ROWS = PLANE_W * PLANE_H;
+  static constexpr int ROWS = (S == 1) ? PLANE_ROWS : 4 * PLANE_ROWS;
+  static constexpr int STAGE_BYTES = ((ROWS * PIX_B + 1023) / 1024) * 1024;
+  static constexpr int NCHUNK = HH * HW * CH;             // 16-byte chunks fetched per tile
+  static constexpr int NLD = (NCHUNK + SP_PT - 1) / SP_PT;
+  static constexpr uint32_t SWMASK = (C == 16) ? 1u : 3u;
+  static constexpr uint32_t LAYOUT = (C == 16) ? 6u : 4u; // UMMA layout type: 32-byte / 64-byte swizzle
+  static constexpr int NSTAGE = (STAGE_BYTES <= 12 * 1024) ? 6 : (STAGE_BYTES <= 20 * 1024 ? 5 : 4);
+};
+
+__device__ __forceinline__ uint32_t sp_swz(uint32_t off, uint32_t mask) {      // offset within a 1024-aligned region
+  return off ^ (((off >> 7) & mask) << 4);
+}
+
+template <int C, int N, int S>
+__global__ void __launch_bounds__(SP_THREADS, 1) conv_sp_kernel(const SpArgs a) {
+  using G = SpGeom<C, S>;
+  constexpr int B_TAP_BYTES = N * G::PIX_B;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + G::NSTAGE * G::STAGE_BYTES;
+  __shared__ __align__(8) uint64_t bars[2 * 8 + 2 * SP_NACC];
+  __shared__ uint32_t s_tmem;
+  __shared__ float s_bias[N];
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
+  const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[16 + SP_NACC]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int MMA_WARP = SP_GROUPS * SP_PT / 32;
+  constexpr uint32_t TMEM_COLS = (SP_NACC * N) < 32 ? 32u : (uint32_t)(SP_NACC * N);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < G::NSTAGE; ++s) { mbar_init(full0 + 8 * s, SP_PT); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < SP_NACC; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // rows the producers never write (plane padding of the stride-2 layout) must hold finite values: zero everything once
+  for (int i = threadIdx.x; i < G::NSTAGE * G::STAGE_BYTES / 16; i += SP_THREADS)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a_base + i * 16), "r"(0u) : "memory");
+  for (int i = threadIdx.x; i < 9 * B_TAP_BYTES / 16; i += SP_THREADS) {          // weights: dense [tap][n][c] -> swizzled
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.w) + i);
+    const uint32_t dst = b_base + sp_swz((uint32_t)i * 16u, G::SWMASK);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+  for (int i = threadIdx.x; i < N; i += SP_THREADS) s_bias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  auto decode_tile = [&](int t, int &n, int &h0, int &w0) {
+    const int tw = t % a.tiles_w; t /= a.tiles_w;
+    const int th = t % a.tiles_h; n = t / a.tiles_h;
+    h0 = th * SP_TH; w0 = tw * SP_TW;
+  };
+  auto sbo_desc = [](uint32_t saddr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)G::LAYOUT << 61;
+    return d;
+  };
+
+  if (warp < MMA_WARP) {
+    // =============================== producers ===============================
+    const int grp = threadIdx.x / SP_PT;
+    const int p = threadIdx.x - grp * SP_PT;
+    // chunk i = (hy*HW + hx)*CH + j of the halo: source offset (elements, relative to the halo origin) is tile
+    // dependent only through (hi0, wi0); destination offset inside a stage is fixed -> precomputed.
+    uint32_t doff[G::NLD];
+    int hyx[G::NLD];                                        // hy << 16 | hx << 8 | j, or -1
+#pragma unroll
+    for (int q = 0; q < G::NLD; ++q) {
+      const int i = p + q * SP_PT;
+      if (i < G::NCHUNK) {
+        const int j = i % G::CH, px = i / G::CH;
+        const int hx = px % G::HW, hy = px / G::HW;
+        int R;
+        if (S == 1) R = hy * G::PLANE_W + hx;
+        else R = ((hy & 1) * 2 + (hx & 1)) * G::PLANE_ROWS + (hy >> 1) * G::PLANE_W + (hx >> 1);
+        doff[q] = sp_swz((uint32_t)(R * G::PIX_B + j * 16), G::SWMASK);
+        hyx[q] = (hy << 16) | (hx << 8) | j;
+      } else {
+        doff[q] = 0; hyx[q] = -1;
+      }
+    }
+    uint4 pre[G::NLD];
+    auto fetch = [&](int t) {
+      int n, h0, w0; decode_tile(t, n, h0, w0);
+      const int hi0 = h0 * S - 1, wi0 = w0 * S - 1;
+      const __nv_bfloat16 *xin = a.x + (size_t)n * a.H * a.W * C;
+#pragma unroll
+      for (int q = 0; q < G::NLD; ++q) {
+        const int hy = hyx[q] >> 16, hx = (hyx[q] >> 8) & 255, j = hyx[q] & 255;
+        const int hi = hi0 + hy, wi = wi0 + hx;
+        const bool ok = hyx[q] >= 0 && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W;
+        pre[q] = ok ? __ldg(reinterpret_cast<const uint4 *>(xin + ((size_t)hi * a.W + wi) * C) + j) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+    const int tstep = gridDim.x * SP_GROUPS;
+    const int t_first = blockIdx.x + grp * gridDim.x;
+    int it = grp;
+    if (t_first < a.total_tiles) fetch(t_first);
+    for (int t = t_first; t < a.total_tiles; t += tstep, it += SP_GROUPS) {
+      const int stage = it % G::NSTAGE;
+      const uint32_t phase = (uint32_t)(it / G::NSTAGE) & 1u;
+      mbar_wait(empty0 + 8 * stage, phase ^ 1);
+      const uint32_t sa = a_base + stage * G::STAGE_BYTES;
+#pragma unroll
+      for (int q = 0; q < G::NLD; ++q)
+        if (hyx[q] >= 0)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + doff[q]), "r"(pre[q].x), "r"(pre[q].y), "r"(pre[q].z),
+                       "r"(pre[q].w) : "memory");
+      if (t + tstep < a.total_tiles) fetch(t + tstep);      // next tile's loads fly while the MMA warp consumes this one
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(full0 + 8 * stage);
+    }
+  } else if (warp == MMA_WARP) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t accphase = 0;
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
+      mbar_wait(full0 + 8 * stage, phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t d_tmem = tmem_base + acc * N;
+        const uint64_t ad0 = sbo_desc(a_base + stage * G::STAGE_BYTES, G::PLANE_W * G::PIX_B);
+        const uint64_t bd0 = sbo_desc(b_base, 8 * G::PIX_B);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int r = tap / 3, s = tap % 3;
+          const int row0 = (S == 1) ? (r * G::PLANE_W + s)
+                                    : (((r & 1) * 2 + (s & 1)) * G::PLANE_ROWS + (r >> 1) * G::PLANE_W + (s >> 1));
+#pragma unroll
+          for (int k = 0; k < C / 16; ++k)
+            umma_bf16(d_tmem, ad0 + (uint32_t)(row0 * (G::PIX_B >> 4) + 2 * k), bd0 + (uint32_t)(tap * (B_TAP_BYTES >> 4) + 2 * k),
+                      idesc, (tap > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty0 + 8 * stage);
+        umma_commit(tfull0 + 8 * acc);
+      }
+      __syncwarp();
+      if (++stage == G::NSTAGE) { stage = 0; phase ^= 1; }
+      if (++acc == SP_NACC) { acc = 0; accphase ^= 1; }
+    }
+  } else {
+    // =============================== epilogue (4 warps) ===============================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ty = m >> 3, tx = m & 7;
+    int acc = 0; uint32_t accphase = 0;
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      int n, h0, w0; decode_tile(t, n, h0, w0);
+      const int ho = h0 + ty, wo = w0 + tx;
+      const bool ok = ho < a.Ho && wo < a.Wo;
+      const size_t pix = ((size_t)n * a.Ho + ho) * a.Wo + wo;
+      __nv_bfloat16 *o = a.y + pix * N;
+      uint4 rr[N / 8];
+      if (a.res && ok) {
+#pragma unroll
+        for (int c = 0; c < N / 8; ++c) rr[c] = __ldg(reinterpret_cast<const uint4 *>(a.res + pix * N) + c);
+      }
+      mbar_wait(tfull0 + 8 * acc, accphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N;
+#pragma unroll
+      for (int c = 0; c < N / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c * 16, v);
+        tmem_ld_wait();
+        if (ok) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c * 16 + j];
+          if (a.res) {
+            const __nv_bfloat162 *rb0 = reinterpret_cast<const __nv_bfloat162 *>(&rr[2 * c]);
+            const __nv_bfloat162 *rb1 = reinterpret_cast<const __nv_bfloat162 *>(&rr[2 * c + 1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 x0 = __bfloat1622float2(rb0[j]), x1 = __bfloat1622float2(rb1[j]);
+              f[2 * j] += x0.x; f[2 * j + 1] += x0.y; f[8 + 2 * j] += x1.x; f[8 + 2 * j + 1] += x1.y;
+            }
+          }
+          uint4 o0, o1;
+          __nv_bfloat162 *ob0 = reinterpret_cast<__nv_bfloat162 *>(&o0), *ob1 = reinterpret_cast<__nv_bfloat162 *>(&o1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ob0[j] = __floats2bfloat162_rn(cpb::act_out<__nv_bfloat16>(f[2 * j], a.act), cpb::act_out<__nv_bfloat16>(f[2 * j + 1], a.act));
+            ob1[j] = __floats2bfloat162_rn(cpb::act_out<__nv_bfloat16>(f[8 + 2 * j], a.act), cpb::act_out<__nv_bfloat16>(f[8 + 2 * j + 1], a.act));
+          }
+          reinterpret_cast<uint4 *>(o + c * 16)[0] = o0;
+          reinterpret_cast<uint4 *>(o + c * 16)[1] = o1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (++acc == SP_NACC) { acc = 0; accphase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int C, int N, int S>
+int launch_sp(const cpb200_op &op, cudaStream_t st) {
+  using G = SpGeom<C, S>;
+  SpArgs a;
+  a.x = static_cast<const __nv_bfloat16 *>(op.src[0]); a.w = static_cast<const __nv_bfloat16 *>(op.weight);
+  a.res = static_cast<const __nv_bfloat16 *>(op.res); a.y = static_cast<__nv_bfloat16 *>(op.dst); a.bias = op.bias;
+  a.B = op.B; a.H = op.H; a.W = op.W; a.Ho = op.Ho; a.Wo = op.Wo;
+  a.tiles_h = (op.Ho + SP_TH - 1) / SP_TH; a.tiles_w = (op.Wo + SP_TW - 1) / SP_TW;
+  a.total_tiles = op.B * a.tiles_h * a.tiles_w;
+  a.act = op.flags & CPB_ACT_MASK;
+  const size_t smem = 1024 + (size_t)G::NSTAGE * G::STAGE_BYTES + 9 * (size_t)N * G::PIX_B;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CPB_CUDA(cudaFuncSetAttribute(conv_sp_kernel<C, N, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int sms = tc::num_sms();
+  const int grid = a.total_tiles < sms ? a.total_tiles : sms;
+  conv_sp_kernel<C, N, S><<<grid, SP_THREADS, smem, st>>>(a);
+  return cpb::check_launch("conv_sp_kernel");
+}
+
+template <int C, int S>
+int dispatch_n(const cpb200_op &op, cudaStream_t st) {
+  switch (op.cout) {
+    case 16: return launch_sp<C, 16, S>(op, st);
+    case 32: return launch_sp<C, 32, S>(op, st);
+    case 64: return launch_sp<C, 64, S>(op, st);
+  }
+  return cpb::fail(CPB200_ERR_ARG, "conv_sp: cout %d", op.cout);
+}
+
+}  // namespace
+
+namespace cpb {
+
+bool sp_eligible(const cpb200_op &op) {
+  static const bool enabled = []() { const char *e = getenv("CPB200_SP"); return !(e && e[0] == '0'); }();
+  return enabled && op.type == CPB200_OP_CONV && (op.flags & CPB200_FLAG_TC) && op.act_dtype == CPB200_BF16 && op.nsrc == 1 &&
+         (op.cin[0] == 16 || op.cin[0] == 32) && (op.cout == 16 || op.cout == 32 || op.cout == 64) && op.kh == 3 && op.kw == 3 &&
+         op.pad_h == 1 && op.pad_w == 1 && (op.stride == 1 || op.stride == 2) &&
+         op.Ho == (op.H + 2 - 3) / op.stride + 1 && op.Wo == (op.W + 2 - 3) / op.stride + 1 &&
+         op.out_sy == 1 && op.out_sx == 1 && !op.out_oy && !op.out_ox && op.Hd == op.Ho && op.Wd == op.Wo &&
+         !(op.flags & (CPB200_FLAG_OUT_NCHW_F32 | CPB200_FLAG_OUT_F32)) && op.Wo >= 8;
+}
+
+int sp_run(const cpb200_op &op, cudaStream_t st) {
+  if (!sp_eligible(op)) return fail(CPB200_ERR_ARG, "conv_sp: unsupported shape");
+  if (op.cin[0] == 16) return op.stride == 1 ? dispatch_n<16, 1>(op, st) : dispatch_n<16, 2>(op, st);
+  return op.stride == 1 ? dispatch_n<32, 1>(op, st) : dispatch_n<32, 2>(op, st);
+}
+
+}  // namespace cpb

@@ -56,6 +56,14 @@ TC_CASES = [
     ([512, 512, 256], 512, 1, 1, 8, 8, False, True, "act"),         # TW=8 tiles
     ([128], 27, 3, 1, 24, 24, False, False, "f32"),      # DCN offset/mask conv: fp32 out, cout 27
     ([64], 256, 3, 1, 32, 32, False, True, "act"),       # head 3x3
+    # small-channel 3x3 convs take the SIMT-fed kernel (csrc/net_tc_sp.cu): both strides, partial tiles, residual
+    ([16], 16, 3, 1, 21, 37, False, True, "act"),
+    ([16], 32, 3, 2, 37, 51, False, True, "act"),
+    ([16], 64, 3, 1, 16, 8, True, False, "act"),
+    ([32], 32, 3, 1, 40, 24, True, True, "act"),         # HRNet branch-0 block conv with residual
+    ([32], 64, 3, 2, 50, 30, False, True, "act"),
+    ([32], 32, 3, 2, 33, 17, False, False, "act"),
+    ([32], 16, 3, 1, 19, 23, False, True, "act"),
     ([256], 34, 1, 1, 32, 32, False, False, "nchw"),     # head 1x1 -> NCHW fp32 logits (hps)
     ([256], 1, 1, 1, 24, 40, False, False, "nchw"),      # head 1x1 (hm), partial tiles
     ([64], 17, 1, 1, 16, 16, False, True, "nchw"),
