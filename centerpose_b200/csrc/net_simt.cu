@@ -393,7 +393,9 @@ __global__ void maxpool_kernel(const T *__restrict__ x, T *__restrict__ y, int B
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) dwdeconv_add_kernel(const T *__restrict__ x, const T *__restrict__ skip, T *__restrict__ y,
                                                            const float *__restrict__ w, int H, int W, int C, int Ho, int Wo,
-                                                           int k, int f, int pad) {
+                                                           int k, int f, int pad, int lf, int lcv) {
+  // f and C / VEC are powers of two (lf = log2 f, lcv = log2(C / VEC), or -1 -> generic division):
+  // the per-element index arithmetic is shifts and masks only.
   extern __shared__ float sw[];                       // [k*k][C]
   for (int i = threadIdx.x; i < k * k * C; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -401,8 +403,9 @@ __global__ void __launch_bounds__(256) dwdeconv_add_kernel(const T *__restrict__
   const int b = blockIdx.x / Ho, ho = blockIdx.x % Ho;
   const int kh0 = (ho + pad) % f;
   const T *xb = x + (size_t)b * H * W * C;
+  const bool fast = lf >= 0 && lcv >= 0;
   for (int i = threadIdx.x; i < Wo * CV; i += blockDim.x) {
-    const int wo = i / CV, cv = i - wo * CV;
+    const int wo = fast ? (i >> lcv) : (i / CV), cv = i - wo * CV;
     const size_t opix = (((size_t)b * Ho + ho) * Wo + wo) * C + cv * VEC;
     float acc[VEC];
 #pragma unroll
@@ -410,14 +413,14 @@ __global__ void __launch_bounds__(256) dwdeconv_add_kernel(const T *__restrict__
       float4 s4 = skip ? Act<T>::ld4(skip + opix + q) : make_float4(0.f, 0.f, 0.f, 0.f);
       acc[q] = s4.x; acc[q + 1] = s4.y; acc[q + 2] = s4.z; acc[q + 3] = s4.w;
     }
-    const int kw0 = (wo + pad) % f;
+    const int kw0 = fast ? ((wo + pad) & (f - 1)) : ((wo + pad) % f);
     for (int khh = kh0; khh < k; khh += f) {
       const int hn = ho + pad - khh;
-      const int hi = hn / f;
+      const int hi = fast ? (hn >> lf) : (hn / f);
       if (hn < 0 || hi >= H) continue;
       for (int kww = kw0; kww < k; kww += f) {
         const int wn = wo + pad - kww;
-        const int wi = wn / f;
+        const int wi = fast ? (wn >> lf) : (wn / f);
         if (wn < 0 || wi >= W) continue;
         const T *xp = xb + ((size_t)hi * W + wi) * C + cv * VEC;
         const float *wp = sw + (khh * k + kww) * C + cv * VEC;
@@ -705,9 +708,10 @@ int run_op_simt(const cpb200_op &op, cudaStream_t st) {
       if (smem > 48 * 1024 &&
           cudaFuncSetAttribute(dwdeconv_add_kernel<T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return cpb::fail(CPB200_ERR_CUDA, "dwdeconv: cannot raise the shared-memory limit to %zu bytes", smem);
+      auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
       dwdeconv_add_kernel<T, VEC><<<(unsigned)(op.B * op.Ho), 256, smem, st>>>(static_cast<const T *>(op.src[0]),
           static_cast<const T *>(op.aux), static_cast<T *>(op.dst), static_cast<const float *>(op.weight),
-          op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h);
+          op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h, ilog2(op.stride), ilog2(op.cin[0] / VEC));
       return cpb::check_launch("dwdeconv_add_kernel");
     }
     case CPB200_OP_DWCONV: {
