@@ -33,8 +33,9 @@ K_DET = 100
 GFLOP_PER_IMG = 80.48            # SURVEY.md §8d (2*MAC of conv+deconv+DCN+heads, DLA-34 @512)
 ARCH_GFLOP = {"dla_34": 80.48, "res_50": 86.85, "hrnet": 85.27, "mobilenetv3": 15.59}
 ARCH_BATCH = {"dla_34": 32, "res_50": 16, "hrnet": 16, "mobilenetv3": 64}   # BASELINE.json configs[1..4] per GPU
-# dram__bytes_read+write summed over the 97 launches of one DLA-34 B=32 step (ncu, profiles/r01_traffic_per_kernel_v13.txt)
-NCU_TRAFFIC_BYTES = {("dla_34", 32): 9.534e9}
+# dram__bytes_read+write summed over the launches of one step (ncu, tools/traffic_list.sh;
+# profiles/r01_traffic_per_kernel_v20.txt, profiles/r01_traffic_res50_b16_v1.txt)
+NCU_TRAFFIC_BYTES = {("dla_34", 32): 9.359e9, ("res_50", 16): 4.659e9}
 DECODE_BYTES_PER_IMG = 1230848
 METRIC = "images/sec 512x512 DLA-34"
 
