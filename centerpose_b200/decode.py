@@ -112,3 +112,39 @@ def sigmoid_(x: torch.Tensor) -> torch.Tensor:
                                                torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(st, "sigmoid_")
     return x
+
+
+def flip_perm(flip_idx, J=17):
+    """[[1,2],[3,4],...] -> the joint permutation that swaps every listed pair."""
+    perm = list(range(J))
+    for a, b in flip_idx:
+        perm[a], perm[b] = perm[b], perm[a]
+    return perm
+
+
+def flip_merge(hm, wh, hps, hm_hp, flip_idx):
+    """Flip-test averaging (``multi_pose.py:45-53`` with ``flip_tensor`` / ``flip_lr`` / ``flip_lr_off``,
+    ``lib/models/utils.py:27-47``) in one CUDA pass.  Inputs are the fp32 NCHW head maps of ``2P`` images ordered
+    ``[image, mirrored image]`` per pair (sigmoid already applied where the reference applies it); returns
+    ``(hm, wh, hps, hm_hp)`` of ``P`` images.  ``hm_hp`` may be ``None``."""
+    import ctypes
+    tens = [hm, wh, hps] + ([hm_hp] if hm_hp is not None else [])
+    for t in tens:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.dim() == 4):
+            raise RuntimeError("flip_merge: contiguous CUDA fp32 NCHW tensors required")
+    B2, CH, H, W = hm.shape
+    if B2 % 2:
+        raise RuntimeError("flip_merge: batch must hold [image, mirrored image] pairs")
+    P, J = B2 // 2, hps.shape[1] // 2
+    if wh.shape != (B2, 2, H, W) or hps.shape != (B2, 2 * J, H, W) or (hm_hp is not None and hm_hp.shape != (B2, J, H, W)):
+        raise RuntimeError("flip_merge: inconsistent head-map shapes")
+    outs = [torch.empty((P,) + tuple(t.shape[1:]), dtype=torch.float32, device=hm.device) for t in tens]
+    perm = (ctypes.c_int * J)(*flip_perm(flip_idx, J))
+    with torch.cuda.device(hm.device):
+        st = _lib.lib().cpb200_flip_merge(hm.data_ptr(), wh.data_ptr(), hps.data_ptr(),
+                                          hm_hp.data_ptr() if hm_hp is not None else None,
+                                          outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
+                                          outs[3].data_ptr() if hm_hp is not None else None,
+                                          P, H, W, J, CH, perm, torch.cuda.current_stream(hm.device).cuda_stream)
+    _lib.check(st, "flip_merge")
+    return outs[0], outs[1], outs[2], (outs[3] if hm_hp is not None else None)

@@ -51,3 +51,19 @@ def soft_nms_39(boxes: np.ndarray, sigma: float = 0.5, Nt: float = 0.3, threshol
                         pos -= 1
             pos += 1
     return list(range(N))
+
+
+def soft_nms_39_cuda(boxes, sigma: float = 0.5, Nt: float = 0.3, threshold: float = 0.001, method: int = 0) -> int:
+    """Same routine on a DEVICE tensor (``cpb200_soft_nms_39``, csrc/post.cu): ``boxes`` is a contiguous CUDA
+    float32 ``(N, 56)`` tensor mutated in place exactly like the host version; returns the number of kept rows."""
+    import torch
+    from . import _lib
+    if not (boxes.is_cuda and boxes.dtype == torch.float32 and boxes.dim() == 2 and boxes.shape[1] == 56
+            and boxes.is_contiguous()):
+        raise ValueError("soft_nms_39_cuda expects a contiguous CUDA float32 (N, 56) tensor")
+    keep = torch.zeros(1, dtype=torch.int32, device=boxes.device)
+    with torch.cuda.device(boxes.device):
+        st = _lib.lib().cpb200_soft_nms_39(boxes.data_ptr(), boxes.shape[0], float(sigma), float(Nt), float(threshold),
+                                           int(method), keep.data_ptr(), torch.cuda.current_stream(boxes.device).cuda_stream)
+    _lib.check(st, "soft_nms_39")
+    return int(keep.item())

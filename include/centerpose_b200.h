@@ -85,6 +85,23 @@ int cpb200_multi_pose_decode_affine(const float *heat, const float *wh, const fl
 /* In-place logistic on n floats — lib/detectors/multi_pose.py:35-37 `hm.sigmoid_()`. */
 int cpb200_sigmoid_inplace(float *x, size_t n, void *stream);
 
+/* Flip-test averaging of the head maps in one pass — lib/detectors/multi_pose.py:45-53 with
+ * flip_tensor / flip_lr / flip_lr_off (lib/models/utils.py:27-47, which round-trip through numpy on the host).
+ * Inputs are the NCHW fp32 maps of 2P images ordered [image, mirrored image] per pair (base_detector.py:54-55);
+ * outputs hold P images: o = (a[2p] + flipped(a[2p+1])) / 2, where `flipped` reverses W, maps joint j to
+ * flip_perm[j] for hps / hm_hp and negates the x offsets (even hps channels).  hm_hp / o_hm_hp may be NULL.
+ * flip_perm is a HOST array of J ints (the permutation generated by flip_idx [[1,2],[3,4],...]). */
+int cpb200_flip_merge(const float *hm, const float *wh, const float *hps, const float *hm_hp, float *o_hm, float *o_wh,
+                      float *o_hps, float *o_hm_hp, int P, int H, int W, int J, int num_classes, const int *flip_perm,
+                      void *stream);
+
+/* soft_nms_39 (lib/external/nms.pyx:172-275) on a DEVICE (N,56) fp32 array, in place, same semantics as the
+ * reference's Cython routine (score decay: 0 hard / 1 linear / 2 gaussian; rows below `threshold` are removed by the
+ * swap-with-last walk; columns 0..38 travel with a row, 39..55 stay).  *keep_count (device int, may be NULL)
+ * receives the number of surviving rows.  One CTA; N*232 bytes of shared memory (N <= 882). */
+int cpb200_soft_nms_39(float *boxes, int N, float sigma, float Nt, float threshold, int method, int *keep_count,
+                       void *stream);
+
 
 /* ------------------------------------------------------------------------------------
  * Network forward.  Replaces `BackBoneWithHead.forward` (lib/models/model.py:57-59): the

@@ -14,6 +14,7 @@ from oracle import decode_ref
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 1e-5
+DEV = "cuda:0"
 
 
 def _cuda_decode(inp, K, use_reg=True, use_off=True, apply_sigmoid=False):
@@ -155,3 +156,53 @@ def test_decode_error_behaviour():
         multi_pose_decode(tb["heat"], tb["wh"], tb["kps"], tb["reg"], tb["hm_hp"], tb["hp_offset"], K=129)
     with pytest.raises(RuntimeError):      # CPU tensors are rejected (like _ext, dcn_v2.h:38)
         multi_pose_decode(*[torch.from_numpy(inp[k]) for k in ("heat", "wh", "kps")])
+
+
+def test_flip_merge_matches_reference_helpers():
+    """cpb200_flip_merge vs the reference's flip_tensor / flip_lr / flip_lr_off (golden, lib/models/utils.py:27-47)
+    and vs the averaging expression of multi_pose.py:45-53 — bit-exact (same fp32 operations)."""
+    from centerpose_b200.decode import flip_merge
+    g = np.load(os.path.join(GOLD, "flip.npz"))
+    idx = [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]]
+    hm_hp_f = torch.from_numpy(g["hm_hp"]); hps_f = torch.from_numpy(g["hps"])          # the "mirrored image" maps
+    H, W = hm_hp_f.shape[2:]
+    gen = torch.Generator().manual_seed(2)
+    hm_hp0 = torch.rand(1, 17, H, W, generator=gen); hps0 = torch.randn(1, 34, H, W, generator=gen)
+    hm = torch.rand(2, 1, H, W, generator=gen); wh = torch.rand(2, 2, H, W, generator=gen) * 30
+    o_hm, o_wh, o_hps, o_hp = flip_merge(hm.to(DEV), wh.to(DEV), torch.cat([hps0, hps_f]).to(DEV),
+                                         torch.cat([hm_hp0, hm_hp_f]).to(DEV), idx)
+    assert torch.equal(o_hm.cpu(), (hm[0:1] + torch.flip(hm[1:2], [3])) / 2)
+    assert torch.equal(o_wh.cpu(), (wh[0:1] + torch.flip(wh[1:2], [3])) / 2)
+    assert torch.equal(o_hps.cpu(), (hps0 + torch.from_numpy(g["flip_lr_off"])) / 2)
+    assert torch.equal(o_hp.cpu(), (hm_hp0 + torch.from_numpy(g["flip_lr"])) / 2)
+    # several pairs, no hm_hp
+    hm = torch.rand(6, 1, H, W, generator=gen); wh = torch.rand(6, 2, H, W, generator=gen); hps = torch.randn(6, 34, H, W, generator=gen)
+    o_hm, o_wh, o_hps, o_hp = flip_merge(hm.to(DEV), wh.to(DEV), hps.to(DEV), None, idx)
+    assert o_hp is None and o_hm.shape[0] == 3
+    assert torch.equal(o_hm.cpu(), (hm[0::2] + torch.flip(hm[1::2], [3])) / 2)
+
+
+def test_soft_nms_cuda_matches_compiled_reference_golden():
+    """cpb200_soft_nms_39 on a device array vs golden vectors from the reference's own Cython module
+    (oracle/build_ref.py): same keep counts and row movements; scores within 1 float ulp (see the host test)."""
+    from centerpose_b200.soft_nms import soft_nms_39, soft_nms_39_cuda
+    g = np.load(os.path.join(GOLD, "soft_nms.npz"))
+    for boxes, out, keep, prm in zip(g["boxes"], g["out"], g["keep"], g["params"]):
+        N, method, Nt, thr = int(prm[0]), int(prm[1]), float(prm[2]), float(prm[3])
+        dev = torch.from_numpy(boxes[:N].copy()).to(DEV)
+        k = soft_nms_39_cuda(dev, sigma=0.5, Nt=Nt, threshold=thr, method=method)
+        assert k == int(keep)
+        assert np.abs(dev.cpu().numpy() - out[:N]).max() <= 2e-7
+        host = boxes[:N].copy()
+        soft_nms_39(host, sigma=0.5, Nt=Nt, threshold=thr, method=method)
+        assert np.array_equal(dev.cpu().numpy(), host) or np.abs(dev.cpu().numpy() - host).max() <= 6e-8
+    # larger than one pass of the block (N > 128) and the empty case
+    rng = np.random.RandomState(5)
+    N = 300
+    c = rng.uniform(0, 400, size=(N, 2)); wh = rng.uniform(5, 120, size=(N, 2))
+    rows = np.zeros((N, 56), np.float32); rows[:, 0:2] = c - wh / 2; rows[:, 2:4] = c + wh / 2
+    rows[:, 4] = rng.uniform(0, 1, N); rows[:, 5:] = rng.uniform(0, 400, size=(N, 51))
+    host = rows.copy(); kh = len(soft_nms_39(host, Nt=0.5, method=2))
+    dev = torch.from_numpy(rows.copy()).to(DEV); kd = soft_nms_39_cuda(dev, Nt=0.5, method=2)
+    assert kd == kh and np.abs(dev.cpu().numpy() - host).max() <= 2e-7
+    assert soft_nms_39_cuda(torch.zeros(0, 56, device=DEV), Nt=0.5, method=2) == 0
