@@ -158,6 +158,71 @@ __device__ void scan_vec(Smem &s, const float *__restrict__ map, int H, int W, b
   if (lane == 0) s.wcnt[wid] = wcount;
 }
 
+// ---- phase 1, W == 128 specialisation (the 512x512 configs: one warp spans a full map row) ---------------
+// Same algorithm as scan_vec with everything the general path pays per row folded away at compile time: lane = column
+// group, warp = row strip, no out-of-range threads, the row's left / right neighbours always come from the shuffle
+// (lane 0 / 31 see -inf), row addresses advance by a constant, the logistic is a template switch.  The general path
+// executes ~150 instructions per row per thread (ncu, profiles/r01_ncu_decode_prof_v3.txt), this one ~60.
+template <bool SIG>
+__device__ void scan_w128(Smem &s, const float *__restrict__ map, int H, float floorv) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  constexpr int S = TPB / 32;                               // 8 strips
+  const int RS = H / S;                                     // rows per strip (H % 8 == 0 checked by the caller)
+  const int r0 = wid * RS;
+  const float NINF = -INFINITY;
+  float *segv = s.cval + wid * SEG;
+  int *segi = s.cidx + wid * SEG;
+  int wcount = 0;
+  const float4 *rowp = reinterpret_cast<const float4 *>(map) + (size_t)r0 * 32 + lane;
+
+  auto hmax = [&](const float4 &v, float4 &h) {
+    float l = __shfl_up_sync(FULL, v.w, 1), r = __shfl_down_sync(FULL, v.x, 1);
+    if (lane == 0) l = NINF;
+    if (lane == 31) r = NINF;
+    const float m01 = fmaxf(v.x, v.y), m23 = fmaxf(v.z, v.w);
+    h.x = fmaxf(l, m01); h.y = fmaxf(m01, v.z); h.z = fmaxf(v.y, m23); h.w = fmaxf(m23, r);
+  };
+  auto ld = [&](const float4 *p) {
+    float4 v = __ldg(p);
+    if (SIG) { v.x = act(v.x, true); v.y = act(v.y, true); v.z = act(v.z, true); v.w = act(v.w, true); }
+    return v;
+  };
+  const float4 ninf4 = make_float4(NINF, NINF, NINF, NINF);
+  float4 vcur, hprev, hcur;
+  if (r0 > 0) { const float4 t = ld(rowp - 32); hmax(t, hprev); } else hprev = ninf4;
+  vcur = ld(rowp); hmax(vcur, hcur);
+  int idx0 = r0 * 128 + lane * 4;                           // flat index of vcur.x
+#pragma unroll 4
+  for (int i = 0; i < RS; ++i) {
+    float4 vn, hn;
+    const bool has_next = (r0 + i + 1) < H;                 // warp-uniform
+    if (has_next) { vn = ld(rowp + (size_t)(i + 1) * 32); hmax(vn, hn); } else { vn = ninf4; hn = ninf4; }
+    const float mx = max3(hprev.x, hcur.x, hn.x), my = max3(hprev.y, hcur.y, hn.y);
+    const float mz = max3(hprev.z, hcur.z, hn.z), mw = max3(hprev.w, hcur.w, hn.w);
+    unsigned b = 0;
+    b |= (vcur.x >= mx && vcur.x > floorv) ? 1u : 0u;       // v <= max always: '>=' is the equality test
+    b |= (vcur.y >= my && vcur.y > floorv) ? 2u : 0u;
+    b |= (vcur.z >= mz && vcur.z > floorv) ? 4u : 0u;
+    b |= (vcur.w >= mw && vcur.w > floorv) ? 8u : 0u;
+    unsigned m = __ballot_sync(FULL, b != 0);
+    while (m) {                                             // 1 pass; a 2nd only if a float4 holds 2 peaks
+      if (b) {
+        const int k = __ffs(b) - 1;
+        b &= b - 1;
+        const float val = (k == 0) ? vcur.x : (k == 1) ? vcur.y : (k == 2) ? vcur.z : vcur.w;
+        const int pos = wcount + __popc(m & lt);
+        if (pos < SEG) { segv[pos] = val; segi[pos] = idx0 + k; }
+      }
+      wcount += __popc(m);
+      m = __ballot_sync(FULL, b != 0);
+    }
+    hprev = hcur; hcur = hn; vcur = vn;
+    idx0 += 128;
+  }
+  if (lane == 0) s.wcnt[wid] = wcount;
+}
+
 // Compact the per-warp segments [wid*SEG, wid*SEG + wcnt) into cval/cidx[0..n).  Returns n, or -1 when
 // a segment overflowed (caller takes the exact slow path).
 __device__ int compact_segments(Smem &s) {
@@ -530,7 +595,9 @@ __global__ void __launch_bounds__(TPB) decode_kernel(const DecodeParams p) {
   __syncthreads();
 
   const bool vec_ok = ((p.W & 3) == 0) && ((reinterpret_cast<uintptr_t>(map) & 15) == 0);
-  if (vec_ok) scan_vec(s, map, p.H, p.W, sig, floorv);
+  if (vec_ok && p.W == 128 && (p.H & 7) == 0) {
+    if (sig) scan_w128<true>(s, map, p.H, floorv); else scan_w128<false>(s, map, p.H, floorv);
+  } else if (vec_ok) scan_vec(s, map, p.H, p.W, sig, floorv);
   else scan_scalar(s, map, p.H, p.W, sig, floorv);
   const int ncand = compact_segments(s);
 
