@@ -179,3 +179,71 @@ extern "C" int cpb200_soft_nms_39(float *boxes, int N, float sigma, float Nt, fl
   soft_nms_kernel<<<1, NMS_T, smem, static_cast<cudaStream_t>(stream)>>>(boxes, N, sigma, Nt, threshold, method, keep_count);
   return cpb::check_launch("soft_nms_kernel");
 }
+
+// ---- device pre_process: warpAffine (bilinear, constant-0 border) + normalise + HWC->CHW (+ mirrored copy) ----
+// Replaces the cv2.warpAffine / numpy part of BaseDetector.pre_process (lib/detectors/base_detector.py:44-55).
+// Bit-exact with cv2.warpAffine(flags=INTER_LINEAR) on 8-bit images (OpenCV imgwarp.cpp, WarpAffineInvoker +
+// remapBilinear): the 2x3 matrix is inverted in double exactly as cv2 does, source coordinates are 10-bit fixed
+// point (AB_SCALE = 1024, round_delta = 16) reduced to 5 fractional bits, the four bilinear weights are the
+// integers (32-fx)(32-fy)*32 ... that sum to 2^15, result = (sum + 2^14) >> 15; then ((u/255 - mean)/std) is
+// evaluated in double and rounded to float like numpy does for `(inp / 255. - mean) / std`.astype(float32).
+namespace {
+
+struct PreArgs {
+  const unsigned char *img;   // (h, w, 3) uint8
+  float *out;                 // (1 or 2, 3, OH, OW) fp32
+  int h, w, OH, OW, flip;
+  double m[6];                // inverse map (dst -> src), as computed by cv2
+  float mean[3], stdv[3];
+};
+
+__global__ void __launch_bounds__(256) pre_process_kernel(const PreArgs a) {
+  const int total = a.OH * a.OW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int x = i % a.OW, y = i / a.OW;
+    const long long adelta = llrint(a.m[0] * (double)x * 1024.0), bdelta = llrint(a.m[3] * (double)x * 1024.0);
+    const long long X0 = llrint((a.m[1] * (double)y + a.m[2]) * 1024.0) + 16, Y0 = llrint((a.m[4] * (double)y + a.m[5]) * 1024.0) + 16;
+    const long long X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+    long long sxl = X >> 5, syl = Y >> 5;
+    sxl = sxl < -32768 ? -32768 : (sxl > 32767 ? 32767 : sxl);       // saturate_cast<short>
+    syl = syl < -32768 ? -32768 : (syl > 32767 ? 32767 : syl);
+    const int sx = (int)sxl, sy = (int)syl, fx = (int)(X & 31), fy = (int)(Y & 31);
+    const int w0 = (32 - fx) * (32 - fy) * 32, w1 = fx * (32 - fy) * 32, w2 = (32 - fx) * fy * 32, w3 = fx * fy * 32;
+    const bool y0 = sy >= 0 && sy < a.h, y1 = sy + 1 >= 0 && sy + 1 < a.h, x0 = sx >= 0 && sx < a.w, x1 = sx + 1 >= 0 && sx + 1 < a.w;
+    const unsigned char *p00 = a.img + ((size_t)sy * a.w + sx) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int v00 = (y0 && x0) ? p00[c] : 0, v01 = (y0 && x1) ? p00[3 + c] : 0;
+      const int v10 = (y1 && x0) ? p00[(size_t)a.w * 3 + c] : 0, v11 = (y1 && x1) ? p00[(size_t)a.w * 3 + 3 + c] : 0;
+      int u = (v00 * w0 + v01 * w1 + v10 * w2 + v11 * w3 + (1 << 14)) >> 15;
+      u = u < 0 ? 0 : (u > 255 ? 255 : u);
+      const float f = (float)(((double)u / 255.0 - (double)a.mean[c]) / (double)a.stdv[c]);
+      a.out[((size_t)c * a.OH + y) * a.OW + x] = f;
+      if (a.flip) a.out[((size_t)(3 + c) * a.OH + y) * a.OW + (a.OW - 1 - x)] = f;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int cpb200_pre_process(const unsigned char *img, int h, int w, const double *trans_input, float *out, int out_h, int out_w,
+                                  const float *mean, const float *stdv, int flip, void *stream) {
+  if (!img || !trans_input || !out || !mean || !stdv || h <= 0 || w <= 0 || out_h <= 0 || out_w <= 0)
+    return cpb::fail(CPB200_ERR_ARG, "pre_process: bad arguments");
+  PreArgs a;
+  a.img = img; a.out = out; a.h = h; a.w = w; a.OH = out_h; a.OW = out_w; a.flip = flip ? 1 : 0;
+  // cv2::warpAffine without WARP_INVERSE_MAP inverts the matrix like this (imgwarp.cpp)
+  double M[6];
+  for (int i = 0; i < 6; ++i) M[i] = trans_input[i];
+  double D = M[0] * M[4] - M[1] * M[3];
+  D = D != 0 ? 1. / D : 0;
+  const double A11 = M[4] * D, A22 = M[0] * D;
+  M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
+  const double b1 = -M[0] * M[2] - M[1] * M[5], b2 = -M[3] * M[2] - M[4] * M[5];
+  M[2] = b1; M[5] = b2;
+  for (int i = 0; i < 6; ++i) a.m[i] = M[i];
+  for (int c = 0; c < 3; ++c) { a.mean[c] = mean[c]; a.stdv[c] = stdv[c]; }
+  const int total = out_h * out_w;
+  pre_process_kernel<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return cpb::check_launch("pre_process_kernel");
+}

@@ -44,6 +44,9 @@ class BaseDetector(object):
         self.scales = cfg.TEST.TEST_SCALES
         self.cfg = cfg
         self.pause = True
+        b200 = cfg.get("B200", None) if hasattr(cfg, "get") else getattr(cfg, "B200", None)
+        # additive: cfg.B200.DEVICE_PREPROCESS (default on) — warp / normalise / transpose on the GPU (same values)
+        self.device_preprocess = bool((b200 or {}).get("DEVICE_PREPROCESS", True)) if isinstance(b200, dict) else True
 
     def pre_process(self, image, scale, meta=None):
         """base_detector.py:32-62 — resize, centre-crop affine warp to the network input, normalise,
@@ -60,6 +63,13 @@ class BaseDetector(object):
             c = np.array([new_width // 2, new_height // 2], dtype=np.float32)
             s = np.array([inp_width, inp_height], dtype=np.float32)
         trans_input = get_affine_transform(c, s, 0, [inp_width, inp_height])
+        meta = {"c": c, "s": s, "out_height": inp_height // self.cfg.MODEL.DOWN_RATIO,
+                "out_width": inp_width // self.cfg.MODEL.DOWN_RATIO}
+        if self.device_preprocess and image.dtype == np.uint8 and image.ndim == 3 and image.shape[2] == 3:
+            # warp + normalise + HWC->CHW (+ mirrored copy) in one CUDA kernel, bit-exact with the cv2 / numpy lines
+            # below (csrc/post.cu); a scale != 1 keeps cv2.resize on the host, as in the reference
+            resized = image if (new_width, new_height) == (width, height) else cv2.resize(image, (new_width, new_height))
+            return self._pre_process_device(resized, trans_input, inp_height, inp_width), meta
         resized = cv2.resize(image, (new_width, new_height))
         inp = cv2.warpAffine(resized, trans_input, (inp_width, inp_height), flags=cv2.INTER_LINEAR)
         inp = ((inp / 255. - self.mean) / self.std).astype(np.float32)
@@ -67,9 +77,24 @@ class BaseDetector(object):
         if self.cfg.TEST.FLIP_TEST:
             images = np.concatenate((images, images[:, :, :, ::-1]), axis=0)
         images = torch.from_numpy(np.ascontiguousarray(images))
-        meta = {"c": c, "s": s, "out_height": inp_height // self.cfg.MODEL.DOWN_RATIO,
-                "out_width": inp_width // self.cfg.MODEL.DOWN_RATIO}
         return images, meta
+
+    def _pre_process_device(self, image_u8, trans_input, inp_height, inp_width):
+        import ctypes
+        from . import _lib
+        dev = torch.device("cuda")
+        src = torch.from_numpy(np.ascontiguousarray(image_u8)).to(dev, non_blocking=True)
+        flip = bool(self.cfg.TEST.FLIP_TEST)
+        out = torch.empty((2 if flip else 1, 3, inp_height, inp_width), dtype=torch.float32, device=dev)
+        M = (ctypes.c_double * 6)(*np.asarray(trans_input, np.float64).reshape(-1))
+        mean = (ctypes.c_float * 3)(*np.asarray(self.mean, np.float32).reshape(-1))
+        std = (ctypes.c_float * 3)(*np.asarray(self.std, np.float32).reshape(-1))
+        with torch.cuda.device(dev):
+            st = _lib.lib().cpb200_pre_process(src.data_ptr(), image_u8.shape[0], image_u8.shape[1], M, out.data_ptr(),
+                                               inp_height, inp_width, mean, std, 1 if flip else 0,
+                                               torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(st, "pre_process")
+        return out
 
     def process(self, images, return_time=False):
         raise NotImplementedError

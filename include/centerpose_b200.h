@@ -95,6 +95,14 @@ int cpb200_flip_merge(const float *hm, const float *wh, const float *hps, const 
                       float *o_hps, float *o_hm_hp, int P, int H, int W, int J, int num_classes, const int *flip_perm,
                       void *stream);
 
+/* Device part of BaseDetector.pre_process (lib/detectors/base_detector.py:44-55): cv2.warpAffine(INTER_LINEAR,
+ * constant-0 border) of an 8-bit HWC image with the 2x3 `trans_input` matrix (HOST array of 6 doubles, as returned
+ * by get_affine_transform), then ((u/255 - mean)/std) in double -> fp32, HWC -> CHW into out[0]; with flip != 0 the
+ * horizontally mirrored copy is written to out[1] (base_detector.py:54-55).  Bit-exact with OpenCV's fixed-point
+ * path (verified against cv2 4.13).  img and out are device pointers; mean / stdv are HOST arrays of 3 floats. */
+int cpb200_pre_process(const unsigned char *img, int h, int w, const double *trans_input, float *out, int out_h, int out_w,
+                       const float *mean, const float *stdv, int flip, void *stream);
+
 /* soft_nms_39 (lib/external/nms.pyx:172-275) on a DEVICE (N,56) fp32 array, in place, same semantics as the
  * reference's Cython routine (score decay: 0 hard / 1 linear / 2 gaussian; rows below `threshold` are removed by the
  * swap-with-last walk; columns 0..38 travel with a row, 39..55 stay).  *keep_count (device int, may be NULL)

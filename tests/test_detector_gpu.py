@@ -36,7 +36,7 @@ def test_flip_helpers_match_reference_golden():
 def _oracle_run(det, sd, cfg, image, flip):
     from oracle import decode_ref, dla_ref, post_process_ref
     images, meta = det.pre_process(image, 1.0)
-    hm, wh, hps, reg, hm_hp, hp_off = dla_ref.forward(sd, images)
+    hm, wh, hps, reg, hm_hp, hp_off = dla_ref.forward(sd, images.cpu())     # pre_process may run on the device
     hm = hm.sigmoid(); hm_hp = hm_hp.sigmoid()
     if flip:
         idx = list(range(17))
@@ -87,3 +87,41 @@ def test_merge_outputs_soft_nms_path():
     d[1][:, 2:4] = d[1][:, 0:2] + 30
     out = det.merge_outputs([d])
     assert len(out) == 100 and len(out[0]) == 56
+
+
+@pytest.mark.parametrize("h,w,fix_res,flip", [(480, 640, True, False), (427, 640, False, True), (333, 500, True, True),
+                                              (96, 1280, False, False), (720, 405, True, False)])
+def test_device_pre_process_is_bit_exact_with_cv2_path(h, w, fix_res, flip):
+    """cpb200_pre_process (warpAffine + normalise + HWC->CHW + mirrored copy in one kernel) vs the reference's
+    cv2.warpAffine / numpy lines (base_detector.py:44-55), which the host branch of pre_process mirrors verbatim."""
+    from centerpose_b200.config import default_cfg
+    from centerpose_b200.detector import MultiPoseDetector
+    cfg = default_cfg("dla_34")
+    cfg.TEST.FIX_RES = fix_res; cfg.TEST.FLIP_TEST = flip
+    det = _shared_detector(cfg)
+    rng = np.random.RandomState(h * 7 + w)
+    img = rng.randint(0, 256, size=(h, w, 3), dtype=np.uint8)
+    det.device_preprocess = False
+    ref, meta_ref = det.pre_process(img, 1.0)
+    det.device_preprocess = True
+    got, meta = det.pre_process(img, 1.0)
+    assert got.is_cuda and got.shape == ref.shape and meta["out_height"] == meta_ref["out_height"]
+    assert torch.equal(got.cpu(), ref)
+    # a scale != 1 keeps cv2.resize on the host and still warps on the device
+    det.device_preprocess = False
+    ref2, _ = det.pre_process(img, 0.75)
+    det.device_preprocess = True
+    got2, _ = det.pre_process(img, 0.75)
+    assert torch.equal(got2.cpu(), ref2)
+
+
+_DET = {}
+
+
+def _shared_detector(cfg):
+    """One model for all parametrisations (the pre_process path does not depend on the weights)."""
+    from centerpose_b200.detector import MultiPoseDetector
+    if "d" not in _DET:
+        _DET["d"] = MultiPoseDetector(cfg)
+    _DET["d"].cfg = cfg
+    return _DET["d"]

@@ -185,3 +185,33 @@ def test_soft_nms_matches_compiled_reference_golden():
         k = soft_nms_39(rows, sigma=0.5, Nt=Nt, threshold=thr, method=method)
         assert len(k) == int(keep)
         assert np.abs(rows - out[:N]).max() <= 2e-7
+
+
+def test_convert_eval_format_matches_reference_statement():
+    """coco_format.convert_eval_format vs a literal restatement of lib/datasets/coco_hp.py:56-83 (the reference method
+    lives on a dataset class that needs pycocotools + annotation files)."""
+    from centerpose_b200.coco_format import convert_eval_format
+
+    def ref(all_bboxes):                                   # coco_hp.py:56-83, verbatim semantics
+        to_float = lambda x: float("{:.2f}".format(x))
+        detections = []
+        for image_id in all_bboxes:
+            for dets in all_bboxes[image_id][1]:
+                bbox = dets[:4]
+                bbox[2] -= bbox[0]; bbox[3] -= bbox[1]
+                score = dets[4]
+                prob = np.array(np.array(dets[39:56]) > 0.1).astype(np.int32).reshape(17, 1)
+                kps = np.array(dets[5:39], dtype=np.float32).reshape(-1, 2)
+                pred = list(map(to_float, np.concatenate([kps, prob], axis=1).reshape(51).tolist()))
+                detections.append({"image_id": int(image_id), "category_id": 1, "bbox": list(map(to_float, bbox)),
+                                   "score": float("{:.2f}".format(score)), "keypoints": pred})
+        return detections
+
+    rng = np.random.RandomState(4)
+    res = {}
+    for img in (17, 42):
+        rows = rng.uniform(0, 640, size=(5, 56)); rows[:, 2:4] += rows[:, 0:2]; rows[:, 4] = rng.uniform(0, 1, 5)
+        rows[:, 39:] = rng.uniform(0, 0.3, size=(5, 17))
+        res[img] = {1: rows.astype(np.float32).tolist()}
+    import copy
+    assert convert_eval_format(copy.deepcopy(res)) == ref(copy.deepcopy(res))
