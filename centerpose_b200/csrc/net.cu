@@ -23,6 +23,9 @@ static int validate(const cpb200_op &op, int i) {
     return cpb::fail(CPB200_ERR_ARG, "op %d: bad act_dtype", i);
   if ((op.type == CPB200_OP_CONV || op.type == CPB200_OP_DCN || op.type == CPB200_OP_STEM) && !op.weight)
     return cpb::fail(CPB200_ERR_ARG, "op %d: null weight", i);
+  for (int s = 0; s < op.nsrc; ++s)
+    if (op.src_pitch[s] != 0 && (op.src_pitch[s] < op.cin[s] || (op.type != CPB200_OP_CONV && op.src_pitch[s] != op.cin[s])))
+      return cpb::fail(CPB200_ERR_ARG, "op %d: channel-slice inputs (src_pitch) are supported by CONV ops only", i);
   if (op.out_sy < 1 || op.out_sx < 1 || op.Hd < 1 || op.Wd < 1)
     return cpb::fail(CPB200_ERR_ARG, "op %d: bad output mapping", i);
   return CPB200_OK;

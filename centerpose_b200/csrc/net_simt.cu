@@ -46,6 +46,7 @@ template <> struct Act<bf16> {
 struct ConvArgs {
   const void *src[4];
   int cin[4];
+  int pitch[4];              // elements between pixels of each input (== cin unless the input is a channel slice)
   int nsrc;
   const void *res;
   const float *aux;       // DCN: (B,H,W,aux_pitch) fp32 offsets+mask logits
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
     int cbase = 0;
     for (int s = 0; s < a.nsrc; ++s) {
       const T *src = static_cast<const T *>(a.src[s]);
-      const int cs = a.cin[s];
+      const int cs = a.cin[s], ps = a.pitch[s];
       for (int c0 = 0; c0 < cs; c0 += BK) {
         // ---- A tile: BM pixels x 16 channels ----
         float4 av[A_ROUNDS];
@@ -149,14 +150,14 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
           if (!DCN) {
             const int hi = pho[r] * a.stride - a.pad_h + r_, wi = pwo[r] * a.stride - a.pad_w + q_;
             if (pok[r] && hi >= 0 && hi < a.H && wi >= 0 && wi < a.W)
-              av[r] = Act<T>::ld4(src + (((size_t)pb[r] * a.H + hi) * a.W + wi) * cs + c0 + kq * 4);
+              av[r] = Act<T>::ld4(src + (((size_t)pb[r] * a.H + hi) * a.W + wi) * ps + c0 + kq * 4);
           } else {
             const int i = (tid >> 2) + 64 * r;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               const float wgt = s_cwt[c][i];
               if (wgt != 0.f) {
-                const float4 v = Act<T>::ld4(src + (size_t)s_coff[c][i] * cs + c0 + kq * 4);
+                const float4 v = Act<T>::ld4(src + (size_t)s_coff[c][i] * ps + c0 + kq * 4);
                 av[r].x += wgt * v.x; av[r].y += wgt * v.y; av[r].z += wgt * v.z; av[r].w += wgt * v.w;
               }
             }
@@ -622,6 +623,7 @@ int launch_conv(const cpb200_op &op, cudaStream_t st) {
   a.cin_total = 0;
   for (int i = 0; i < 4; ++i) {
     a.src[i] = op.src[i]; a.cin[i] = (i < op.nsrc) ? op.cin[i] : 0;
+    a.pitch[i] = (i < op.nsrc && op.src_pitch[i] > 0) ? op.src_pitch[i] : a.cin[i];
     if (i < op.nsrc) {
       if (op.cin[i] % BK) return cpb::fail(CPB200_ERR_ARG, "conv: input channels %d not a multiple of %d", op.cin[i], BK);
       a.cin_total += op.cin[i];

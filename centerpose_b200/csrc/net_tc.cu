@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
                 mbar_expect_tx(full0 + 8 * stage, a_bytes + b_bytes);
                 tma_load_4d(sa, &a.amap[s], full0 + 8 * stage, c0, wi, hi, n);
               }
-              tma_load_3d(sb, &a.bmap, full0 + 8 * stage, cb + c0, nt * BN, tap);
+              tma_load_3d(sb, &a.bmap, full0 + 8 * stage, 0, nt * BN, tap * kblocks_per_tap + (cb + c0) / a.BK);
               if (++stage == a.stages) { stage = 0; phase ^= 1; }
             }
             cb += a.cin[s];
@@ -485,8 +485,10 @@ int tc_prepare_op(cpb200_op &op) {
   t->grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
 
   for (int s = 0; s < op.nsrc && !dcn; ++s) {
+    // a channel slice of a wider tensor: `pitch` elements between pixels, op.src[s] already points at the slice
+    const cuuint64_t pitch = op.src_pitch[s] > 0 ? (cuuint64_t)op.src_pitch[s] : (cuuint64_t)op.cin[s];
     const cuuint64_t dims[4] = {(cuuint64_t)op.cin[s], (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.B};
-    const cuuint64_t strides[3] = {(cuuint64_t)op.cin[s] * 2, (cuuint64_t)op.W * op.cin[s] * 2, (cuuint64_t)op.H * op.W * op.cin[s] * 2};
+    const cuuint64_t strides[3] = {pitch * 2, (cuuint64_t)op.W * pitch * 2, (cuuint64_t)op.H * op.W * pitch * 2};
     const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(a.TW * op.stride), (cuuint32_t)(a.TH * op.stride), 1};
     const cuuint32_t estr[4] = {1, (cuuint32_t)op.stride, (cuuint32_t)op.stride, 1};
     CUresult r = enc(&a.amap[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(op.src[s]), dims, strides, box, estr,
@@ -494,9 +496,10 @@ int tc_prepare_op(cpb200_op &op) {
     if (r != CUDA_SUCCESS) { delete t; return fail(CPB200_ERR_CUDA, "tc: cuTensorMapEncodeTiled(A[%d]) failed: %d", s, (int)r); }
   }
   {
+    // weights are packed slab-major [tap][K-slab][cout_pad][bk] (plan.py::_pack_conv_tc): a box is one dense run
     const int cout_pad = (op.cout + 15) / 16 * 16;
-    const cuuint64_t dims[3] = {(cuuint64_t)cin_total, (cuuint64_t)cout_pad, (cuuint64_t)(op.kh * op.kw)};
-    const cuuint64_t strides[2] = {(cuuint64_t)cin_total * 2, (cuuint64_t)cout_pad * cin_total * 2};
+    const cuuint64_t dims[3] = {(cuuint64_t)bk, (cuuint64_t)cout_pad, (cuuint64_t)(op.kh * op.kw) * (cuuint64_t)(cin_total / bk)};
+    const cuuint64_t strides[2] = {(cuuint64_t)bk * 2, (cuuint64_t)cout_pad * bk * 2};
     const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)BN, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&a.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(op.weight), dims, strides, box, estr,

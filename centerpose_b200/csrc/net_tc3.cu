@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
         mbar_expect_tx(ball, (uint32_t)a.taps * a.slabs * a.b_tx_bytes);
         for (int sl = 0; sl < a.slabs; ++sl)
           for (int tap = 0; tap < a.taps; ++tap)
-            tma_load_3d(b_base + (sl * a.taps + tap) * a.b_stage_bytes, &a.bmap, ball, sl * a.BK, 0, tap);
+            tma_load_3d(b_base + (sl * a.taps + tap) * a.b_stage_bytes, &a.bmap, ball, 0, 0, tap * a.slabs + sl);
       } else {
         int sb = 0; uint32_t phb = 0;
         for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
             for (int tap = 0; tap < a.taps; ++tap) {
               mbar_wait(bempty0 + 8 * sb, phb ^ 1);
               mbar_expect_tx(bfull0 + 8 * sb, a.b_tx_bytes);
-              tma_load_3d(b_base + sb * a.b_stage_bytes, &a.bmap, bfull0 + 8 * sb, sl * a.BK, nt * BN, tap);
+              tma_load_3d(b_base + sb * a.b_stage_bytes, &a.bmap, bfull0 + 8 * sb, 0, nt * BN, tap * a.slabs + sl);
               if (++sb == a.nb) { sb = 0; phb ^= 1; }
             }
         }
@@ -321,7 +321,8 @@ namespace cpb {
 bool c3_eligible(const cpb200_op &op) {
   const bool geom = (op.kh == 3 && op.kw == 3) || (op.kh == 7 && op.kw == 1) || (op.kh == 1 && op.kw == 7) || (op.kh == 5 && op.kw == 5);
   return op.type == CPB200_OP_CONV && geom && op.stride == 1 && op.pad_h == op.kh / 2 && op.pad_w == op.kw / 2 &&
-         op.nsrc == 1 && op.cin[0] % 16 == 0 && op.Wo >= 8 && op.Ho >= 8 && op.H == op.Ho && op.W == op.Wo &&
+         op.nsrc == 1 && op.cin[0] % 16 == 0 && (op.src_pitch[0] == 0 || op.src_pitch[0] == op.cin[0]) && op.Wo >= 8 && op.Ho >= 8 &&
+         op.H == op.Ho && op.W == op.Wo &&
          op.out_sy == 1 && op.out_sx == 1 && !op.out_oy && !op.out_ox && op.Hd == op.Ho && op.Wd == op.Wo &&
          !(op.flags & CPB200_FLAG_OUT_NCHW_F32) && op.act_dtype == CPB200_BF16 &&
          ((op.flags & CPB200_FLAG_OUT_F32) || op.cout % 16 == 0);
@@ -344,6 +345,7 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   a.tiles_h = (op.Ho + TH - 1) / TH; a.tiles_w = (op.Wo + TW - 1) / TW;
   int BN = 16;
   while (BN < op.cout && BN < 256) BN <<= 1;
+  if (const char *e = getenv("CPB200_C3_BN")) { int v = atoi(e); if (v >= BN && v <= 256 && (v & (v - 1)) == 0) BN = v; }   // experiments
   t->BN = BN;
   a.n_tiles = (op.cout + BN - 1) / BN;
   a.cout = op.cout; a.cout_store = op.cout;
@@ -385,9 +387,10 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
     if (r != CUDA_SUCCESS) { delete t; *rc = fail(CPB200_ERR_CUDA, "tc3: cuTensorMapEncodeTiled(A) failed: %d", (int)r); return nullptr; }
   }
   {
+    // weights are packed slab-major [tap][K-slab][cout_pad][bk] (plan.py::_pack_conv_tc): a box is one dense run
     const int cout_pad = (op.cout + 15) / 16 * 16;
-    const cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout_pad, (cuuint64_t)a.taps};
-    const cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout_pad * cin * 2};
+    const cuuint64_t dims[3] = {(cuuint64_t)bk, (cuuint64_t)cout_pad, (cuuint64_t)a.taps * (cuuint64_t)a.slabs};
+    const cuuint64_t strides[2] = {(cuuint64_t)bk * 2, (cuuint64_t)cout_pad * bk * 2};
     const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)BN, 1};
     const cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(&a.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(op.weight), dims, strides, box, es,

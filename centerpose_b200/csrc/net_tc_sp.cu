@@ -307,6 +307,7 @@ namespace cpb {
 bool sp_eligible(const cpb200_op &op) {
   static const bool enabled = []() { const char *e = getenv("CPB200_SP"); return !(e && e[0] == '0'); }();
   return enabled && op.type == CPB200_OP_CONV && (op.flags & CPB200_FLAG_TC) && op.act_dtype == CPB200_BF16 && op.nsrc == 1 &&
+         (op.src_pitch[0] == 0 || op.src_pitch[0] == op.cin[0]) &&
          (op.cin[0] == 16 || op.cin[0] == 32) && (op.cout == 16 || op.cout == 32 || op.cout == 64) && op.kh == 3 && op.kw == 3 &&
          op.pad_h == 1 && op.pad_w == 1 && (op.stride == 1 || op.stride == 2) &&
          op.Ho == (op.H + 2 - 3) / op.stride + 1 && op.Wo == (op.W + 2 - 3) / op.stride + 1 &&

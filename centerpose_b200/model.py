@@ -9,6 +9,8 @@ product has no CPU path and raises if the CUDA library is missing.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -118,12 +120,29 @@ class BackBoneWithHead(nn.Module):
             x = pb.input(3)
             feat = self._arch_mod.lower(pb, StateView(sd, "backbone_model.", device), x)
             P = StateView(sd, "head_model.", device)
-            for name, c in HEADS:
-                dst = pb.output(c, feat.H, feat.W, name)
+
+            def w0_of(name):
                 w0 = P(f"{name}.0.weight").float()
                 if feat.C > w0.shape[1]:                 # backbone carries zero-padded channels (archs/mobilenet.py)
                     w0 = torch.nn.functional.pad(w0, (0, 0, 0, 0, 0, feat.C - w0.shape[1]))
-                t = pb.conv([feat], w0, P(f"{name}.0.bias").float(), stride=1, pad=1, relu=True)
+                return w0
+
+            hc = self.head_conv
+            fuse = pb.use_tc and hc % 16 == 0 and hc <= 128 and os.environ.get("CPB200_FUSE_HEADS", "1") != "0"
+            if fuse:
+                # Narrow heads (ResNet-50 / HRNet: head_conv 64): ONE 3x3 conv produces all six hidden maps.  A
+                # tcgen05.mma costs the issuing thread the same ~90 cycles whether N is 64 or 256 (measured: the
+                # 256->64 head conv takes 190 us at N = 64, 194 at 128, 204 at 256), so six N=64 convs are issue-bound
+                # at 6x the instruction count of one N=384 conv; the feature map is also read once instead of six times.
+                w_cat = torch.cat([w0_of(name) for name, _ in HEADS], dim=0)
+                b_cat = torch.cat([P(f"{name}.0.bias").float() for name, _ in HEADS], dim=0)
+                hid = pb.conv([feat], w_cat, b_cat, stride=1, pad=1, relu=True)
+            for i, (name, c) in enumerate(HEADS):
+                dst = pb.output(c, feat.H, feat.W, name)
+                if fuse:
+                    t = pb.channel_slice(hid, i * hc, hc)
+                else:
+                    t = pb.conv([feat], w0_of(name), P(f"{name}.0.bias").float(), stride=1, pad=1, relu=True)
                 pb.conv([t], P(f"{name}.2.weight").float(), P(f"{name}.2.bias").float(),
                         stride=1, pad=0, relu=False, out="nchw", dst=dst)
             plan = pb.build()

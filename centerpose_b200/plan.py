@@ -47,20 +47,46 @@ class OpStruct(ctypes.Structure):
         ("aux_pitch", ctypes.c_int32),
         ("src", ctypes.c_void_p * 4), ("res", ctypes.c_void_p), ("aux", ctypes.c_void_p),
         ("dst", ctypes.c_void_p), ("weight", ctypes.c_void_p), ("bias", ctypes.c_void_p),
-        ("tc", ctypes.c_void_p), ("reserved1", ctypes.c_uint64 * 2),
+        ("tc", ctypes.c_void_p), ("src_pitch", ctypes.c_int32 * 4),
     ]
 
 
 class Sym:
     """Symbolic activation tensor (NHWC unless kind says otherwise)."""
-    __slots__ = ("C", "H", "W", "kind", "name", "buf", "producer", "last_use", "fixed")
+    __slots__ = ("C", "H", "W", "kind", "name", "_buf", "producer", "_last_use", "fixed", "parent", "ch_off")
 
-    def __init__(self, C, H, W, kind="act", name=""):
+    def __init__(self, C, H, W, kind="act", name="", parent=None, ch_off=0):
         self.C, self.H, self.W, self.kind, self.name = C, H, W, kind, name
-        self.buf = None          # torch tensor once allocated
+        self._buf = None         # torch tensor once allocated
         self.producer = -1
-        self.last_use = -1
+        self._last_use = -1
         self.fixed = False       # externally provided storage (network input / outputs)
+        self.parent = parent     # channel slice [ch_off, ch_off + C) of `parent` (shares its storage)
+        self.ch_off = ch_off
+
+    # a slice lives in its parent's buffer and keeps the parent alive
+    @property
+    def buf(self):
+        return self.parent.buf if self.parent is not None else self._buf
+
+    @buf.setter
+    def buf(self, v):
+        self._buf = v
+
+    @property
+    def last_use(self):
+        return self.parent.last_use if self.parent is not None else self._last_use
+
+    @last_use.setter
+    def last_use(self, v):
+        if self.parent is not None:
+            self.parent.last_use = v
+        else:
+            self._last_use = v
+
+    @property
+    def pitch(self):
+        return self.parent.C if self.parent is not None else self.C
 
 
 class _PendingOp:
@@ -144,13 +170,34 @@ class PlanBuilder:
         p[:, :, :co] = w.permute(2, 3, 1, 0).reshape(kh * kw, ci, co)
         return self._dev(p)
 
-    def _pack_conv_tc(self, w: torch.Tensor):
-        """(Co,Ci,kh,kw) fp32 -> tcgen05 layout [kh*kw][Co_pad16][Ci] bf16 (K-major B operand)."""
+    def _pack_conv_tc(self, w: torch.Tensor, bk: int):
+        """(Co,Ci,kh,kw) fp32 -> tcgen05 layout [kh*kw][Ci/bk][Co_pad16][bk] bf16 (K-major B operand, slab-major:
+        the rows of one (tap, K-slab) block are contiguous, so a TMA weight box is one dense run of memory instead of
+        Co rows strided by Ci).  bk = the kernels' K-slab width.  (No measurable speed difference against the
+        strided [tap][Co][Ci] layout on B200 — kept because it lets one box span several slabs.)"""
         co, ci, kh, kw = w.shape
+        assert ci % bk == 0
         cop = (co + 15) // 16 * 16
-        p = torch.zeros(kh * kw, cop, ci, dtype=torch.float32, device=w.device)
-        p[:, :co, :] = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
+        p = torch.zeros(kh * kw, ci // bk, cop, bk, dtype=torch.float32, device=w.device)
+        p[:, :, :co, :] = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci // bk, bk).permute(0, 2, 1, 3)
         return self._dev(p, torch.bfloat16)
+
+    @staticmethod
+    def _tc_bk(srcs) -> int:
+        """K-slab width the tensor-core kernels use for these inputs (csrc/net_tc.cu, net_tc3.cu: 64 / 32 / 16)."""
+        bk = 64
+        for s in srcs:
+            if s.C % 64:
+                bk = min(bk, 32 if s.C % 32 == 0 else 16)
+        return bk
+
+    def channel_slice(self, x: Sym, off: int, c: int) -> Sym:
+        """View of channels [off, off+c) of an NHWC activation (no copy): readable by conv ops through the op's
+        ``src_pitch`` field.  Used to feed the six head 1x1 convs from ONE fused hidden tensor."""
+        assert x.parent is None and x.kind == "act" and 0 <= off and off + c <= x.C and off % 16 == 0 and c % 16 == 0
+        v = Sym(c, x.H, x.W, "act", parent=x, ch_off=off)
+        v.producer = x.producer
+        return v
 
     def _pack_stem_tc(self, w: torch.Tensor):
         """(N,3,7,7) fp32 -> the 128-byte-swizzled K-major B operand image of csrc/net_stem_tc.cu:
@@ -247,7 +294,7 @@ class PlanBuilder:
         if tc:
             flags |= FLAG_TC
         self._emit(_PendingOp(type=OP_CONV, flags=flags, k=(kh, kw), stride=stride, pad=(ph, pw),
-                              weight=self._pack_conv_tc(w) if tc else self._pack_conv(w),
+                              weight=self._pack_conv_tc(w, self._tc_bk(srcs)) if tc else self._pack_conv(w),
                               bias=self._dev(b), cout=co, ch_off=ch_off,
                               out_map=(Hd, Wd, sy, sx, oy, ox), HoWo=(Ho, Wo), w_raw=w), srcs, y, [res])
         return y
@@ -314,7 +361,7 @@ class PlanBuilder:
         tc = (self.use_tc and x.kind == "act" and x.C % 64 == 0 and co % 16 == 0 and 32 <= co and x.W >= 8
               and os.environ.get("CPB200_TC_DCN", "1") != "0")
         self._emit(_PendingOp(type=OP_DCN, flags=(FLAG_RELU if relu else 0) | (FLAG_TC if tc else 0), k=(3, 3),
-                              stride=1, pad=(1, 1), weight=self._pack_conv_tc(w) if tc else self._pack_conv(w),
+                              stride=1, pad=(1, 1), weight=self._pack_conv_tc(w, 64) if tc else self._pack_conv(w),
                               bias=self._dev(b), cout=co, w_raw=w), [x], y, [om])
         return y
 
@@ -345,7 +392,8 @@ class Plan:
                 if s.kind == "nchw_in":
                     self.in_slots.append((i, j))
                 else:
-                    o.src[j] = s.buf.data_ptr()
+                    o.src[j] = s.buf.data_ptr() + s.ch_off * (4 if pb.act_dtype == F32 else 2)
+                    o.src_pitch[j] = s.pitch if s.parent is not None else 0
             o.cout = po.cout
             o.kh, o.kw = po.k; o.stride = po.stride; o.pad_h, o.pad_w = po.pad
             d = po.dst

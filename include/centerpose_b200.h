@@ -181,7 +181,9 @@ typedef struct cpb200_op {
   const void *weight;        /* packed by centerpose_b200/plan.py, layout per op type */
   const float *bias;         /* fp32 [cout] (BatchNorm folded), may be NULL */
   void *tc;                  /* opaque tensor-core state prepared by cpb200_prepare_ops, or NULL */
-  uint64_t reserved1[2];
+  int32_t src_pitch[4];      /* channel pitch (elements per pixel) of each input when it is a channel SLICE of a wider NHWC
+                                tensor (src[i] then points at the slice's first channel); 0 = dense (pitch == cin[i]).
+                                Used by the fused head: one 3x3 conv produces all six hidden maps, the 1x1 convs read slices */
 } cpb200_op;
 
 /* Validate the program and build device-side descriptors (TMA tensor maps) for ops flagged

@@ -513,6 +513,35 @@ def test_mobilenet_ops_match_torch(precision):
             _check(_nchw(_run(pb, y)), fn(F.conv2d(x, w, b)), precision, 2e-2 if tc else None)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "bf16", "bf16tc"])
+def test_conv_reads_channel_slices(mode):
+    """cpb200_op.src_pitch: 1x1 convs reading channel slices of ONE wide NHWC tensor (the fused-head layout:
+    a single 3x3 conv writes all six hidden maps, each 1x1 head conv reads its slice through the pitch field)."""
+    precision = "fp32" if mode == "fp32" else "bf16"
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    B, C, H, W, hc = 2, 32, 16, 24, 64
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(B, C, H, W, generator=g).bfloat16().float()
+    w3 = (torch.randn(3 * hc, C, 3, 3, generator=g) * 0.1).bfloat16().float(); b3 = torch.randn(3 * hc, generator=g)
+    hid_ref = F.relu(F.conv2d(x, w3, b3, padding=1))
+    pb = _builder(B, precision, tc=(mode == "bf16tc"))
+    hid = pb.conv([pb.external(_nhwc(x, dt))], w3.to(DEV), b3.to(DEV), stride=1, pad=1, relu=True)
+    outs, refs = {}, []
+    for i, co in enumerate((5, 34, 17)):
+        w1 = (torch.randn(co, hc, 1, 1, generator=g) * 0.2).bfloat16().float(); b1 = torch.randn(co, generator=g)
+        sl = pb.channel_slice(hid, i * hc, hc)
+        dst = pb.output(co, H, W, f"o{i}")
+        pb.conv([sl], w1.to(DEV), b1.to(DEV), out="nchw", dst=dst)
+        assert pb.ops[-1].srcs[0].pitch == 3 * hc
+        outs[f"o{i}"] = torch.zeros(B, co, H, W, device=DEV)
+        hr = hid_ref[:, i * hc:(i + 1) * hc]
+        refs.append(F.conv2d(hr if precision == "fp32" else hr.bfloat16().float(), w1, b1))
+    plan = pb.build(); plan.bind(torch.zeros(1, device=DEV), outs)
+    plan.run(torch.cuda.current_stream().cuda_stream); torch.cuda.synchronize()
+    for i, ref in enumerate(refs):
+        _check(outs[f"o{i}"].cpu(), ref, precision, 2e-2 if precision == "bf16" else None)
+
+
 def test_forward_rejects_cpu_and_training():
     m, _ = _model("bf16")
     with pytest.raises(RuntimeError):

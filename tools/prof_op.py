@@ -15,7 +15,7 @@ OPS = {
     "head3x3": ("conv", 64, 256, 128, 3, 1), "conv64": ("conv", 64, 64, 128, 3, 1), "conv128": ("conv", 128, 128, 64, 3, 1),
     "conv256": ("conv", 256, 256, 32, 3, 1), "conv512": ("conv", 512, 512, 16, 3, 1), "om64": ("conv", 64, 27, 128, 3, 1),
     "level0": ("conv", 16, 16, 512, 3, 1), "level1": ("conv", 16, 32, 512, 3, 2), "root448": ("conv", 448, 128, 64, 1, 1),
-    "head1x1": ("conv", 256, 34, 128, 1, 1), "stem": ("stem",),
+    "head1x1": ("conv", 256, 34, 128, 1, 1), "reshead": ("conv", 256, 64, 128, 3, 1), "res1x1": ("conv", 64, 256, 128, 1, 1), "stem": ("stem",),
 }
 
 
