@@ -28,7 +28,7 @@ namespace {
 using namespace tc;
 
 constexpr int SP_TH = 16, SP_TW = 8;
-constexpr int SP_GROUPS = 3;
+constexpr int SP_GROUPS = 2;
 constexpr int SP_PT = 256;                                // producer threads per group
 constexpr int SP_THREADS = SP_GROUPS * SP_PT + 5 * 32;    // + MMA warp + 4 epilogue warps
 constexpr int SP_NACC = 4;
