@@ -14,6 +14,7 @@
 //                 fused here: the sampled im2col tile lives in shared memory only (the
 //                 reference round-trips a (B, 9C, HW) fp32 `columns` buffer through HBM).
 #include "common.cuh"
+#include <cstdlib>
 #include <algorithm>
 
 namespace {
@@ -439,6 +440,66 @@ __global__ void __launch_bounds__(256) dwdeconv_add_kernel(const T *__restrict__
   }
 }
 
+// Fast path for the shapes IDAUp uses (k == 2f, f and C/VEC powers of two, 256 % (f * C/VEC) == 0): every item a
+// thread visits in one output row has the same channel group and the same column parity class, so its four
+// (kh, kw) tap weight vectors are loaded into registers ONCE per CTA instead of 8 LDS.128 per item.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) dwdeconv_add_fast_kernel(const T *__restrict__ x, const T *__restrict__ skip, T *__restrict__ y,
+                                                                const float *__restrict__ w, int H, int W, int C, int Ho, int Wo,
+                                                                int k, int f, int pad, int lf, int lcv) {
+  const int CV = C / VEC;
+  const int b = blockIdx.x / Ho, ho = blockIdx.x % Ho;
+  const int i0 = threadIdx.x;
+  const int wo_first = i0 >> lcv, cv = i0 & (CV - 1);
+  const int kh0 = (ho + pad) & (f - 1), kw0 = (wo_first + pad) & (f - 1);
+  float wt[2][2][VEC];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float *wp = w + (size_t)((kh0 + a * f) * k + kw0 + c * f) * C + cv * VEC;
+#pragma unroll
+      for (int q = 0; q < VEC; q += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(wp + q));
+        wt[a][c][q] = v.x; wt[a][c][q + 1] = v.y; wt[a][c][q + 2] = v.z; wt[a][c][q + 3] = v.w;
+      }
+    }
+  const T *xb = x + (size_t)b * H * W * C + cv * VEC;
+  const int hn0 = ho + pad - kh0;                               // >= 0; tap a reads input row (hn0 >> lf) - a
+  const int hi0 = hn0 >> lf;
+  const size_t orow = ((size_t)b * Ho + ho) * Wo;
+  for (int i = i0; i < Wo * CV; i += 256) {
+    const int wo = i >> lcv;
+    const size_t opix = (orow + wo) * C + cv * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; q += 4) {
+      float4 s4 = skip ? Act<T>::ld4(skip + opix + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[q] = s4.x; acc[q + 1] = s4.y; acc[q + 2] = s4.z; acc[q + 3] = s4.w;
+    }
+    const int wi0 = (wo + pad - kw0) >> lf;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int hi = hi0 - a;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int wi = wi0 - c;
+        if (wi < 0 || wi >= W) continue;
+        const T *xp = xb + ((size_t)hi * W + wi) * C;
+#pragma unroll
+        for (int q = 0; q < VEC; q += 4) {
+          const float4 v = Act<T>::ld4(xp + q);
+          acc[q] = fmaf(v.x, wt[a][c][q], acc[q]); acc[q + 1] = fmaf(v.y, wt[a][c][q + 1], acc[q + 1]);
+          acc[q + 2] = fmaf(v.z, wt[a][c][q + 2], acc[q + 2]); acc[q + 3] = fmaf(v.w, wt[a][c][q + 3], acc[q + 3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < VEC; q += 4) Act<T>::st4(y + opix + q, make_float4(acc[q], acc[q + 1], acc[q + 2], acc[q + 3]));
+  }
+}
+
 // ---- nearest-neighbour upsample x f (+ skip add)(+ReLU), NHWC ----
 // out[b,ho,wo,c] = act(skip[b,ho,wo,c] + x[b,ho/f,wo/f,c])     (HRNet fuse_layers, pose_higher_hrnet.py:186-187,224-232)
 // Thread = 4 channels of one output pixel; f is a power of two (shift).
@@ -711,6 +772,16 @@ int run_op_simt(const cpb200_op &op, cudaStream_t st) {
           cudaFuncSetAttribute(dwdeconv_add_kernel<T, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return cpb::fail(CPB200_ERR_CUDA, "dwdeconv: cannot raise the shared-memory limit to %zu bytes", smem);
       auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
+      {
+        const int lf = ilog2(op.stride), lcv = ilog2(op.cin[0] / VEC);
+        const int CVv = op.cin[0] / VEC;
+        if (lf >= 0 && lcv >= 0 && op.kh == 2 * op.stride && CVv <= 256 && (256 / CVv) % op.stride == 0 && getenv("CPB200_DWDECONV_GENERIC") == nullptr) {
+          dwdeconv_add_fast_kernel<T, VEC><<<(unsigned)(op.B * op.Ho), 256, 0, st>>>(static_cast<const T *>(op.src[0]),
+              static_cast<const T *>(op.aux), static_cast<T *>(op.dst), static_cast<const float *>(op.weight),
+              op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h, lf, lcv);
+          return cpb::check_launch("dwdeconv_add_fast_kernel");
+        }
+      }
       dwdeconv_add_kernel<T, VEC><<<(unsigned)(op.B * op.Ho), 256, smem, st>>>(static_cast<const T *>(op.src[0]),
           static_cast<const T *>(op.aux), static_cast<T *>(op.dst), static_cast<const float *>(op.weight),
           op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h, ilog2(op.stride), ilog2(op.cin[0] / VEC));
