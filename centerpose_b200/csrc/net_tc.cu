@@ -52,7 +52,12 @@ struct alignas(64) TcArgs {
 
 using namespace tc;
 
-constexpr int DCN_THREADS = 448;   // + 8 gather-producer warps
+#ifndef CPB_DCN_GW
+#define CPB_DCN_GW 16                 // gather-producer warps: 8 (16 rows each, two half batches) or 16 (8 rows each)
+#endif
+constexpr int DCN_GW = CPB_DCN_GW;
+constexpr int DCN_ROWS = 128 / DCN_GW;          // operand rows per gather warp
+constexpr int DCN_THREADS = (6 + DCN_GW) * 32;
 
 struct __align__(16) DcnPrm { int off[4]; uint32_t wt[4]; };   // element offsets, packed bf16x2 (w,w) corner weights
 
@@ -66,7 +71,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
   __shared__ __align__(8) uint64_t bars[2 * 8 + 16];
   __shared__ uint32_t s_tmem;
   __shared__ float s_bias[2][BN];
-  __shared__ DcnPrm s_prm[DCN ? 8 : 1][DCN ? 9 : 1][DCN ? 16 : 1];
+  __shared__ DcnPrm s_prm[DCN ? DCN_GW : 1][DCN ? 9 : 1][DCN ? DCN_ROWS : 1];
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
   const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[24]);
 
@@ -77,7 +82,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
   if (warp == 0 && lane == 0) {
     if (!DCN) for (int s = 0; s < a.nsrc; ++s) tmap_prefetch(&a.amap[s]);
     tmap_prefetch(&a.bmap);
-    for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, DCN ? 1 + 256 : 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, DCN ? 1 + DCN_GW * 32 : 1); mbar_init(empty0 + 8 * s, 1); }
     for (int s = 0; s < 8; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -172,97 +177,187 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
     const int nk = 9 * slabs;
     const int chunk = lane & 7, rsub = lane >> 3;
     const __nv_bfloat16 *srcc = a.dcn_src + chunk * 8;
-    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-      int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
-      {   // ---- sampling parameters of this warp's 16 pixels, all 9 taps ----
-        const int rp = gw * 16 + (lane & 15);
-        const int ho = h0 + rp / a.TW, wo = w0 + rp % a.TW;
-        const bool okp = ho < a.Ho && wo < a.Wo;
-        const float *om = a.dcn_om + (((size_t)n * a.H + ho) * a.W + wo) * a.om_pitch;
-        const int tap0 = (lane < 16) ? 0 : 5, ntap = (lane < 16) ? 5 : 4;
-        float oh[5], ow[5], ml[5];
+    if constexpr (DCN_ROWS == 8) {
+      // ---- 16 gather warps x 8 rows: four warps per scheduler instead of two, 8 corner loads per thread and stage,
+      //      issued for the NEXT stage right after this stage's rows are stored ----
+      const int px = lane & 7, tg = lane >> 3;               // pixel of the warp, tap group {0,1,2} {3,4} {5,6} {7,8}
+      const int tap0 = tg == 0 ? 0 : 1 + 2 * tg, ntap = tg == 0 ? 3 : 2;
+      for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
+        {
+          const int rp = gw * 8 + px;
+          const int ho = h0 + rp / a.TW, wo = w0 + rp % a.TW;
+          const bool okp = ho < a.Ho && wo < a.Wo;
+          const float *om = a.dcn_om + (((size_t)n * a.H + ho) * a.W + wo) * a.om_pitch;
+          float oh[3], ow[3], ml[3];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          const int tap = tap0 + i;
-          const bool ld = okp && i < ntap;
-          oh[i] = ld ? __ldg(om + 2 * tap) : 0.f; ow[i] = ld ? __ldg(om + 2 * tap + 1) : 0.f; ml[i] = ld ? __ldg(om + 18 + tap) : 0.f;
-        }
-        __syncwarp();                                      // previous tile's readers are done with s_prm
-#pragma unroll
-        for (int i = 0; i < 5; ++i) {
-          if (i < ntap) {
+          for (int i = 0; i < 3; ++i) {
             const int tap = tap0 + i;
-            DcnPrm pr;
+            const bool ld = okp && i < ntap;
+            oh[i] = ld ? __ldg(om + 2 * tap) : 0.f; ow[i] = ld ? __ldg(om + 2 * tap + 1) : 0.f; ml[i] = ld ? __ldg(om + 18 + tap) : 0.f;
+          }
+          __syncwarp();                                      // previous tile's readers are done with s_prm
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { pr.off[c] = 0; pr.wt[c] = 0u; }
-            if (okp) {
-              const float mk = 1.0f / (1.0f + __expf(-ml[i]));
-              const float h_im = (float)(ho - 1 + tap / 3) + oh[i], w_im = (float)(wo - 1 + tap % 3) + ow[i];
-              if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {
-                const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-                const int h_high = h_low + 1, w_high = w_low + 1;
-                const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
-                const int rowb = n * a.H;
-                auto pk = [](float w) { __nv_bfloat162 b = __float2bfloat162_rn(w); return *reinterpret_cast<uint32_t *>(&b); };
-                if (h_low >= 0 && w_low >= 0) { pr.off[0] = ((rowb + h_low) * a.W + w_low) * Cin; pr.wt[0] = pk(hh * hw * mk); }
-                if (h_low >= 0 && w_high <= a.W - 1) { pr.off[1] = ((rowb + h_low) * a.W + w_high) * Cin; pr.wt[1] = pk(hh * lw * mk); }
-                if (h_high <= a.H - 1 && w_low >= 0) { pr.off[2] = ((rowb + h_high) * a.W + w_low) * Cin; pr.wt[2] = pk(lh * hw * mk); }
-                if (h_high <= a.H - 1 && w_high <= a.W - 1) { pr.off[3] = ((rowb + h_high) * a.W + w_high) * Cin; pr.wt[3] = pk(lh * lw * mk); }
+          for (int i = 0; i < 3; ++i) {
+            if (i < ntap) {
+              const int tap = tap0 + i;
+              DcnPrm pr;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) { pr.off[c] = 0; pr.wt[c] = 0u; }
+              if (okp) {
+                const float mk = 1.0f / (1.0f + __expf(-ml[i]));
+                const float h_im = (float)(ho - 1 + tap / 3) + oh[i], w_im = (float)(wo - 1 + tap % 3) + ow[i];
+                if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {
+                  const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                  const int h_high = h_low + 1, w_high = w_low + 1;
+                  const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+                  const int rowb = n * a.H;
+                  auto pk = [](float w) { __nv_bfloat162 b = __float2bfloat162_rn(w); return *reinterpret_cast<uint32_t *>(&b); };
+                  if (h_low >= 0 && w_low >= 0) { pr.off[0] = ((rowb + h_low) * a.W + w_low) * Cin; pr.wt[0] = pk(hh * hw * mk); }
+                  if (h_low >= 0 && w_high <= a.W - 1) { pr.off[1] = ((rowb + h_low) * a.W + w_high) * Cin; pr.wt[1] = pk(hh * lw * mk); }
+                  if (h_high <= a.H - 1 && w_low >= 0) { pr.off[2] = ((rowb + h_high) * a.W + w_low) * Cin; pr.wt[2] = pk(lh * hw * mk); }
+                  if (h_high <= a.H - 1 && w_high <= a.W - 1) { pr.off[3] = ((rowb + h_high) * a.W + w_high) * Cin; pr.wt[3] = pk(lh * lw * mk); }
+                }
               }
+              s_prm[gw][tap][px] = pr;
             }
-            s_prm[gw][tap][lane & 15] = pr;
           }
+          __syncwarp();
         }
-        __syncwarp();
+        uint4 v[2][4];
+        uint32_t w[2][4];
+        auto issue = [&](int tap, int c0) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const DcnPrm q = s_prm[gw][tap][i * 4 + rsub];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {       // invalid corners: weight 0, offset 0 (a safe address)
+              v[i][c] = __ldg(reinterpret_cast<const uint4 *>(srcc + (size_t)(unsigned)q.off[c] + c0));
+              w[i][c] = q.wt[c];
+            }
+          }
+        };
+        int tap_n = 0, c0_n = 0;
+        issue(0, 0);
+        for (int k = 0; k < nk; ++k) {
+          c0_n += 64;
+          if (c0_n >= Cin) { c0_n = 0; ++tap_n; }
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            __nv_bfloat162 acc2[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const __nv_bfloat162 w2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[i][c]);
+              const __nv_bfloat162 *vv = reinterpret_cast<const __nv_bfloat162 *>(&v[i][c]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc2[j] = (c == 0) ? __hmul2(w2, vv[j]) : __hfma2(w2, vv[j], acc2[j]);
+            }
+            const uint4 o = *reinterpret_cast<const uint4 *>(acc2);
+            const int row = gw * 8 + i * 4 + rsub;
+            const uint32_t dst = sa + row * 128 + ((chunk ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
+          if (k + 1 < nk) issue(tap_n, c0_n);                // next stage's corners fly across the fence / arrive / wait
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(full0 + 8 * stage);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
       }
-      uint4 vA[2][4], vB[2][4];
-      uint32_t wA[2][4], wB[2][4];
-      // (tap, channel offset) of a stage are tracked incrementally — no integer division in the hot loop
-      auto issue = [&](int tap, int c0, int half, uint4 (&v)[2][4], uint32_t (&w)[2][4]) {
+    } else {
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+        int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
+        {   // ---- sampling parameters of this warp's 16 pixels, all 9 taps ----
+          const int rp = gw * 16 + (lane & 15);
+          const int ho = h0 + rp / a.TW, wo = w0 + rp % a.TW;
+          const bool okp = ho < a.Ho && wo < a.Wo;
+          const float *om = a.dcn_om + (((size_t)n * a.H + ho) * a.W + wo) * a.om_pitch;
+          const int tap0 = (lane < 16) ? 0 : 5, ntap = (lane < 16) ? 5 : 4;
+          float oh[5], ow[5], ml[5];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const DcnPrm q = s_prm[gw][tap][(half * 2 + i) * 4 + rsub];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {       // invalid corners: weight 0, offset 0 (a safe address)
-            v[i][c] = __ldg(reinterpret_cast<const uint4 *>(srcc + (size_t)(unsigned)q.off[c] + c0));
-            w[i][c] = q.wt[c];
+          for (int i = 0; i < 5; ++i) {
+            const int tap = tap0 + i;
+            const bool ld = okp && i < ntap;
+            oh[i] = ld ? __ldg(om + 2 * tap) : 0.f; ow[i] = ld ? __ldg(om + 2 * tap + 1) : 0.f; ml[i] = ld ? __ldg(om + 18 + tap) : 0.f;
           }
-        }
-      };
-      auto blend_store = [&](uint32_t sa, int half, const uint4 (&v)[2][4], const uint32_t (&w)[2][4]) {
+          __syncwarp();                                      // previous tile's readers are done with s_prm
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          __nv_bfloat162 acc2[4];
+          for (int i = 0; i < 5; ++i) {
+            if (i < ntap) {
+              const int tap = tap0 + i;
+              DcnPrm pr;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const __nv_bfloat162 w2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[i][c]);
-            const __nv_bfloat162 *vv = reinterpret_cast<const __nv_bfloat162 *>(&v[i][c]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc2[j] = (c == 0) ? __hmul2(w2, vv[j]) : __hfma2(w2, vv[j], acc2[j]);
+              for (int c = 0; c < 4; ++c) { pr.off[c] = 0; pr.wt[c] = 0u; }
+              if (okp) {
+                const float mk = 1.0f / (1.0f + __expf(-ml[i]));
+                const float h_im = (float)(ho - 1 + tap / 3) + oh[i], w_im = (float)(wo - 1 + tap % 3) + ow[i];
+                if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {
+                  const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                  const int h_high = h_low + 1, w_high = w_low + 1;
+                  const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+                  const int rowb = n * a.H;
+                  auto pk = [](float w) { __nv_bfloat162 b = __float2bfloat162_rn(w); return *reinterpret_cast<uint32_t *>(&b); };
+                  if (h_low >= 0 && w_low >= 0) { pr.off[0] = ((rowb + h_low) * a.W + w_low) * Cin; pr.wt[0] = pk(hh * hw * mk); }
+                  if (h_low >= 0 && w_high <= a.W - 1) { pr.off[1] = ((rowb + h_low) * a.W + w_high) * Cin; pr.wt[1] = pk(hh * lw * mk); }
+                  if (h_high <= a.H - 1 && w_low >= 0) { pr.off[2] = ((rowb + h_high) * a.W + w_low) * Cin; pr.wt[2] = pk(lh * hw * mk); }
+                  if (h_high <= a.H - 1 && w_high <= a.W - 1) { pr.off[3] = ((rowb + h_high) * a.W + w_high) * Cin; pr.wt[3] = pk(lh * lw * mk); }
+                }
+              }
+              s_prm[gw][tap][lane & 15] = pr;
+            }
           }
-          const uint4 o = *reinterpret_cast<const uint4 *>(acc2);
-          const int row = gw * 16 + (half * 2 + i) * 4 + rsub;
-          const uint32_t dst = sa + row * 128 + ((chunk ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          __syncwarp();
         }
-      };
-      int tap_c = 0, c0_c = 0;            // current stage
-      int tap_n = 0, c0_n = 64;           // next stage
-      if (c0_n >= Cin) { c0_n = 0; tap_n = 1; }
-      issue(tap_c, c0_c, 0, vA, wA);
-      for (int k = 0; k < nk; ++k) {
-        issue(tap_c, c0_c, 1, vB, wB);
-        mbar_wait(empty0 + 8 * stage, phase ^ 1);
-        const uint32_t sa = smem_base + stage * stage_bytes;
-        blend_store(sa, 0, vA, wA);
-        if (k + 1 < nk) issue(tap_n, c0_n, 0, vA, wA);
-        blend_store(sa, 1, vB, wB);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(full0 + 8 * stage);
-        if (++stage == a.stages) { stage = 0; phase ^= 1; }
-        tap_c = tap_n; c0_c = c0_n;
-        c0_n += 64;
-        if (c0_n >= Cin) { c0_n = 0; ++tap_n; }
+        uint4 vA[2][4], vB[2][4];
+        uint32_t wA[2][4], wB[2][4];
+        // (tap, channel offset) of a stage are tracked incrementally — no integer division in the hot loop
+        auto issue = [&](int tap, int c0, int half, uint4 (&v)[2][4], uint32_t (&w)[2][4]) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const DcnPrm q = s_prm[gw][tap][(half * 2 + i) * 4 + rsub];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {       // invalid corners: weight 0, offset 0 (a safe address)
+              v[i][c] = __ldg(reinterpret_cast<const uint4 *>(srcc + (size_t)(unsigned)q.off[c] + c0));
+              w[i][c] = q.wt[c];
+            }
+          }
+        };
+        auto blend_store = [&](uint32_t sa, int half, const uint4 (&v)[2][4], const uint32_t (&w)[2][4]) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            __nv_bfloat162 acc2[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const __nv_bfloat162 w2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[i][c]);
+              const __nv_bfloat162 *vv = reinterpret_cast<const __nv_bfloat162 *>(&v[i][c]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc2[j] = (c == 0) ? __hmul2(w2, vv[j]) : __hfma2(w2, vv[j], acc2[j]);
+            }
+            const uint4 o = *reinterpret_cast<const uint4 *>(acc2);
+            const int row = gw * 16 + (half * 2 + i) * 4 + rsub;
+            const uint32_t dst = sa + row * 128 + ((chunk ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
+        };
+        int tap_c = 0, c0_c = 0;            // current stage
+        int tap_n = 0, c0_n = 64;           // next stage
+        if (c0_n >= Cin) { c0_n = 0; tap_n = 1; }
+        issue(tap_c, c0_c, 0, vA, wA);
+        for (int k = 0; k < nk; ++k) {
+          issue(tap_c, c0_c, 1, vB, wB);
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          blend_store(sa, 0, vA, wA);
+          if (k + 1 < nk) issue(tap_n, c0_n, 0, vA, wA);
+          blend_store(sa, 1, vB, wB);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(full0 + 8 * stage);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          tap_c = tap_n; c0_c = c0_n;
+          c0_n += 64;
+          if (c0_n >= Cin) { c0_n = 0; ++tap_n; }
+        }
       }
     }
   } else {
