@@ -31,7 +31,7 @@ using namespace tc;
 
 namespace {
 
-constexpr int C3_THREADS = 224;
+constexpr int C3_THREADS = 352;     // warps: 0 halo producer, 1 MMA, 2-5 epilogue group 0, 6 weight producer, 7-10 epilogue group 1
 constexpr int TW = 8, TH = 16, HW_ = TW + 2, HH_ = TH + 2;
 constexpr int MAX_NA = 16, MAX_NB = 8;
 
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
   const uint32_t a_base = smem_base, b_base = smem_base + a.na * a.a_stage_bytes;
   __shared__ __align__(8) uint64_t bars[2 * MAX_NA + 2 * MAX_NB + 1 + 16];
   __shared__ uint32_t s_tmem;
-  __shared__ float s_bias[2][BN];
+  __shared__ float s_bias[2][2][BN];      // [epilogue group][tile parity within the group]
   const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[MAX_NA]);
   const uint32_t bfull0 = smem_u32(&bars[2 * MAX_NA]), bempty0 = smem_u32(&bars[2 * MAX_NA + MAX_NB]);
   const uint32_t ball = smem_u32(&bars[2 * MAX_NA + 2 * MAX_NB]);
@@ -203,24 +203,30 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
     }
   } else {
-    // =============================== epilogue (warps 2..5) ===============================
+    // =============================== epilogue (two groups of four warps, alternate tiles) ===============================
+    // With N = 256 tiles the read-out of one accumulator (128 x 256 fp32 -> bias, activation, bf16, 512 B per thread)
+    // takes as long as the MMAs of the next tile; two groups working on alternate tiles (= alternate accumulator
+    // stages) keep the tensor pipe from waiting for a free accumulator.
+    const int grp = warp >= 7 ? 1 : 0;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;
+    const int et = grp ? (int)threadIdx.x - 224 : (int)threadIdx.x - 64;
     const uint32_t act = a.flags & CPB_ACT_MASK;
     const bool out_f32 = a.flags & CPB200_FLAG_OUT_F32;
-    int acc = 0; uint32_t accphase = 0;
+    int acc = grp; uint32_t accphase = 0;
+    int par = 0;                                            // tile parity within this group (bias double buffer)
     bool bias_loaded = false;
-    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x + grp * gridDim.x; t < a.total_tiles; t += 2 * gridDim.x) {
       int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
       const int n0 = nt * BN;
+      float *sbias = s_bias[grp][par];
       if (a.n_tiles > 1 || !bias_loaded) {      // one N tile: the bias never changes — load it once
         for (int i = et; i < BN; i += 128) {
           const float bv = (a.bias && n0 + i < a.cout) ? __ldg(a.bias + n0 + i) : 0.f;
-          s_bias[acc & 1][i] = bv;
-          if (a.n_tiles == 1) s_bias[(acc & 1) ^ 1][i] = bv;
+          sbias[i] = bv;
+          if (a.n_tiles == 1) s_bias[grp][par ^ 1][i] = bv;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
         bias_loaded = true;
       }
       mbar_wait(tfull0 + 8 * acc, accphase);
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
         if (ok && nb < a.cout) {
           float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[acc & 1][c * 16 + j];
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + sbias[c * 16 + j];
           if (out_f32) {
             float *o = static_cast<float *>(a.dst) + pix * a.cout_store + nb;
             if (nb + 16 <= a.cout && (a.cout_store & 3) == 0) {
@@ -285,7 +291,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-      if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
+      acc += 2; par ^= 1;
+      if (acc >= a.nacc) { acc -= a.nacc; accphase ^= 1; }
     }
   }
 
