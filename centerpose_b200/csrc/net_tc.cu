@@ -11,12 +11,12 @@
 // TMA zero-fills out-of-bounds coordinates, which IS the convolution's zero padding, and lands the
 // box in shared memory as 128 rows of BK bf16 in the 128B/64B/32B-swizzled K-major layout the UMMA
 // shared-memory descriptor expects — no im2col buffer exists anywhere.
-// B operand: weights packed [tap][Cout_pad][Cin_total] bf16 (K-major), 3-D TMA box {BK, BN, 1}.
+// B operand: weights packed slab-major [tap][K-slab][Cout_pad][BK] bf16 (K-major), 3-D TMA box {BK, BN, 1}.
 // `Root` concatenations are K-slabs from up to four tensor maps (no torch.cat copy).
 //
 // Warp roles (192 threads, persistent CTAs, one per SM): warp 0 = TMA producer, warp 1 = MMA
 // issuer + TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> +bias (+residual) -> ReLU -> bf16 ->
-// global).  Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1;
+// global).  Two to eight TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1;
 // a STAGES-deep smem ring with full/empty mbarriers feeds the tensor core.
 #include "tc_common.cuh"
 #include <mutex>
@@ -166,11 +166,12 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
     // A[row = pixel][k = channel] of tap t is  sigmoid(mask_t) * bilinear(x, p + tap_t + offset_t)
     // (dcn_v2_im2col_cuda.cu:25-54,125-195), rounded to bf16 and stored straight into the 128B-swizzled
     // K-major tile the UMMA descriptor reads (16-byte chunk j of row r lives at chunk j ^ (r & 7)).
-    // 8 warps x 16 rows.  Per tile each warp first turns the 27 offset/mask values of its 16 pixels into
+    // DCN_GW warps x DCN_ROWS rows (16 x 8; the 8 x 16 variant below is kept for reference).  Per tile each warp first
+    // turns the 27 offset/mask values of its pixels into
     // (4 corner offsets, 4 packed corner weights) for all 9 taps (one round trip to global memory instead
     // of one per tap); the per-stage work is then software-pipelined in two half batches of 8 corner loads:
     // the loads of the next half are always in flight while the current half is blended.
-    const int gw = warp - 6;                               // rows [16*gw, 16*gw+16)
+    const int gw = warp - 6;                               // rows [DCN_ROWS*gw, DCN_ROWS*(gw+1))
     int stage = 0; uint32_t phase = 0;
     const int Cin = a.cin[0];
     const int slabs = Cin >> 6;

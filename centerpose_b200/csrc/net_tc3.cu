@@ -13,10 +13,10 @@
 // cpb200_probe_halo (csrc/probe.cu, tools/halo_probe.py: exact with descriptor base_offset = 0).
 // TMA's out-of-bounds zero fill provides the conv padding for the halo border.
 //
-// Weights: [tap][Cout_pad][Cin] bf16 via 3-D TMA; when the whole filter bank fits beside the halo
+// Weights: slab-major [tap][K-slab][Cout_pad][BK] bf16 via 3-D TMA; when the whole filter bank fits beside the halo
 // ring it is loaded ONCE per CTA and stays resident (e.g. 64->64: 72 KB), otherwise it streams
-// through its own ring.  Warps: 0 = halo producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue,
-// 6 = weight producer; persistent CTAs, up to eight TMEM accumulator stages.
+// through its own ring.  Warps: 0 = halo producer, 1 = MMA issuer + TMEM owner, 2..5 and 7..10 = two epilogue
+// groups on alternate tiles, 6 = weight producer; persistent CTAs, up to eight TMEM accumulator stages.
 //
 // Tried and dropped (round 1, see profiles/r01_group_interleave_experiment.log): interleaving the taps of G
 // tiles in the issue loop so that consecutive tcgen05.mma instructions target different accumulators (and

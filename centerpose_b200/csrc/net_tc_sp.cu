@@ -17,7 +17,7 @@
 //            (r&1, s&1), window offset ((r/2)*9 + s/2) rows, group stride 9 rows.
 //   swizzle  32-byte (C=16) / 64-byte (C=32) pattern applied on absolute shared-memory address bits
 //            (chunk bit(s) [4..] ^= address bits [7..]); stage bases are 1024-aligned.
-//   weights  the ordinary tensor-core packing [tap][N][C] bf16 (plan.py::_pack_conv_tc), swizzled while being
+//   weights  the ordinary tensor-core packing [tap][1 slab][N][C] bf16 (plan.py::_pack_conv_tc, bk = C), swizzled while being
 //            copied to shared memory once per CTA.
 #include "tc_common.cuh"
 
