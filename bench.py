@@ -180,7 +180,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CPB200_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("CPB200_PRECISION", "bf16"), choices=["fp16x2", "bf16x2", "bf16", "fp32"])
     ap.add_argument("--arch", default="dla_34", choices=sorted(ARCH_GFLOP), help="dla_34 = the headline config")
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

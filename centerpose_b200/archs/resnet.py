@@ -47,20 +47,11 @@ def build_params(cfg=None) -> nn.Module:
     return root
 
 
-_KSEL = {0: [3, 1], 1: [2, 0]}        # kernel rows/cols feeding output parity 0 / 1, in input order
-
-
 def _deconv_bn_relu(pb: PlanBuilder, P: StateView, x: Sym, wkey: str, bnkey: str) -> Sym:
+    """ConvTranspose2d(k4,s2,p1) + BN + ReLU (msra_resnet.py:168-193) -> four parity 2x2 convs (PlanBuilder.deconv_k4s2)."""
     w_t = P(wkey + ".weight").float()                  # (Cin, Cout, 4, 4)
     w_full, b = fold_bn(w_t.permute(1, 0, 2, 3).contiguous(), None, P.bn(bnkey))   # (Cout, Cin, 4, 4)
-    co = w_full.shape[0]
-    y = pb._sym(co, 2 * x.H, 2 * x.W)
-    for a in (0, 1):
-        for bb in (0, 1):
-            w_sub = w_full[:, :, _KSEL[a], :][:, :, :, _KSEL[bb]].contiguous()        # (Cout, Cin, 2, 2)
-            pb.conv([x], w_sub, b, stride=1, relu=True, dst=y, pad_hw=(1 - a, 1 - bb),
-                    out_map=(2 * x.H, 2 * x.W, 2, 2, a, bb, x.H, x.W))
-    return y
+    return pb.deconv_k4s2(x, w_full, b, relu=True)
 
 
 def lower(pb: PlanBuilder, P: StateView, x: Sym) -> Sym:

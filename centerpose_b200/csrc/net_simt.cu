@@ -14,6 +14,7 @@
 //                 fused here: the sampled im2col tile lives in shared memory only (the
 //                 reference round-trips a (B, 9C, HW) fp32 `columns` buffer through HBM).
 #include "common.cuh"
+#include <cuda_fp16.h>
 #include <cstdlib>
 #include <algorithm>
 
@@ -678,6 +679,146 @@ __global__ void __launch_bounds__(256) scale_add_kernel(const T *__restrict__ x,
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Split-operand activations (CPB200_BF16X2 / CPB200_F16X2): a value is hi + lo, two 16-bit planes `plane` elements apart
+// (include/centerpose_b200.h).  hi + lo is exact in fp32 and split(hi + lo) reproduces the value exactly, so max-pooling
+// and copies are lossless; arithmetic happens in fp32 and the result is re-split.
+struct Sp16 {
+  __device__ static float2 up(uint32_t v, uint32_t fmt) {
+    if (fmt) return __half22float2(*reinterpret_cast<const __half2 *>(&v));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&v));
+  }
+  __device__ static float4 ld4(const uint16_t *p, size_t plane, uint32_t fmt) {
+    const uint2 h = __ldg(reinterpret_cast<const uint2 *>(p)), l = __ldg(reinterpret_cast<const uint2 *>(p + plane));
+    const float2 h0 = up(h.x, fmt), h1 = up(h.y, fmt), l0 = up(l.x, fmt), l1 = up(l.y, fmt);
+    return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+  }
+  __device__ static void split2(float a, float b, uint32_t fmt, uint32_t &hi, uint32_t &lo) {
+    if (fmt) {
+      a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
+      const __half2 h = __floats2half2_rn(a, b);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+      hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
+    } else {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      const float2 hf = __bfloat1622float2(h);
+      const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+      hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
+    }
+  }
+  __device__ static void st4(uint16_t *p, size_t plane, uint32_t fmt, float4 v) {
+    uint2 h, l;
+    split2(v.x, v.y, fmt, h.x, l.x); split2(v.z, v.w, fmt, h.y, l.y);
+    *reinterpret_cast<uint2 *>(p) = h;
+    *reinterpret_cast<uint2 *>(p + plane) = l;
+  }
+};
+
+// fp32 NHWC <-> split planes (CPB200_OP_CONVERT), 4 elements per thread
+__global__ void __launch_bounds__(256) convert_to_split_kernel(const float *__restrict__ x, uint16_t *__restrict__ y, long long n4, size_t plane, uint32_t fmt) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    Sp16::st4(y + i * 4, plane, fmt, __ldg(reinterpret_cast<const float4 *>(x) + i));
+}
+__global__ void __launch_bounds__(256) convert_from_split_kernel(const uint16_t *__restrict__ x, float *__restrict__ y, long long n4, size_t plane, uint32_t fmt) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+    reinterpret_cast<float4 *>(y)[i] = Sp16::ld4(x + i * 4, plane, fmt);
+}
+
+// max-pool on split planes (pose_dla_dcn.py:196, msra_resnet.py:126): exact (the maximum is one of the inputs)
+__global__ void maxpool_split_kernel(const uint16_t *__restrict__ x, uint16_t *__restrict__ y, int B, int H, int W, int C,
+                                     int Ho, int Wo, int k, int stride, int pad, uint32_t fmt) {
+  const int C4 = C >> 2;
+  const long long total = (long long)B * Ho * Wo * C4;
+  const size_t xplane = (size_t)B * H * W * C, yplane = (size_t)B * Ho * Wo * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long long p = i / C4;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int r = 0; r < k; ++r) {
+      const int hi = ho * stride - pad + r;
+      if (hi < 0 || hi >= H) continue;
+      for (int q = 0; q < k; ++q) {
+        const int wi = wo * stride - pad + q;
+        if (wi < 0 || wi >= W) continue;
+        const float4 v = Sp16::ld4(x + (((size_t)b * H + hi) * W + wi) * C + c4 * 4, xplane, fmt);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    Sp16::st4(y + (((size_t)b * Ho + ho) * Wo + wo) * C + c4 * 4, yplane, fmt, m);
+  }
+}
+
+// depthwise ConvTranspose2d(k = 2f, stride f, pad f/2) + skip add on split planes (IDAUp up_*, pose_dla_dcn.py:361-364,374-377).
+// One CTA = one output row (b, ho); thread = (wo, 4 channels); every output pixel has exactly 2 x 2 contributing taps
+// (k == 2f).  fp32 arithmetic, tap weights fp32 [k*k][C].
+__global__ void __launch_bounds__(256) dwdeconv_add_split_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict__ skip,
+                                                                 uint16_t *__restrict__ y, const float *__restrict__ w, int B, int H, int W, int C,
+                                                                 int Ho, int Wo, int k, int f, int pad, uint32_t fmt) {
+  const int C4 = C >> 2;
+  const int b = blockIdx.x / Ho, ho = blockIdx.x % Ho;
+  const size_t xplane = (size_t)B * H * W * C, yplane = (size_t)B * Ho * Wo * C;
+  const int kh0 = (ho + pad) % f;
+  for (int i = threadIdx.x; i < Wo * C4; i += blockDim.x) {
+    const int wo = i / C4, c4 = i - wo * C4;
+    const size_t opix = (((size_t)b * Ho + ho) * Wo + wo) * C + c4 * 4;
+    float4 acc = skip ? Sp16::ld4(skip + opix, yplane, fmt) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int kw0 = (wo + pad) % f;
+    for (int khh = kh0; khh < k; khh += f) {
+      const int hn = ho + pad - khh;
+      if (hn < 0) continue;
+      const int hi = hn / f;
+      if (hi >= H) continue;
+      for (int kww = kw0; kww < k; kww += f) {
+        const int wn = wo + pad - kww;
+        if (wn < 0) continue;
+        const int wi = wn / f;
+        if (wi >= W) continue;
+        const float4 v = Sp16::ld4(x + (((size_t)b * H + hi) * W + wi) * C + c4 * 4, xplane, fmt);
+        const float4 ww = __ldg(reinterpret_cast<const float4 *>(w + (size_t)(khh * k + kww) * C + c4 * 4));
+        acc.x = fmaf(v.x, ww.x, acc.x); acc.y = fmaf(v.y, ww.y, acc.y); acc.z = fmaf(v.z, ww.z, acc.z); acc.w = fmaf(v.w, ww.w, acc.w);
+      }
+    }
+    Sp16::st4(y + opix, yplane, fmt, acc);
+  }
+}
+
+int run_op_split(const cpb200_op &op, cudaStream_t st) {
+  const uint32_t fmt = op.act_dtype == CPB200_F16X2 ? 1u : 0u;
+  switch (op.type) {
+    case CPB200_OP_CONVERT: {
+      const long long n = (long long)op.B * op.H * op.W * op.cin[0];
+      if (n % 4) return cpb::fail(CPB200_ERR_ARG, "convert: element count must be a multiple of 4");
+      const unsigned grid = (unsigned)std::min<long long>((n / 4 + 255) / 256, 148LL * 16);
+      if (op.flags & CPB200_FLAG_TO_F32)
+        convert_from_split_kernel<<<grid, 256, 0, st>>>(static_cast<const uint16_t *>(op.src[0]), static_cast<float *>(op.dst), n / 4, (size_t)n, fmt);
+      else
+        convert_to_split_kernel<<<grid, 256, 0, st>>>(static_cast<const float *>(op.src[0]), static_cast<uint16_t *>(op.dst), n / 4, (size_t)n, fmt);
+      return cpb::check_launch("convert_split_kernel");
+    }
+    case CPB200_OP_MAXPOOL: {
+      if (op.cin[0] % 4) return cpb::fail(CPB200_ERR_ARG, "maxpool: C %% 4 != 0");
+      const long long total = (long long)op.B * op.Ho * op.Wo * (op.cin[0] / 4);
+      const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 32);
+      maxpool_split_kernel<<<grid, 256, 0, st>>>(static_cast<const uint16_t *>(op.src[0]), static_cast<uint16_t *>(op.dst),
+                                                 op.B, op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h, fmt);
+      return cpb::check_launch("maxpool_split_kernel");
+    }
+    case CPB200_OP_DWDECONV_ADD: {
+      if (op.cin[0] % 4 || op.kh != 2 * op.stride) return cpb::fail(CPB200_ERR_ARG, "dwdeconv (split): needs C %% 4 == 0 and k == 2 * stride");
+      dwdeconv_add_split_kernel<<<(unsigned)(op.B * op.Ho), 256, 0, st>>>(static_cast<const uint16_t *>(op.src[0]),
+          static_cast<const uint16_t *>(op.aux), static_cast<uint16_t *>(op.dst), static_cast<const float *>(op.weight),
+          op.B, op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h, fmt);
+      return cpb::check_launch("dwdeconv_add_split_kernel");
+    }
+    default:
+      return cpb::fail(CPB200_ERR_ARG, "op type %d has no split-precision kernel (the host must route it through fp32)", op.type);
+  }
+}
+
 template <typename T, bool DCN>
 int launch_conv(const cpb200_op &op, cudaStream_t st) {
   ConvArgs a;
@@ -845,6 +986,8 @@ int run_op_simt(const cpb200_op &op, cudaStream_t st) {
 
 namespace cpb {
 int run_op_simt_dispatch(const cpb200_op &op, cudaStream_t st) {
+  if (op.act_dtype == CPB200_BF16X2 || op.act_dtype == CPB200_F16X2) return run_op_split(op, st);
+  if (op.type == CPB200_OP_CONVERT) return fail(CPB200_ERR_ARG, "convert: act_dtype must name a split layout");
   if (op.act_dtype == CPB200_F32) return run_op_simt<float>(op, st);
   if (op.act_dtype == CPB200_BF16) return run_op_simt<__nv_bfloat16>(op, st);
   return fail(CPB200_ERR_ARG, "bad act_dtype %d", op.act_dtype);

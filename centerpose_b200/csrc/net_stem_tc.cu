@@ -34,12 +34,15 @@ constexpr int NACC = 4;
 
 struct StemArgs {
   const float *x;            // (B,3,H,W) fp32
-  __nv_bfloat16 *y;          // (B,Ho,Wo,N) bf16
+  __nv_bfloat16 *y;          // (B,Ho,Wo,N) bf16   [split mode: hi plane, lo plane y_plane elements later]
   const uint4 *wimg;         // pre-swizzled B operand image: SLABS x (N x 128 B)
   const float *bias;
   int B, H, W, Ho, Wo;
   int tiles_h, tiles_w, total_tiles;
   uint32_t act;
+  uint32_t fmt;              // split mode (stem_tc_h_kernel<N, 2>): 0 = bf16 planes, 1 = fp16 planes
+  float acc_scale;
+  long long y_plane;
 };
 
 template <int N, int S>
@@ -238,17 +241,26 @@ constexpr int HT_H = 16, HT_W = 8;                       // output tile, M = 128
 constexpr int HP_W = HT_W + 6, HP_H = HT_H + 6;          // input patch 22 x 14 per channel
 constexpr int HVEC = HT_H * HP_W;                        // 224 operand vectors per tile = producer threads
 constexpr int HA_STAGE_BYTES = ((HVEC * 64 + 1023) / 1024) * 1024;
-constexpr int H_NSTAGE = 6;
 constexpr int H_GROUPS = 3;                              // producer groups (7 warps each) on alternate tiles: tiles in flight
 constexpr int H_THREADS = H_GROUPS * HVEC + 5 * 32;      // producers + MMA warp + 4 epilogue warps
+template <int N_, int P_> struct HStages { static constexpr int value = (P_ == 2 && N_ > 16) ? 4 : 6; };
 
-template <int N>
+// P = 2 (split operands, CPB200_BF16X2 / CPB200_F16X2): every producer thread splits its 21 fp32 input values into a hi and a
+// lo 64-byte vector; a stage is [hi vectors | lo vectors], the weight image per horizontal tap [hi tile | lo tile]
+// (plan.py::_pack_stem_tc_h), so A_hi x [W_hi ; W_lo] is one N = 2N instruction into two accumulator halves and
+// A_lo x W_hi a second one; the epilogue adds the halves and stores the hi / lo planes of the output.
+template <int N, int P>
 __global__ void __launch_bounds__(H_THREADS, 1) stem_tc_h_kernel(const StemArgs a) {
-  constexpr int B_TAP_BYTES = N * 64;
+  constexpr int H_NSTAGE = HStages<N, P>::value;
+  constexpr int HA_PLANE_BYTES = HA_STAGE_BYTES;           // one plane of a stage
+  constexpr int HA_STAGE = P * HA_PLANE_BYTES;
+  constexpr int B_TILE_BYTES = N * 64;
+  constexpr int B_TAP_BYTES = P * B_TILE_BYTES;
+  constexpr int ACC_COLS = P * N;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = smem_base + H_NSTAGE * HA_STAGE_BYTES;
+  const uint32_t b_base = smem_base + H_NSTAGE * HA_STAGE;
   __shared__ __align__(8) uint64_t bars[2 * H_NSTAGE + 2 * NACC];
   __shared__ uint32_t s_tmem;
   __shared__ float s_bias[N];
@@ -256,7 +268,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) stem_tc_h_kernel(const StemArgs 
   const uint32_t tfull0 = smem_u32(&bars[2 * H_NSTAGE]), tempty0 = smem_u32(&bars[2 * H_NSTAGE + NACC]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int MMA_WARP = H_GROUPS * HVEC / 32;
-  constexpr uint32_t TMEM_COLS = (NACC * N) < 32 ? 32u : (uint32_t)(NACC * N);
+  constexpr uint32_t TMEM_COLS = (NACC * ACC_COLS) < 32 ? 32u : (uint32_t)(NACC * ACC_COLS);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < H_NSTAGE; ++s) { mbar_init(full0 + 8 * s, HVEC); mbar_init(empty0 + 8 * s, 1); }
@@ -267,7 +279,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) stem_tc_h_kernel(const StemArgs 
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < H_NSTAGE * HA_STAGE_BYTES / 16; i += H_THREADS)      // pad values (k >= 21) stay zero
+  for (int i = threadIdx.x; i < H_NSTAGE * HA_STAGE / 16; i += H_THREADS)      // pad values (k >= 21) stay zero
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(a_base + i * 16), "r"(0u) : "memory");
   for (int i = threadIdx.x; i < 7 * B_TAP_BYTES / 16; i += H_THREADS) {
     const uint4 v = __ldg(a.wimg + i);
@@ -343,40 +355,58 @@ __global__ void __launch_bounds__(H_THREADS, 1) stem_tc_h_kernel(const StemArgs 
     for (int t = t_first; t < a.total_tiles; t += tstep, it += H_GROUPS) {
       const int stage = it % H_NSTAGE;
       const uint32_t phase = (uint32_t)(it / H_NSTAGE) & 1u;
-      uint32_t pk[12];
+      uint32_t pk[12], pl_[P == 2 ? 12 : 1];
 #pragma unroll
       for (int q = 0; q < 12; ++q) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
-        pk[q] = *reinterpret_cast<uint32_t *>(&h);
+        if constexpr (P == 2) {
+          split2(f[2 * q], f[2 * q + 1], a.fmt, pk[q], pl_[q]);
+        } else {
+          __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+          pk[q] = *reinterpret_cast<uint32_t *>(&h);
+        }
       }
       if (t + tstep < a.total_tiles) fetch(t + tstep);                   // in flight while we wait for the stage
       mbar_wait(empty0 + 8 * stage, phase ^ 1);
-      const uint32_t sa = a_base + stage * HA_STAGE_BYTES + vrow;
+      const uint32_t sa = a_base + stage * HA_STAGE + vrow;
 #pragma unroll
       for (int j = 0; j < 3; ++j)
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + ((j ^ sw) << 4)), "r"(pk[4 * j]), "r"(pk[4 * j + 1]),
                      "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+      if constexpr (P == 2) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + HA_PLANE_BYTES + ((j ^ sw) << 4)), "r"(pl_[4 * j]),
+                       "r"(pl_[4 * j + 1]), "r"(pl_[4 * j + 2]), "r"(pl_[4 * j + 3]) : "memory");
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(full0 + 8 * stage);
     }
   } else if (warp == MMA_WARP) {
     // =============================== MMA issuer ===============================
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = P == 1 ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
+                                  : idesc_m128(N, a.fmt);
+    const uint32_t idesc2 = idesc_m128(2 * N, a.fmt);
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t accphase = 0;
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
       mbar_wait(full0 + 8 * stage, phase);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t d_tmem = tmem_base + acc * N;
-        const uint64_t ad0 = sbo_desc(a_base + stage * HA_STAGE_BYTES, HP_W * 64);
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        const uint64_t ad0 = sbo_desc(a_base + stage * HA_STAGE, HP_W * 64);
         const uint64_t bd0 = sbo_desc(b_base, 8 * 64);
 #pragma unroll
         for (int s = 0; s < 7; ++s) {
 #pragma unroll
-          for (int k = 0; k < 2; ++k)
-            umma_bf16(d_tmem, ad0 + (uint32_t)(s * 4 + 2 * k), bd0 + (uint32_t)(s * (B_TAP_BYTES >> 4) + 2 * k), idesc,
-                      (s > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 2; ++k) {
+            const uint32_t first = (s > 0 || k > 0) ? 1u : 0u;
+            if constexpr (P == 2) {
+              umma_bf16(d_tmem, ad0 + (uint32_t)(s * 4 + 2 * k), bd0 + (uint32_t)(s * (B_TAP_BYTES >> 4) + 2 * k), idesc2, first);
+              umma_bf16(d_tmem, ad0 + (uint32_t)((HA_PLANE_BYTES >> 4) + s * 4 + 2 * k), bd0 + (uint32_t)(s * (B_TAP_BYTES >> 4) + 2 * k), idesc, 1u);
+            } else {
+              umma_bf16(d_tmem, ad0 + (uint32_t)(s * 4 + 2 * k), bd0 + (uint32_t)(s * (B_TAP_BYTES >> 4) + 2 * k), idesc, first);
+            }
+          }
         }
         umma_commit(empty0 + 8 * stage);
         umma_commit(tfull0 + 8 * acc);
@@ -398,11 +428,31 @@ __global__ void __launch_bounds__(H_THREADS, 1) stem_tc_h_kernel(const StemArgs 
       __nv_bfloat16 *o = a.y + (((size_t)n * a.Ho + ho) * a.Wo + wo) * N;
       mbar_wait(tfull0 + 8 * acc, accphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * N;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
 #pragma unroll
       for (int c = 0; c < N / 16; ++c) {
         uint32_t v[16];
         tmem_ld16(taddr + c * 16, v);
+        if constexpr (P == 2) {
+          uint32_t v2[16];
+          tmem_ld16(taddr + N + c * 16, v2);
+          tmem_ld_wait();
+          if (ok) {
+            uint32_t oh[8], ol[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float x0 = fmaf(__uint_as_float(v[2 * j]) + __uint_as_float(v2[2 * j]), a.acc_scale, s_bias[c * 16 + 2 * j]);
+              const float x1 = fmaf(__uint_as_float(v[2 * j + 1]) + __uint_as_float(v2[2 * j + 1]), a.acc_scale, s_bias[c * 16 + 2 * j + 1]);
+              split2(cpb::act_fn(x0, a.act), cpb::act_fn(x1, a.act), a.fmt, oh[j], ol[j]);
+            }
+            uint16_t *op_ = reinterpret_cast<uint16_t *>(o) + c * 16;
+            reinterpret_cast<uint4 *>(op_)[0] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+            reinterpret_cast<uint4 *>(op_)[1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
+            reinterpret_cast<uint4 *>(op_ + a.y_plane)[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+            reinterpret_cast<uint4 *>(op_ + a.y_plane)[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+          }
+          continue;
+        }
         tmem_ld_wait();
         if (ok) {
           uint4 o0, o1;
@@ -433,24 +483,24 @@ __global__ void __launch_bounds__(H_THREADS, 1) stem_tc_h_kernel(const StemArgs 
   }
 }
 
-template <int N>
+template <int N, int P>
 int launch_stem_h(const cpb200_op &op, cudaStream_t st) {
   StemArgs a;
+  a.fmt = op.act_dtype == CPB200_F16X2 ? 1u : 0u;
+  a.acc_scale = op.acc_scale != 0.f ? op.acc_scale : 1.f;
+  a.y_plane = (long long)op.B * op.Ho * op.Wo * N;
   a.x = static_cast<const float *>(op.src[0]); a.y = static_cast<__nv_bfloat16 *>(op.dst);
   a.wimg = static_cast<const uint4 *>(op.weight); a.bias = op.bias;
   a.B = op.B; a.H = op.H; a.W = op.W; a.Ho = op.Ho; a.Wo = op.Wo;
   a.tiles_h = (op.Ho + HT_H - 1) / HT_H; a.tiles_w = (op.Wo + HT_W - 1) / HT_W;
   a.total_tiles = op.B * a.tiles_h * a.tiles_w;
   a.act = op.flags & CPB_ACT_MASK;
-  const size_t smem = 1024 + (size_t)H_NSTAGE * HA_STAGE_BYTES + 7 * (size_t)N * 64;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CPB_CUDA(cudaFuncSetAttribute(stem_tc_h_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  const size_t smem = 1024 + (size_t)HStages<N, P>::value * P * HA_STAGE_BYTES + 7 * (size_t)P * N * 64;
+  static SmemAttrCache cache;
+  if (int rc = ensure_smem(stem_tc_h_kernel<N, P>, smem, cache)) return rc;
   const int sms = tc::num_sms();
   const int grid = a.total_tiles < sms ? a.total_tiles : sms;
-  stem_tc_h_kernel<N><<<grid, H_THREADS, smem, st>>>(a);
+  stem_tc_h_kernel<N, P><<<grid, H_THREADS, smem, st>>>(a);
   return cpb::check_launch("stem_tc_h_kernel");
 }
 
@@ -464,12 +514,10 @@ int launch_stem(const cpb200_op &op, cudaStream_t st) {
   a.tiles_h = (op.Ho + TH - 1) / TH; a.tiles_w = (op.Wo + TW - 1) / TW;
   a.total_tiles = op.B * a.tiles_h * a.tiles_w;
   a.act = op.flags & CPB_ACT_MASK;
+  a.fmt = 0; a.acc_scale = 1.f; a.y_plane = 0;
   const size_t smem = 1024 + (size_t)NSTAGE * A_STAGE_BYTES + (size_t)SLABS * N * 128 + (size_t)PGROUPS * 2 * CIN * PH * PP * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CPB_CUDA(cudaFuncSetAttribute(stem_tc_kernel<N, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  static SmemAttrCache cache;
+  if (int rc = ensure_smem(stem_tc_kernel<N, S>, smem, cache)) return rc;
   const int sms = tc::num_sms();
   const int grid = a.total_tiles < sms ? a.total_tiles : sms;
   stem_tc_kernel<N, S><<<grid, ST_THREADS, smem, st>>>(a);
@@ -481,16 +529,19 @@ int launch_stem(const cpb200_op &op, cudaStream_t st) {
 namespace cpb {
 
 bool stem_tc_eligible(const cpb200_op &op) {
-  return op.type == CPB200_OP_STEM && op.act_dtype == CPB200_BF16 && op.cin[0] == 3 && op.kh == 7 && op.kw == 7 &&
+  const bool split = op.act_dtype == CPB200_BF16X2 || op.act_dtype == CPB200_F16X2;
+  // split operands: the stride-1 kernel only (the stride-2 im2col stages do not fit twice; plan.py routes those through fp32)
+  return op.type == CPB200_OP_STEM && (op.act_dtype == CPB200_BF16 || (split && op.stride == 1)) && op.cin[0] == 3 && op.kh == 7 && op.kw == 7 &&
          op.pad_h == 3 && op.pad_w == 3 && (op.stride == 1 || op.stride == 2) && (op.cout == 16 || op.cout == 64) &&
          op.Ho == (op.H + 6 - 7) / op.stride + 1 && op.Wo == (op.W + 6 - 7) / op.stride + 1;
 }
 
 int stem_tc_run(const cpb200_op &op, cudaStream_t st) {
-  if (!stem_tc_eligible(op)) return fail(CPB200_ERR_ARG, "stem_tc: unsupported shape (needs 7x7, Cin 3, stride 1/2, cout 16/64, bf16)");
+  if (!stem_tc_eligible(op)) return fail(CPB200_ERR_ARG, "stem_tc: unsupported shape (needs 7x7, Cin 3, stride 1/2, cout 16/64; split precisions stride 1 only)");
+  const bool split = op.act_dtype != CPB200_BF16;
   // stride 1: vertical-fold kernel (weight image = 7 taps x N rows x 64 B); stride 2: full im2col rows (3 slabs x N x 128 B)
-  if (op.cout == 16 && op.stride == 1) return launch_stem_h<16>(op, st);
-  if (op.cout == 64 && op.stride == 1) return launch_stem_h<64>(op, st);
+  if (op.cout == 16 && op.stride == 1) return split ? launch_stem_h<16, 2>(op, st) : launch_stem_h<16, 1>(op, st);
+  if (op.cout == 64 && op.stride == 1) return split ? launch_stem_h<64, 2>(op, st) : launch_stem_h<64, 1>(op, st);
   if (op.cout == 16) return launch_stem<16, 2>(op, st);
   return launch_stem<64, 2>(op, st);
 }

@@ -18,6 +18,11 @@
 // issuer + TMEM owner, warps 2..5 = epilogue (tcgen05.ld -> +bias (+residual) -> ReLU -> bf16 ->
 // global).  Two to eight TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1;
 // a STAGES-deep smem ring with full/empty mbarriers feeds the tensor core.
+//
+// Split-operand precisions (P = 2, CPB200_BF16X2 / CPB200_F16X2, see tc_common.cuh): a stage is
+// [A_hi | A_lo | W_hi | W_lo]; per K step the issuer emits A_hi x [W_hi ; W_lo] as one N = 2*BN instruction when
+// 2*BN <= 256 (two adjacent accumulator halves, added in the epilogue) plus A_lo x W_hi, or three N = BN instructions
+// for BN = 256.  The DCN gather blends the four corners of BOTH planes in fp32 and re-splits the sample.
 #include "tc_common.cuh"
 #include <mutex>
 #include <cstdlib>
@@ -48,6 +53,12 @@ struct alignas(64) TcArgs {
   int H, W, om_pitch, dcn_prefetch;
   int Hd, Wd, sy, sx, oy, ox;     // strided output mapping (dense ConvTranspose2d parity sub-convs)
   int out_ch_off, out_ch_total;   // NCHW fp32 output: channel slice of dst
+  // split-operand mode (P = 2)
+  unsigned fmt;                   // 0 = bf16 planes, 1 = fp16 planes
+  float acc_scale;                // accumulator multiplier (inverse of the host's power-of-two weight scale)
+  long long dst_plane;            // elements between the hi and lo planes of dst / res
+  long long src_plane;            // DCN: elements between the planes of dcn_src
+  int wplane;                     // weight blocks (tap x K-slab) per plane
 };
 
 using namespace tc;
@@ -59,15 +70,17 @@ constexpr int DCN_GW = CPB_DCN_GW;
 constexpr int DCN_ROWS = 128 / DCN_GW;          // operand rows per gather warp
 constexpr int DCN_THREADS = (6 + DCN_GW) * 32;
 
-struct __align__(16) DcnPrm { int off[4]; uint32_t wt[4]; };   // element offsets, packed bf16x2 (w,w) corner weights
+struct __align__(16) DcnPrm { int off[4]; uint32_t wt[4]; };   // element offsets; corner weights: packed bf16x2 (w,w), or fp32 bits when P = 2
 
-template <int BN, bool DCN>
+template <int BN, bool DCN, int P>
 __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+  constexpr bool NCAT = (P == 2) && (2 * BN <= 256);       // hi*[hi;lo] as one N = 2*BN instruction
+  constexpr int ACC_COLS = NCAT ? 2 * BN : BN;             // TMEM columns per accumulator stage
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A | B)] then barriers
+  // carve: [stages x (A planes | B planes)] then barriers
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_bytes = TILE_M * a.BK * 2, b_bytes = BN * a.BK * 2;
-  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
+  const uint32_t stage_bytes = P * a_bytes + ((P * b_bytes + 1023u) & ~1023u);
   __shared__ __align__(8) uint64_t bars[2 * 8 + 16];
   __shared__ uint32_t s_tmem;
   __shared__ float s_bias[2][BN];
@@ -76,7 +89,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
   const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[24]);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t need_cols = (uint32_t)a.nacc * BN;
+  const uint32_t need_cols = (uint32_t)a.nacc * ACC_COLS;
   const uint32_t TMEM_COLS = need_cols <= 32 ? 32u : need_cols <= 64 ? 64u : need_cols <= 128 ? 128u : need_cols <= 256 ? 256u : 512u;
 
   if (warp == 0 && lane == 0) {
@@ -120,14 +133,18 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
           for (int s = 0; s < a.nsrc; ++s) {
             for (int c0 = 0; c0 < a.cin[s]; c0 += a.BK) {
               mbar_wait(empty0 + 8 * stage, phase ^ 1);
-              const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
+              const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + P * a_bytes;
               if (DCN) {
-                mbar_expect_tx(full0 + 8 * stage, b_bytes);
+                mbar_expect_tx(full0 + 8 * stage, P * b_bytes);
               } else {
-                mbar_expect_tx(full0 + 8 * stage, a_bytes + b_bytes);
-                tma_load_4d(sa, &a.amap[s], full0 + 8 * stage, c0, wi, hi, n);
+                mbar_expect_tx(full0 + 8 * stage, P * (a_bytes + b_bytes));
+#pragma unroll
+                for (int pl = 0; pl < P; ++pl) tma_load_4d(sa + pl * a_bytes, &a.amap[s], full0 + 8 * stage, c0, wi, hi, n + pl * a.B);
               }
-              tma_load_3d(sb, &a.bmap, full0 + 8 * stage, 0, nt * BN, tap * kblocks_per_tap + (cb + c0) / a.BK);
+#pragma unroll
+              for (int pl = 0; pl < P; ++pl)
+                tma_load_3d(sb + pl * b_bytes, &a.bmap, full0 + 8 * stage, 0, nt * BN,
+                            pl * a.wplane + tap * kblocks_per_tap + (cb + c0) / a.BK);
               if (++stage == a.stages) { stage = 0; phase ^= 1; }
             }
             cb += a.cin[s];
@@ -138,21 +155,37 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
     // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+    const uint32_t idesc = P == 1 ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24))
+                                  : idesc_m128(BN, a.fmt);
+    const uint32_t idesc2 = idesc_m128(NCAT ? 2 * BN : BN, a.fmt);
     int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t accphase = 0;
     const uint32_t row_bytes = a.BK * 2;
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(full0 + 8 * stage, phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + a_bytes;
+          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + P * a_bytes;
           const uint64_t ad = make_desc(sa, row_bytes, a.swizzle_bits), bd = make_desc(sb, row_bytes, a.swizzle_bits);
-          for (int k = 0; k < a.BK / 16; ++k)
-            umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          if constexpr (P == 1) {
+            for (int k = 0; k < a.BK / 16; ++k)
+              umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          } else {
+            const uint32_t aplane = a_bytes >> 4, bplane = b_bytes >> 4;      // descriptor start-address units
+            for (int k = 0; k < a.BK / 16; ++k) {
+              const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+              if constexpr (NCAT) {
+                umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc2, first);                 // A_hi x [W_hi ; W_lo]
+              } else {
+                umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, first);                  // A_hi x W_hi
+                umma_bf16(d_tmem, ad + 2 * k, bd + bplane + 2 * k, idesc, 1u);            // A_hi x W_lo
+              }
+              umma_bf16(d_tmem, ad + aplane + 2 * k, bd + 2 * k, idesc, 1u);              // A_lo x W_hi
+            }
+          }
           umma_commit(empty0 + 8 * stage);              // frees the smem slot when these MMAs retire
           if (kb == kblocks - 1) umma_commit(tfull0 + 8 * acc);
         }
@@ -162,15 +195,18 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
       if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
     }
   } else if (DCN && warp >= 6) {
-    // =============================== DCN gather producers (warps 6..13) ===============================
+    // =============================== DCN gather producers (warps 6..21) ===============================
     // A[row = pixel][k = channel] of tap t is  sigmoid(mask_t) * bilinear(x, p + tap_t + offset_t)
     // (dcn_v2_im2col_cuda.cu:25-54,125-195), rounded to bf16 and stored straight into the 128B-swizzled
     // K-major tile the UMMA descriptor reads (16-byte chunk j of row r lives at chunk j ^ (r & 7)).
-    // DCN_GW warps x DCN_ROWS rows (16 x 8; the 8 x 16 variant below is kept for reference).  Per tile each warp first
-    // turns the 27 offset/mask values of its pixels into
-    // (4 corner offsets, 4 packed corner weights) for all 9 taps (one round trip to global memory instead
-    // of one per tap); the per-stage work is then software-pipelined in two half batches of 8 corner loads:
-    // the loads of the next half are always in flight while the current half is blended.
+    // 16 gather warps x 8 rows (four warps per scheduler: the gather is latency-bound, more resident warps beat deeper
+    // per-thread pipelining; an 8 x 16 variant was 12 % slower).  Per tile each warp first turns the 27 offset/mask
+    // values of its pixels into (4 corner offsets, 4 corner weights) for all 9 taps (one round trip to global memory
+    // instead of one per tap); per stage every thread fetches 2 rows x 4 corners of one 16-byte chunk, and the loads
+    // of the NEXT unit of work are issued before this one's results are stored.
+    // P = 2 (split operands): corners come from both planes, are summed and blended in fp32 with fp32 weights
+    // (expf, not ex2.approx, for the mask), and the sample is re-split into the hi / lo A tiles; the unit of
+    // software pipelining is one row (8 loads in flight per thread, as for P = 1).
     const int gw = warp - 6;                               // rows [DCN_ROWS*gw, DCN_ROWS*(gw+1))
     int stage = 0; uint32_t phase = 0;
     const int Cin = a.cin[0];
@@ -178,53 +214,55 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
     const int nk = 9 * slabs;
     const int chunk = lane & 7, rsub = lane >> 3;
     const __nv_bfloat16 *srcc = a.dcn_src + chunk * 8;
-    if constexpr (DCN_ROWS == 8) {
-      // ---- 16 gather warps x 8 rows: four warps per scheduler instead of two, 8 corner loads per thread and stage,
-      //      issued for the NEXT stage right after this stage's rows are stored ----
-      const int px = lane & 7, tg = lane >> 3;               // pixel of the warp, tap group {0,1,2} {3,4} {5,6} {7,8}
-      const int tap0 = tg == 0 ? 0 : 1 + 2 * tg, ntap = tg == 0 ? 3 : 2;
-      for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-        int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
-        {
-          const int rp = gw * 8 + px;
-          const int ho = h0 + rp / a.TW, wo = w0 + rp % a.TW;
-          const bool okp = ho < a.Ho && wo < a.Wo;
-          const float *om = a.dcn_om + (((size_t)n * a.H + ho) * a.W + wo) * a.om_pitch;
-          float oh[3], ow[3], ml[3];
+    static_assert(DCN_ROWS == 8, "gather layout: 16 warps x 8 rows");
+    const int px = lane & 7, tg = lane >> 3;               // pixel of the warp, tap group {0,1,2} {3,4} {5,6} {7,8}
+    const int tap0 = tg == 0 ? 0 : 1 + 2 * tg, ntap = tg == 0 ? 3 : 2;
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+      int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
+      {
+        const int rp = gw * 8 + px;
+        const int ho = h0 + rp / a.TW, wo = w0 + rp % a.TW;
+        const bool okp = ho < a.Ho && wo < a.Wo;
+        const float *om = a.dcn_om + (((size_t)n * a.H + ho) * a.W + wo) * a.om_pitch;
+        float oh[3], ow[3], ml[3];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const int tap = tap0 + i;
-            const bool ld = okp && i < ntap;
-            oh[i] = ld ? __ldg(om + 2 * tap) : 0.f; ow[i] = ld ? __ldg(om + 2 * tap + 1) : 0.f; ml[i] = ld ? __ldg(om + 18 + tap) : 0.f;
-          }
-          __syncwarp();                                      // previous tile's readers are done with s_prm
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            if (i < ntap) {
-              const int tap = tap0 + i;
-              DcnPrm pr;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) { pr.off[c] = 0; pr.wt[c] = 0u; }
-              if (okp) {
-                const float mk = 1.0f / (1.0f + __expf(-ml[i]));
-                const float h_im = (float)(ho - 1 + tap / 3) + oh[i], w_im = (float)(wo - 1 + tap % 3) + ow[i];
-                if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {
-                  const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-                  const int h_high = h_low + 1, w_high = w_low + 1;
-                  const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
-                  const int rowb = n * a.H;
-                  auto pk = [](float w) { __nv_bfloat162 b = __float2bfloat162_rn(w); return *reinterpret_cast<uint32_t *>(&b); };
-                  if (h_low >= 0 && w_low >= 0) { pr.off[0] = ((rowb + h_low) * a.W + w_low) * Cin; pr.wt[0] = pk(hh * hw * mk); }
-                  if (h_low >= 0 && w_high <= a.W - 1) { pr.off[1] = ((rowb + h_low) * a.W + w_high) * Cin; pr.wt[1] = pk(hh * lw * mk); }
-                  if (h_high <= a.H - 1 && w_low >= 0) { pr.off[2] = ((rowb + h_high) * a.W + w_low) * Cin; pr.wt[2] = pk(lh * hw * mk); }
-                  if (h_high <= a.H - 1 && w_high <= a.W - 1) { pr.off[3] = ((rowb + h_high) * a.W + w_high) * Cin; pr.wt[3] = pk(lh * lw * mk); }
-                }
-              }
-              s_prm[gw][tap][px] = pr;
-            }
-          }
-          __syncwarp();
+        for (int i = 0; i < 3; ++i) {
+          const int tap = tap0 + i;
+          const bool ld = okp && i < ntap;
+          oh[i] = ld ? __ldg(om + 2 * tap) : 0.f; ow[i] = ld ? __ldg(om + 2 * tap + 1) : 0.f; ml[i] = ld ? __ldg(om + 18 + tap) : 0.f;
         }
+        __syncwarp();                                      // previous tile's readers are done with s_prm
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if (i < ntap) {
+            const int tap = tap0 + i;
+            DcnPrm pr;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { pr.off[c] = 0; pr.wt[c] = 0u; }
+            if (okp) {
+              const float mk = P == 2 ? 1.0f / (1.0f + expf(-ml[i])) : 1.0f / (1.0f + __expf(-ml[i]));
+              const float h_im = (float)(ho - 1 + tap / 3) + oh[i], w_im = (float)(wo - 1 + tap % 3) + ow[i];
+              if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {
+                const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
+                const int h_high = h_low + 1, w_high = w_low + 1;
+                const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+                const int rowb = n * a.H;
+                auto pk = [](float w) {
+                  if constexpr (P == 2) return __float_as_uint(w);
+                  __nv_bfloat162 b = __float2bfloat162_rn(w); return *reinterpret_cast<uint32_t *>(&b);
+                };
+                if (h_low >= 0 && w_low >= 0) { pr.off[0] = ((rowb + h_low) * a.W + w_low) * Cin; pr.wt[0] = pk(hh * hw * mk); }
+                if (h_low >= 0 && w_high <= a.W - 1) { pr.off[1] = ((rowb + h_low) * a.W + w_high) * Cin; pr.wt[1] = pk(hh * lw * mk); }
+                if (h_high <= a.H - 1 && w_low >= 0) { pr.off[2] = ((rowb + h_high) * a.W + w_low) * Cin; pr.wt[2] = pk(lh * hw * mk); }
+                if (h_high <= a.H - 1 && w_high <= a.W - 1) { pr.off[3] = ((rowb + h_high) * a.W + w_high) * Cin; pr.wt[3] = pk(lh * lw * mk); }
+              }
+            }
+            s_prm[gw][tap][px] = pr;
+          }
+        }
+        __syncwarp();
+      }
+      if constexpr (P == 1) {
         uint4 v[2][4];
         uint32_t w[2][4];
         auto issue = [&](int tap, int c0) {
@@ -265,99 +303,56 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
           mbar_arrive(full0 + 8 * stage);
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
-      }
-    } else {
-    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-        int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
-        {   // ---- sampling parameters of this warp's 16 pixels, all 9 taps ----
-          const int rp = gw * 16 + (lane & 15);
-          const int ho = h0 + rp / a.TW, wo = w0 + rp % a.TW;
-          const bool okp = ho < a.Ho && wo < a.Wo;
-          const float *om = a.dcn_om + (((size_t)n * a.H + ho) * a.W + wo) * a.om_pitch;
-          const int tap0 = (lane < 16) ? 0 : 5, ntap = (lane < 16) ? 5 : 4;
-          float oh[5], ow[5], ml[5];
+      } else {
+        uint4 vh[4], vl[4];
+        float wq[4];
+        const __nv_bfloat16 *srcl = srcc + a.src_plane;      // lo plane (16-bit elements either format)
+        auto issue = [&](int tap, int c0, int i) {
+          const DcnPrm q = s_prm[gw][tap][i * 4 + rsub];
 #pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            const int tap = tap0 + i;
-            const bool ld = okp && i < ntap;
-            oh[i] = ld ? __ldg(om + 2 * tap) : 0.f; ow[i] = ld ? __ldg(om + 2 * tap + 1) : 0.f; ml[i] = ld ? __ldg(om + 18 + tap) : 0.f;
-          }
-          __syncwarp();                                      // previous tile's readers are done with s_prm
-#pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            if (i < ntap) {
-              const int tap = tap0 + i;
-              DcnPrm pr;
-#pragma unroll
-              for (int c = 0; c < 4; ++c) { pr.off[c] = 0; pr.wt[c] = 0u; }
-              if (okp) {
-                const float mk = 1.0f / (1.0f + __expf(-ml[i]));
-                const float h_im = (float)(ho - 1 + tap / 3) + oh[i], w_im = (float)(wo - 1 + tap % 3) + ow[i];
-                if (h_im > -1.f && w_im > -1.f && h_im < (float)a.H && w_im < (float)a.W) {
-                  const int h_low = (int)floorf(h_im), w_low = (int)floorf(w_im);
-                  const int h_high = h_low + 1, w_high = w_low + 1;
-                  const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
-                  const int rowb = n * a.H;
-                  auto pk = [](float w) { __nv_bfloat162 b = __float2bfloat162_rn(w); return *reinterpret_cast<uint32_t *>(&b); };
-                  if (h_low >= 0 && w_low >= 0) { pr.off[0] = ((rowb + h_low) * a.W + w_low) * Cin; pr.wt[0] = pk(hh * hw * mk); }
-                  if (h_low >= 0 && w_high <= a.W - 1) { pr.off[1] = ((rowb + h_low) * a.W + w_high) * Cin; pr.wt[1] = pk(hh * lw * mk); }
-                  if (h_high <= a.H - 1 && w_low >= 0) { pr.off[2] = ((rowb + h_high) * a.W + w_low) * Cin; pr.wt[2] = pk(lh * hw * mk); }
-                  if (h_high <= a.H - 1 && w_high <= a.W - 1) { pr.off[3] = ((rowb + h_high) * a.W + w_high) * Cin; pr.wt[3] = pk(lh * lw * mk); }
-                }
-              }
-              s_prm[gw][tap][lane & 15] = pr;
-            }
-          }
-          __syncwarp();
-        }
-        uint4 vA[2][4], vB[2][4];
-        uint32_t wA[2][4], wB[2][4];
-        // (tap, channel offset) of a stage are tracked incrementally — no integer division in the hot loop
-        auto issue = [&](int tap, int c0, int half, uint4 (&v)[2][4], uint32_t (&w)[2][4]) {
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const DcnPrm q = s_prm[gw][tap][(half * 2 + i) * 4 + rsub];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {       // invalid corners: weight 0, offset 0 (a safe address)
-              v[i][c] = __ldg(reinterpret_cast<const uint4 *>(srcc + (size_t)(unsigned)q.off[c] + c0));
-              w[i][c] = q.wt[c];
-            }
+          for (int c = 0; c < 4; ++c) {         // invalid corners: weight 0, offset 0 (a safe address)
+            vh[c] = __ldg(reinterpret_cast<const uint4 *>(srcc + (size_t)(unsigned)q.off[c] + c0));
+            vl[c] = __ldg(reinterpret_cast<const uint4 *>(srcl + (size_t)(unsigned)q.off[c] + c0));
+            wq[c] = __uint_as_float(q.wt[c]);
           }
         };
-        auto blend_store = [&](uint32_t sa, int half, const uint4 (&v)[2][4], const uint32_t (&w)[2][4]) {
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            __nv_bfloat162 acc2[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const __nv_bfloat162 w2 = *reinterpret_cast<const __nv_bfloat162 *>(&w[i][c]);
-              const __nv_bfloat162 *vv = reinterpret_cast<const __nv_bfloat162 *>(&v[i][c]);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) acc2[j] = (c == 0) ? __hmul2(w2, vv[j]) : __hfma2(w2, vv[j], acc2[j]);
-            }
-            const uint4 o = *reinterpret_cast<const uint4 *>(acc2);
-            const int row = gw * 16 + (half * 2 + i) * 4 + rsub;
-            const uint32_t dst = sa + row * 128 + ((chunk ^ (row & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
-          }
-        };
-        int tap_c = 0, c0_c = 0;            // current stage
-        int tap_n = 0, c0_n = 64;           // next stage
-        if (c0_n >= Cin) { c0_n = 0; tap_n = 1; }
-        issue(tap_c, c0_c, 0, vA, wA);
+        int tap_c = 0, c0_c = 0;                             // (tap, channel offset) of the current stage
+        issue(0, 0, 0);
         for (int k = 0; k < nk; ++k) {
-          issue(tap_c, c0_c, 1, vB, wB);
+          int tap_n = tap_c, c0_n = c0_c + 64;
+          if (c0_n >= Cin) { c0_n = 0; ++tap_n; }
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_base + stage * stage_bytes;
-          blend_store(sa, 0, vA, wA);
-          if (k + 1 < nk) issue(tap_n, c0_n, 0, vA, wA);
-          blend_store(sa, 1, vB, wB);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t hw_[4] = {vh[c].x, vh[c].y, vh[c].z, vh[c].w};
+              const uint32_t lw_[4] = {vl[c].x, vl[c].y, vl[c].z, vl[c].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 x = join2(hw_[j], lw_[j], a.fmt);
+                f[2 * j] = fmaf(wq[c], x.x, f[2 * j]); f[2 * j + 1] = fmaf(wq[c], x.y, f[2 * j + 1]);
+              }
+            }
+            // the registers are free again: the next unit's corners fly while this one is split and stored
+            if (i == 0) issue(tap_c, c0_c, 1);
+            else if (k + 1 < nk) issue(tap_n, c0_n, 0);
+            uint32_t oh[4], ol[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split2(f[2 * j], f[2 * j + 1], a.fmt, oh[j], ol[j]);
+            const int row = gw * 8 + i * 4 + rsub;
+            const uint32_t dst = sa + row * 128 + ((chunk ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(oh[0]), "r"(oh[1]), "r"(oh[2]), "r"(oh[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + a_bytes), "r"(ol[0]), "r"(ol[1]), "r"(ol[2]), "r"(ol[3]) : "memory");
+          }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           mbar_arrive(full0 + 8 * stage);
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
           tap_c = tap_n; c0_c = c0_n;
-          c0_n += 64;
-          if (c0_n >= Cin) { c0_n = 0; ++tap_n; }
         }
       }
     }
@@ -381,17 +376,30 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
       const int ho = h0 + th, wo = w0 + tw;
       const bool ok = ho < a.Ho && wo < a.Wo;
       const size_t pix = ((size_t)n * a.Hd + (ho * a.sy + a.oy)) * a.Wd + (wo * a.sx + a.ox);
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
 #pragma unroll 1
       for (int c = 0; c < BN / 16; ++c) {
         uint32_t v[16];
         tmem_ld16(taddr + c * 16, v);
-        tmem_ld_wait();
+        if constexpr (NCAT) {
+          uint32_t v2[16];
+          tmem_ld16(taddr + BN + c * 16, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          tmem_ld_wait();
+        }
         const int nb = n0 + c * 16;
         if (ok && nb < a.cout) {
           float f[16];
+          if constexpr (P == 2) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[acc & 1][c * 16 + j];
+            for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), a.acc_scale, s_bias[acc & 1][c * 16 + j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[acc & 1][c * 16 + j];
+          }
           if (out_nchw) {
             // head outputs: lanes are consecutive pixels of a tile row -> coalesced fp32 stores per channel
             float *o = static_cast<float *>(a.dst) +
@@ -399,7 +407,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
             const size_t plane = (size_t)a.Hd * a.Wd;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (nb + j < a.cout) o[j * plane] = cpb::act_out<__nv_bfloat16>(f[j], act);
+              if (nb + j < a.cout) o[j * plane] = P == 2 ? cpb::act_fn(f[j], act) : cpb::act_out<__nv_bfloat16>(f[j], act);
           } else if (out_f32) {
             float *o = static_cast<float *>(a.dst) + pix * a.cout_store + nb;
             if (nb + 16 <= a.cout && (a.cout_store & 3) == 0) {
@@ -414,6 +422,29 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
               for (int j = 0; j < 16; ++j)
                 if (nb + j < a.cout) o[j] = cpb::act_out<__nv_bfloat16>(f[j], act);
             }
+          } else if constexpr (P == 2) {
+            // split output: hi plane at dst, lo plane dst_plane elements later; the residual is read the same way
+            uint16_t *o = static_cast<uint16_t *>(a.dst) + pix * a.cout_store + nb;
+            if (a.res) {
+              const uint16_t *rh = static_cast<const uint16_t *>(a.res) + pix * a.cout_store + nb;
+              const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(rh)), h1 = __ldg(reinterpret_cast<const uint4 *>(rh) + 1);
+              const uint4 l0 = __ldg(reinterpret_cast<const uint4 *>(rh + a.dst_plane)), l1 = __ldg(reinterpret_cast<const uint4 *>(rh + a.dst_plane) + 1);
+              const uint32_t hw_[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+              const uint32_t lw_[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 x = join2(hw_[j], lw_[j], a.fmt);
+                f[2 * j] += x.x; f[2 * j + 1] += x.y;
+              }
+            }
+            uint32_t oh[8], ol[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              split2(cpb::act_fn(f[2 * j], act), cpb::act_fn(f[2 * j + 1], act), a.fmt, oh[j], ol[j]);
+            reinterpret_cast<uint4 *>(o)[0] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+            reinterpret_cast<uint4 *>(o)[1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
+            reinterpret_cast<uint4 *>(o + a.dst_plane)[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+            reinterpret_cast<uint4 *>(o + a.dst_plane)[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
           } else {
             __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(a.dst) + pix * a.cout_store + nb;
             if (a.res) {
@@ -461,7 +492,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
 // ------------------------------------------------------------------------------- host side
 struct TcOp {
   TcArgs args;
-  int BN;
+  int BN, P;
   bool dcn;
   void *c3 = nullptr;      // halo-reuse 3x3 kernel handle (net_tc3.cu) when that path was chosen
   int grid;
@@ -469,14 +500,11 @@ struct TcOp {
 };
 
 
-template <int BN, bool DCN>
-int launch_tc(const TcOp &t, cudaStream_t st) {
-  static size_t attr_smem = 0;
-  if (t.smem > attr_smem) {
-    CPB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, DCN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
-    attr_smem = t.smem;
-  }
-  conv_tc_kernel<BN, DCN><<<t.grid, DCN ? DCN_THREADS : TC_THREADS, t.smem, st>>>(t.args);
+template <int BN, bool DCN, int P>
+int launch_tc(const TcOp &t, const TcArgs &args, cudaStream_t st) {
+  static SmemAttrCache cache;
+  if (int rc = ensure_smem(conv_tc_kernel<BN, DCN, P>, t.smem, cache)) return rc;
+  conv_tc_kernel<BN, DCN, P><<<t.grid, DCN ? DCN_THREADS : TC_THREADS, t.smem, st>>>(args);
   return cpb::check_launch(DCN ? "dcn_tc_kernel" : "conv_tc_kernel");
 }
 
@@ -495,14 +523,21 @@ EncodeTiledFn get_encode() {
   });
   return fn;
 }
+int cur_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  return dev;
+}
 int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static std::atomic<int> n[MAX_DEVICES];          // zero-initialised; per device (a process may drive several GPUs)
+  const int dev = cur_device();
+  if (dev < 0 || dev >= MAX_DEVICES) return 148;
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (!v) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
 }
 }  // namespace tc
 
@@ -511,7 +546,7 @@ namespace cpb {
 bool c3_eligible(const cpb200_op &op);
 void *c3_prepare(const cpb200_op &op, int *rc);
 void c3_release(void *h);
-int c3_run(const void *h, cudaStream_t st);
+int c3_run(const void *h, const cpb200_op &op, cudaStream_t st);
 
 static bool halo_enabled() {
   const char *e = getenv("CPB200_TC_HALO");
@@ -533,7 +568,8 @@ int tc_prepare_op(cpb200_op &op) {
   if (dcn && (op.kh != 3 || op.kw != 3 || op.stride != 1 || op.pad_h != 1 || op.pad_w != 1 || op.nsrc != 1 ||
               op.cin[0] % 64 || !op.aux || op.H != op.Ho || op.W != op.Wo))
     return fail(CPB200_ERR_ARG, "tc: DCN needs 3x3/s1/p1, one input with C %% 64 == 0 and the offset/mask tensor");
-  if (op.act_dtype != CPB200_BF16) return fail(CPB200_ERR_ARG, "tc: bf16 activations required");
+  if (op.act_dtype != CPB200_BF16 && op.act_dtype != CPB200_BF16X2 && op.act_dtype != CPB200_F16X2)
+    return fail(CPB200_ERR_ARG, "tc: bf16 or split (bf16x2 / fp16x2) activations required");
   if (op.stride < 1 || op.stride > 2) return fail(CPB200_ERR_ARG, "tc: stride %d", op.stride);
   if (op.Wo < 8 || op.Ho < 1) return fail(CPB200_ERR_ARG, "tc: output too small");
   EncodeTiledFn enc = get_encode();
@@ -542,6 +578,10 @@ int tc_prepare_op(cpb200_op &op) {
   TcOp *t = new TcOp();
   TcArgs &a = t->args;
   memset(&a, 0, sizeof(a));
+  const int P = op.act_dtype == CPB200_BF16 ? 1 : 2;
+  t->P = P;
+  a.fmt = op.act_dtype == CPB200_F16X2 ? 1u : 0u;
+  a.acc_scale = op.acc_scale != 0.f ? op.acc_scale : 1.f;
   int cin_total = 0, bk = 64;
   for (int s = 0; s < op.nsrc; ++s) {
     const int c = op.cin[s];
@@ -558,6 +598,7 @@ int tc_prepare_op(cpb200_op &op) {
   a.tiles_h = (op.Ho + a.TH - 1) / a.TH; a.tiles_w = (op.Wo + a.TW - 1) / a.TW;
   int BN = 16;
   while (BN < op.cout && BN < 256) BN <<= 1;
+  if (dcn && P == 2 && BN > 128) BN = 128;     // split DCN: two stages of [A_hi|A_lo|W_hi|W_lo] must fit beside 39 KB of sampling parameters
   t->BN = BN; t->dcn = dcn;
   a.dcn_src = static_cast<const __nv_bfloat16 *>(op.src[0]); a.dcn_om = static_cast<const float *>(op.aux);
   a.H = op.H; a.W = op.W; a.om_pitch = op.aux_pitch > 0 ? op.aux_pitch : 27;
@@ -565,12 +606,16 @@ int tc_prepare_op(cpb200_op &op) {
   a.Hd = op.Hd; a.Wd = op.Wd; a.sy = op.out_sy; a.sx = op.out_sx; a.oy = op.out_oy; a.ox = op.out_ox;
   a.n_tiles = (op.cout + BN - 1) / BN;
   a.cout = op.cout; a.cout_store = op.cout;
-  if (!(op.flags & (CPB200_FLAG_OUT_F32 | CPB200_FLAG_OUT_NCHW_F32)) && (op.cout % 16)) { delete t; return fail(CPB200_ERR_ARG, "tc: bf16 output needs cout %% 16 == 0"); }
+  if (!(op.flags & (CPB200_FLAG_OUT_F32 | CPB200_FLAG_OUT_NCHW_F32)) && (op.cout % 16)) { delete t; return fail(CPB200_ERR_ARG, "tc: 16-bit output needs cout %% 16 == 0"); }
   a.out_ch_off = op.out_ch_off; a.out_ch_total = op.out_ch_total;
   a.total_tiles = op.B * a.tiles_h * a.tiles_w * a.n_tiles;
-  a.nacc = 512 / BN > 8 ? 8 : 512 / BN;      // TMEM accumulator stages
+  const int acc_cols = (P == 2 && 2 * BN <= 256) ? 2 * BN : BN;
+  a.nacc = 512 / acc_cols > 8 ? 8 : 512 / acc_cols;      // TMEM accumulator stages
   a.dst = op.dst; a.res = op.res; a.bias = op.bias; a.flags = op.flags;
-  const size_t a_bytes = (size_t)TILE_M * bk * 2, b_bytes = ((size_t)BN * bk * 2 + 1023) / 1024 * 1024;
+  a.dst_plane = (long long)op.B * op.Hd * op.Wd * op.cout;
+  a.src_plane = (long long)op.B * op.H * op.W * op.cin[0];
+  a.wplane = op.kh * op.kw * (cin_total / bk);
+  const size_t a_bytes = (size_t)P * TILE_M * bk * 2, b_bytes = ((size_t)P * BN * bk * 2 + 1023) / 1024 * 1024;
   const size_t budget = dcn ? 176 * 1024 : 200 * 1024;     // the DCN variant keeps 39 KB of sampling parameters in static smem
   int stages = (int)(budget / (a_bytes + b_bytes));
   if (stages > 8) stages = 8;
@@ -579,26 +624,28 @@ int tc_prepare_op(cpb200_op &op) {
   a.stages = stages;
   t->smem = stages * (a_bytes + b_bytes) + 1024;
   t->grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
+  const CUtensorMapDataType dt = a.fmt ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 
   for (int s = 0; s < op.nsrc && !dcn; ++s) {
-    // a channel slice of a wider tensor: `pitch` elements between pixels, op.src[s] already points at the slice
+    // a channel slice of a wider tensor: `pitch` elements between pixels, op.src[s] already points at the slice.
+    // Split activations: the lo plane follows the hi plane of the (parent) tensor, i.e. a batch of 2B images.
     const cuuint64_t pitch = op.src_pitch[s] > 0 ? (cuuint64_t)op.src_pitch[s] : (cuuint64_t)op.cin[s];
-    const cuuint64_t dims[4] = {(cuuint64_t)op.cin[s], (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.B};
+    const cuuint64_t dims[4] = {(cuuint64_t)op.cin[s], (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.B * P};
     const cuuint64_t strides[3] = {pitch * 2, (cuuint64_t)op.W * pitch * 2, (cuuint64_t)op.H * op.W * pitch * 2};
     const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(a.TW * op.stride), (cuuint32_t)(a.TH * op.stride), 1};
     const cuuint32_t estr[4] = {1, (cuuint32_t)op.stride, (cuuint32_t)op.stride, 1};
-    CUresult r = enc(&a.amap[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(op.src[s]), dims, strides, box, estr,
+    CUresult r = enc(&a.amap[s], dt, 4, const_cast<void *>(op.src[s]), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete t; return fail(CPB200_ERR_CUDA, "tc: cuTensorMapEncodeTiled(A[%d]) failed: %d", s, (int)r); }
   }
   {
-    // weights are packed slab-major [tap][K-slab][cout_pad][bk] (plan.py::_pack_conv_tc): a box is one dense run
+    // weights are packed slab-major [plane][tap][K-slab][cout_pad][bk] (plan.py::_pack_conv_tc): a box is one dense run
     const int cout_pad = (op.cout + 15) / 16 * 16;
-    const cuuint64_t dims[3] = {(cuuint64_t)bk, (cuuint64_t)cout_pad, (cuuint64_t)(op.kh * op.kw) * (cuuint64_t)(cin_total / bk)};
+    const cuuint64_t dims[3] = {(cuuint64_t)bk, (cuuint64_t)cout_pad, (cuuint64_t)(op.kh * op.kw) * (cuuint64_t)(cin_total / bk) * P};
     const cuuint64_t strides[2] = {(cuuint64_t)bk * 2, (cuuint64_t)cout_pad * bk * 2};
     const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)BN, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&a.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(op.weight), dims, strides, box, estr,
+    CUresult r = enc(&a.bmap, dt, 3, const_cast<void *>(op.weight), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete t; return fail(CPB200_ERR_CUDA, "tc: cuTensorMapEncodeTiled(B) failed: %d", (int)r); }
   }
@@ -617,23 +664,24 @@ int tc_release_op(cpb200_op &op) {
 int tc_run_op(const cpb200_op &op, cudaStream_t st) {
   const TcOp *t = static_cast<const TcOp *>(op.tc);
   if (!t) return fail(CPB200_ERR_STATE, "tc: op not prepared");
-  if (t->c3) return c3_run(t->c3, st);
+  if (t->c3) return c3_run(t->c3, op, st);
+  // dst / res / bias / the DCN offset tensor are taken from the live op: the model binds new output tensors every
+  // forward (include/centerpose_b200.h); input activations and weights were baked into the tensor maps at prepare.
+  TcArgs args = t->args;
+  args.dst = op.dst; args.res = op.res; args.bias = op.bias;
+  args.dcn_om = static_cast<const float *>(op.aux);
+#define TC_CASE(N, D)                                                                                  \
+  case N: return t->P == 2 ? launch_tc<N, D, 2>(*t, args, st) : launch_tc<N, D, 1>(*t, args, st);
   if (t->dcn) {
     switch (t->BN) {
-      case 32: return launch_tc<32, true>(*t, st);
-      case 64: return launch_tc<64, true>(*t, st);
-      case 128: return launch_tc<128, true>(*t, st);
-      case 256: return launch_tc<256, true>(*t, st);
+      TC_CASE(32, true) TC_CASE(64, true) TC_CASE(128, true) TC_CASE(256, true)
     }
     return fail(CPB200_ERR_STATE, "tc: DCN supports cout 32/64/128/256 tiles only");
   }
   switch (t->BN) {
-    case 16: return launch_tc<16, false>(*t, st);
-    case 32: return launch_tc<32, false>(*t, st);
-    case 64: return launch_tc<64, false>(*t, st);
-    case 128: return launch_tc<128, false>(*t, st);
-    case 256: return launch_tc<256, false>(*t, st);
+    TC_CASE(16, false) TC_CASE(32, false) TC_CASE(64, false) TC_CASE(128, false) TC_CASE(256, false)
   }
+#undef TC_CASE
   return fail(CPB200_ERR_STATE, "tc: bad BN");
 }
 

@@ -24,6 +24,13 @@
 // extra bookkeeping in the single issuing lane made that baseline slower than this straight-line version
 // (64->64: 59 us here, 67 us grouped), i.e. the issuer is bound by instructions issued, not by the
 // accumulator dependency chain.
+//
+// Split-operand precisions (P = 2, act_dtype CPB200_BF16X2 / CPB200_F16X2; tc_common.cuh): activations and weights arrive
+// as hi / lo 16-bit planes.  The halo ring is plane-granular (the planes of a slab are two consecutive stages, TMA batch
+// coordinate n and n + B); a weight stage holds the hi tile immediately followed by the lo tile, so for 2*BN <= 256 the
+// products A_hi*[W_hi ; W_lo] are ONE tcgen05.mma of N = 2*BN into two adjacent accumulator halves (the issuing thread
+// is the bottleneck for N <= 128, ~90 cycles per instruction whatever N) and A_lo*W_hi a second one into the first
+// half; the epilogue adds the halves, scales by acc_scale, and writes hi / lo planes.  BN = 256: three N = 256 MMAs.
 #include "tc_common.cuh"
 #include <cstdlib>
 
@@ -47,6 +54,11 @@ struct alignas(64) C3Args {
   const void *res;
   const float *bias;
   unsigned flags, swizzle_bits;
+  // split-operand mode (P = 2)
+  unsigned fmt;                // 0 = bf16 planes, 1 = fp16 planes
+  float acc_scale;             // accumulator multiplier (inverse of the host's power-of-two weight scale)
+  long long dst_plane;         // elements between the hi and lo planes of dst / res
+  unsigned b_tile_bytes;       // bytes of one weight tile (BN x BK x 2); a P = 2 weight stage is [hi tile | lo tile]
 };
 
 __device__ __forceinline__ uint64_t desc_sbo(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
@@ -59,8 +71,10 @@ __device__ __forceinline__ uint64_t desc_sbo(uint32_t saddr, uint32_t sbo_bytes,
   return d;
 }
 
-template <int BN>
+template <int BN, int P>
 __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ C3Args a) {
+  constexpr bool NCAT = (P == 2) && (2 * BN <= 256);       // hi*[hi;lo] as one N = 2*BN instruction
+  constexpr int ACC_COLS = NCAT ? 2 * BN : BN;             // TMEM columns per accumulator stage
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base, b_base = smem_base + a.na * a.a_stage_bytes;
@@ -72,7 +86,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
   const uint32_t ball = smem_u32(&bars[2 * MAX_NA + 2 * MAX_NB]);
   const uint32_t tfull0 = ball + 8, tempty0 = ball + 8 + 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t need_cols = (uint32_t)a.nacc * BN;
+  const uint32_t need_cols = (uint32_t)a.nacc * ACC_COLS;
   const uint32_t TMEM_COLS = need_cols <= 32 ? 32u : need_cols <= 64 ? 64u : need_cols <= 128 ? 128u : need_cols <= 256 ? 256u : 512u;
 
   if (warp == 0 && lane == 0) {
@@ -107,21 +121,28 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
         int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
         for (int sl = 0; sl < a.slabs; ++sl) {
-          mbar_wait(aempty0 + 8 * sa, pha ^ 1);
-          mbar_expect_tx(afull0 + 8 * sa, a.a_tx_bytes);
-          tma_load_4d(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, w0 - (a.kw >> 1), h0 - (a.kh >> 1), n);
-          if (++sa == a.na) { sa = 0; pha ^= 1; }
+#pragma unroll
+          for (int pl = 0; pl < P; ++pl) {                 // plane-granular stages: hi then lo (batch coordinate n + B)
+            mbar_wait(aempty0 + 8 * sa, pha ^ 1);
+            mbar_expect_tx(afull0 + 8 * sa, a.a_tx_bytes);
+            tma_load_4d(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, w0 - (a.kw >> 1), h0 - (a.kh >> 1), n + pl * a.B);
+            if (++sa == a.na) { sa = 0; pha ^= 1; }
+          }
         }
       }
     }
   } else if (warp == 6) {
     // =============================== weight producer ===============================
     if (elect_one()) {
+      const int wplane = a.taps * a.slabs;                 // weight blocks per plane
       if (a.b_resident) {
-        mbar_expect_tx(ball, (uint32_t)a.taps * a.slabs * a.b_tx_bytes);
+        mbar_expect_tx(ball, (uint32_t)P * a.taps * a.slabs * a.b_tx_bytes);
         for (int sl = 0; sl < a.slabs; ++sl)
           for (int tap = 0; tap < a.taps; ++tap)
-            tma_load_3d(b_base + (sl * a.taps + tap) * a.b_stage_bytes, &a.bmap, ball, 0, 0, tap * a.slabs + sl);
+#pragma unroll
+            for (int pl = 0; pl < P; ++pl)
+              tma_load_3d(b_base + (sl * a.taps + tap) * a.b_stage_bytes + pl * a.b_tile_bytes, &a.bmap, ball, 0, 0,
+                          pl * wplane + tap * a.slabs + sl);
       } else {
         int sb = 0; uint32_t phb = 0;
         for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
@@ -129,8 +150,11 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
           for (int sl = 0; sl < a.slabs; ++sl)
             for (int tap = 0; tap < a.taps; ++tap) {
               mbar_wait(bempty0 + 8 * sb, phb ^ 1);
-              mbar_expect_tx(bfull0 + 8 * sb, a.b_tx_bytes);
-              tma_load_3d(b_base + sb * a.b_stage_bytes, &a.bmap, bfull0 + 8 * sb, 0, nt * BN, tap * a.slabs + sl);
+              mbar_expect_tx(bfull0 + 8 * sb, P * a.b_tx_bytes);
+#pragma unroll
+              for (int pl = 0; pl < P; ++pl)
+                tma_load_3d(b_base + sb * a.b_stage_bytes + pl * a.b_tile_bytes, &a.bmap, bfull0 + 8 * sb, 0, nt * BN,
+                            pl * wplane + tap * a.slabs + sl);
               if (++sb == a.nb) { sb = 0; phb ^= 1; }
             }
         }
@@ -138,67 +162,146 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // P = 1: idesc = bf16 x bf16, N = BN.  P = 2: idescN (N = BN) and idesc2 (N = 2*BN, NCAT only), format from a.fmt.
+    const uint32_t idesc = P == 1 ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
+                                  : idesc_m128(BN, a.fmt);
+    const uint32_t idesc2 = idesc_m128(NCAT ? 2 * BN : BN, a.fmt);
     int sa = 0; uint32_t pha = 0; int sb = 0; uint32_t phb = 0; int acc = 0; uint32_t accphase = 0;
     if (a.b_resident) { mbar_wait(ball, 0); tc_fence_after(); }
     const int ksteps = a.BK / 16;
+    const uint32_t bstep = a.b_stage_bytes >> 4, pstep = pix_bytes >> 4, btile = a.b_tile_bytes >> 4;
     for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
       mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
       for (int sl = 0; sl < a.slabs; ++sl) {
-        mbar_wait(afull0 + 8 * sa, pha);
-        tc_fence_after();
-        const uint32_t halo = a_base + sa * a.a_stage_bytes;
-        if (a.b_resident) {
-          // resident weights: nothing to wait for inside the slab — one lane issues all 9 x ksteps MMAs
-          // back to back; descriptors differ only in the 14-bit start-address field (adds on the low word)
-          if (elect_one()) {
-            const uint64_t ad0 = desc_sbo(halo, a.hw * pix_bytes, a.swizzle_bits);
-            const uint64_t bd0 = desc_sbo(b_base + sl * a.taps * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
-            const uint32_t bstep = a.b_stage_bytes >> 4, pstep = pix_bytes >> 4;
-            if (a.taps == 9) {
+        if constexpr (P == 1) {
+          mbar_wait(afull0 + 8 * sa, pha);
+          tc_fence_after();
+          const uint32_t halo = a_base + sa * a.a_stage_bytes;
+          if (a.b_resident) {
+            // resident weights: nothing to wait for inside the slab — one lane issues all 9 x ksteps MMAs
+            // back to back; descriptors differ only in the 14-bit start-address field (adds on the low word)
+            if (elect_one()) {
+              const uint64_t ad0 = desc_sbo(halo, a.hw * pix_bytes, a.swizzle_bits);
+              const uint64_t bd0 = desc_sbo(b_base + sl * a.taps * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
+              if (a.taps == 9) {
 #pragma unroll
-              for (int tap = 0; tap < 9; ++tap) {
-                const uint64_t ad = ad0 + (uint32_t)((tap / 3) * HW_ + (tap % 3)) * pstep;
-                const uint64_t bd = bd0 + (uint32_t)tap * bstep;
+                for (int tap = 0; tap < 9; ++tap) {
+                  const uint64_t ad = ad0 + (uint32_t)((tap / 3) * HW_ + (tap % 3)) * pstep;
+                  const uint64_t bd = bd0 + (uint32_t)tap * bstep;
+                  for (int k = 0; k < ksteps; ++k)
+                    umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                }
+              } else {
+                int tap = 0;
+                for (int r = 0; r < a.kh; ++r)
+                  for (int q2 = 0; q2 < a.kw; ++q2, ++tap) {
+                    const uint64_t ad = ad0 + (uint32_t)(r * a.hw + q2) * pstep;
+                    const uint64_t bd = bd0 + (uint32_t)tap * bstep;
+                    for (int k = 0; k < ksteps; ++k)
+                      umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  }
+              }
+            }
+            __syncwarp();
+          } else {
+            for (int tap = 0; tap < a.taps; ++tap) {
+              mbar_wait(bfull0 + 8 * sb, phb);
+              tc_fence_after();
+              if (elect_one()) {
+                const int r = tap / a.kw, s = tap - a.kw * r;
+                const uint64_t ad = desc_sbo(halo + (r * a.hw + s) * pix_bytes, a.hw * pix_bytes, a.swizzle_bits);
+                const uint64_t bd = desc_sbo(b_base + sb * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
                 for (int k = 0; k < ksteps; ++k)
                   umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                umma_commit(bempty0 + 8 * sb);
               }
-            } else {
+              __syncwarp();
+              if (++sb == a.nb) { sb = 0; phb ^= 1; }
+            }
+          }
+          if (elect_one()) {
+            umma_commit(aempty0 + 8 * sa);
+            if (sl == a.slabs - 1) umma_commit(tfull0 + 8 * acc);
+          }
+          __syncwarp();
+          if (++sa == a.na) { sa = 0; pha ^= 1; }
+        } else if (a.b_resident) {
+          // ---- split operands, resident weights: hi-plane stage (A_hi x [W_hi ; W_lo]), then lo-plane stage (A_lo x W_hi)
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) {
+            mbar_wait(afull0 + 8 * sa, pha);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t ad0 = desc_sbo(a_base + sa * a.a_stage_bytes, a.hw * pix_bytes, a.swizzle_bits);
+              const uint64_t bd0 = desc_sbo(b_base + sl * a.taps * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
               int tap = 0;
               for (int r = 0; r < a.kh; ++r)
                 for (int q2 = 0; q2 < a.kw; ++q2, ++tap) {
                   const uint64_t ad = ad0 + (uint32_t)(r * a.hw + q2) * pstep;
                   const uint64_t bd = bd0 + (uint32_t)tap * bstep;
-                  for (int k = 0; k < ksteps; ++k)
-                    umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                  for (int k = 0; k < ksteps; ++k) {
+                    const uint32_t first = (sl > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                    if (pl == 0) {
+                      if constexpr (NCAT) {
+                        umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc2, first);
+                      } else {
+                        umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, first);
+                        umma_bf16(d_tmem, ad + 2 * k, bd + btile + 2 * k, idesc, 1u);
+                      }
+                    } else {
+                      umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                    }
+                  }
                 }
+              umma_commit(aempty0 + 8 * sa);
+              if (pl == 1 && sl == a.slabs - 1) umma_commit(tfull0 + 8 * acc);
             }
+            __syncwarp();
+            if (++sa == a.na) { sa = 0; pha ^= 1; }
           }
-          __syncwarp();
         } else {
+          // ---- split operands, streamed weights: both planes of the slab resident, one [W_hi | W_lo] stage per tap
+          const int sa_h = sa; const uint32_t pha_h = pha;
+          if (++sa == a.na) { sa = 0; pha ^= 1; }
+          const int sa_l = sa; const uint32_t pha_l = pha;
+          if (++sa == a.na) { sa = 0; pha ^= 1; }
+          mbar_wait(afull0 + 8 * sa_h, pha_h);
+          mbar_wait(afull0 + 8 * sa_l, pha_l);
+          tc_fence_after();
+          const uint32_t halo_h = a_base + sa_h * a.a_stage_bytes, halo_l = a_base + sa_l * a.a_stage_bytes;
           for (int tap = 0; tap < a.taps; ++tap) {
             mbar_wait(bfull0 + 8 * sb, phb);
             tc_fence_after();
             if (elect_one()) {
               const int r = tap / a.kw, s = tap - a.kw * r;
-              const uint64_t ad = desc_sbo(halo + (r * a.hw + s) * pix_bytes, a.hw * pix_bytes, a.swizzle_bits);
+              const uint32_t toff = (r * a.hw + s) * pix_bytes;
+              const uint64_t adh = desc_sbo(halo_h + toff, a.hw * pix_bytes, a.swizzle_bits);
+              const uint64_t adl = desc_sbo(halo_l + toff, a.hw * pix_bytes, a.swizzle_bits);
               const uint64_t bd = desc_sbo(b_base + sb * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t first = (sl > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                if constexpr (NCAT) {
+                  umma_bf16(d_tmem, adh + 2 * k, bd + 2 * k, idesc2, first);
+                } else {
+                  umma_bf16(d_tmem, adh + 2 * k, bd + 2 * k, idesc, first);
+                  umma_bf16(d_tmem, adh + 2 * k, bd + btile + 2 * k, idesc, 1u);
+                }
+                umma_bf16(d_tmem, adl + 2 * k, bd + 2 * k, idesc, 1u);
+              }
               umma_commit(bempty0 + 8 * sb);
             }
             __syncwarp();
             if (++sb == a.nb) { sb = 0; phb ^= 1; }
           }
+          if (elect_one()) {
+            umma_commit(aempty0 + 8 * sa_h);
+            umma_commit(aempty0 + 8 * sa_l);
+            if (sl == a.slabs - 1) umma_commit(tfull0 + 8 * acc);
+          }
+          __syncwarp();
         }
-        if (elect_one()) {
-          umma_commit(aempty0 + 8 * sa);
-          if (sl == a.slabs - 1) umma_commit(tfull0 + 8 * acc);
-        }
-        __syncwarp();
-        if (++sa == a.na) { sa = 0; pha ^= 1; }
       }
       if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
     }
@@ -234,17 +337,30 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       const int ho = h0 + (row >> 3), wo = w0 + (row & 7);
       const bool ok = ho < a.Ho && wo < a.Wo;
       const size_t pix = ((size_t)n * a.Ho + ho) * a.Wo + wo;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
 #pragma unroll 1
       for (int c = 0; c < BN / 16; ++c) {
         uint32_t v[16];
         tmem_ld16(taddr + c * 16, v);
-        tmem_ld_wait();
+        if constexpr (NCAT) {
+          uint32_t v2[16];
+          tmem_ld16(taddr + BN + c * 16, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        } else {
+          tmem_ld_wait();
+        }
         const int nb = n0 + c * 16;
         if (ok && nb < a.cout) {
           float f[16];
+          if constexpr (P == 2) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + sbias[c * 16 + j];
+            for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), a.acc_scale, sbias[c * 16 + j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + sbias[c * 16 + j];
+          }
           if (out_f32) {
             float *o = static_cast<float *>(a.dst) + pix * a.cout_store + nb;
             if (nb + 16 <= a.cout && (a.cout_store & 3) == 0) {
@@ -259,6 +375,29 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
               for (int j = 0; j < 16; ++j)
                 if (nb + j < a.cout) o[j] = cpb::act_out<__nv_bfloat16>(f[j], act);
             }
+          } else if constexpr (P == 2) {
+            // split output: hi plane at dst, lo plane dst_plane elements later; the residual is read the same way
+            uint16_t *o = static_cast<uint16_t *>(a.dst) + pix * a.cout_store + nb;
+            if (a.res) {
+              const uint16_t *rh = static_cast<const uint16_t *>(a.res) + pix * a.cout_store + nb;
+              const uint4 h0 = __ldg(reinterpret_cast<const uint4 *>(rh)), h1 = __ldg(reinterpret_cast<const uint4 *>(rh) + 1);
+              const uint4 l0 = __ldg(reinterpret_cast<const uint4 *>(rh + a.dst_plane)), l1 = __ldg(reinterpret_cast<const uint4 *>(rh + a.dst_plane) + 1);
+              const uint32_t hw_[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+              const uint32_t lw_[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float2 x = join2(hw_[j], lw_[j], a.fmt);
+                f[2 * j] += x.x; f[2 * j + 1] += x.y;
+              }
+            }
+            uint32_t oh[8], ol[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              split2(cpb::act_fn(f[2 * j], act), cpb::act_fn(f[2 * j + 1], act), a.fmt, oh[j], ol[j]);
+            reinterpret_cast<uint4 *>(o)[0] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+            reinterpret_cast<uint4 *>(o)[1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
+            reinterpret_cast<uint4 *>(o + a.dst_plane)[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+            reinterpret_cast<uint4 *>(o + a.dst_plane)[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
           } else {
             __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(a.dst) + pix * a.cout_store + nb;
             if (a.res) {
@@ -306,18 +445,15 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
 
 struct C3Op {
   C3Args args;
-  int BN, grid;
+  int BN, P, grid;
   size_t smem;
 };
 
-template <int BN>
-int launch_c3(const C3Op &t, cudaStream_t st) {
-  static size_t attr_smem = 0;
-  if (t.smem > attr_smem) {
-    CPB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
-    attr_smem = t.smem;
-  }
-  conv3x3_tc_kernel<BN><<<t.grid, C3_THREADS, t.smem, st>>>(t.args);
+template <int BN, int P>
+int launch_c3(const C3Op &t, const C3Args &args, cudaStream_t st) {
+  static SmemAttrCache cache;
+  if (int rc = ensure_smem(conv3x3_tc_kernel<BN, P>, t.smem, cache)) return rc;
+  conv3x3_tc_kernel<BN, P><<<t.grid, C3_THREADS, t.smem, st>>>(args);
   return cpb::check_launch("conv3x3_tc_kernel");
 }
 
@@ -325,13 +461,15 @@ int launch_c3(const C3Op &t, cudaStream_t st) {
 
 namespace cpb {
 
+static bool tc_act_dtype(int d) { return d == CPB200_BF16 || d == CPB200_BF16X2 || d == CPB200_F16X2; }
+
 bool c3_eligible(const cpb200_op &op) {
   const bool geom = (op.kh == 3 && op.kw == 3) || (op.kh == 7 && op.kw == 1) || (op.kh == 1 && op.kw == 7) || (op.kh == 5 && op.kw == 5);
   return op.type == CPB200_OP_CONV && geom && op.stride == 1 && op.pad_h == op.kh / 2 && op.pad_w == op.kw / 2 &&
          op.nsrc == 1 && op.cin[0] % 16 == 0 && (op.src_pitch[0] == 0 || op.src_pitch[0] == op.cin[0]) && op.Wo >= 8 && op.Ho >= 8 &&
          op.H == op.Ho && op.W == op.Wo &&
          op.out_sy == 1 && op.out_sx == 1 && !op.out_oy && !op.out_ox && op.Hd == op.Ho && op.Wd == op.Wo &&
-         !(op.flags & CPB200_FLAG_OUT_NCHW_F32) && op.act_dtype == CPB200_BF16 &&
+         !(op.flags & CPB200_FLAG_OUT_NCHW_F32) && tc_act_dtype(op.act_dtype) &&
          ((op.flags & CPB200_FLAG_OUT_F32) || op.cout % 16 == 0);
 }
 
@@ -343,6 +481,11 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   C3Op *t = new C3Op();
   C3Args &a = t->args;
   memset(&a, 0, sizeof(a));
+  const int P = op.act_dtype == CPB200_BF16 ? 1 : 2;
+  t->P = P;
+  a.fmt = op.act_dtype == CPB200_F16X2 ? 1u : 0u;
+  a.acc_scale = op.acc_scale != 0.f ? op.acc_scale : 1.f;
+  a.dst_plane = (long long)op.B * op.Ho * op.Wo * op.cout;
   const int cin = op.cin[0];
   const int bk = (cin % 64 == 0) ? 64 : (cin % 32 == 0) ? 32 : 16;
   a.cin = cin; a.BK = bk; a.slabs = cin / bk;
@@ -357,50 +500,62 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   a.n_tiles = (op.cout + BN - 1) / BN;
   a.cout = op.cout; a.cout_store = op.cout;
   a.total_tiles = op.B * a.tiles_h * a.tiles_w * a.n_tiles;
-  a.nacc = 512 / BN > 8 ? 8 : 512 / BN;      // TMEM accumulator stages (hides the MMA<->epilogue hand-off latency)
+  const int acc_cols = (P == 2 && 2 * BN <= 256) ? 2 * BN : BN;
+  a.nacc = 512 / acc_cols > 8 ? 8 : 512 / acc_cols;      // TMEM accumulator stages (hides the MMA<->epilogue hand-off latency)
   a.dst = op.dst; a.res = op.res; a.bias = op.bias; a.flags = op.flags;
   a.kh = op.kh; a.kw = op.kw; a.taps = op.kh * op.kw; a.hw = TW + op.kw - 1;
   const int hh = TH + op.kh - 1;
   a.a_tx_bytes = (unsigned)(a.hw * hh * bk * 2);
-  a.a_stage_bytes = (a.a_tx_bytes + 1023u) & ~1023u;
+  a.a_stage_bytes = (a.a_tx_bytes + 1023u) & ~1023u;       // one plane of one slab's halo
   a.b_tx_bytes = BN * bk * 2;
-  a.b_stage_bytes = (a.b_tx_bytes + 1023u) & ~1023u;
-  const size_t budget = 200 * 1024;
+  a.b_tile_bytes = a.b_tx_bytes;
+  a.b_stage_bytes = ((unsigned)P * a.b_tx_bytes + 1023u) & ~1023u;      // P = 2: [hi tile | lo tile]
+  // dynamic shared memory: 227 KB per CTA minus the static part (barriers, up to 4 KB of bias) and the alignment slack
+  const size_t budget = (P == 2 ? 220 : 200) * 1024;
   a.na = 3;
   if (a.a_stage_bytes <= 12 * 1024) a.na = (a.a_stage_bytes <= 6 * 1024) ? 16 : 8;   // small halos: deeper ring hides TMA latency
   if (const char *e = getenv("CPB200_C3_NA")) { int v = atoi(e); if (v >= 2 && v <= MAX_NA) a.na = v; }
+  if (P == 2 && a.na < 4) a.na = 4;                         // two slabs' worth of planes in flight
   const size_t resident_bytes = (size_t)a.taps * a.slabs * a.b_stage_bytes;
-  if (a.n_tiles == 1 && a.na * (size_t)a.a_stage_bytes + resident_bytes <= budget) {
+  int na_res = a.na;
+  while (na_res > 2 && na_res * (size_t)a.a_stage_bytes + resident_bytes > budget) --na_res;
+  if (a.n_tiles == 1 && na_res >= (P == 2 ? 3 : a.na) && na_res * (size_t)a.a_stage_bytes + resident_bytes <= budget) {
+    a.na = na_res;
     a.b_resident = 1; a.nb = a.taps * a.slabs;
     t->smem = a.na * (size_t)a.a_stage_bytes + resident_bytes + 1024;
   } else {
     a.b_resident = 0;
-    if (a.na * (size_t)a.a_stage_bytes + 3 * (size_t)a.b_stage_bytes > budget) a.na = 2;
+    const int min_b = P == 2 ? 2 : 3;                       // weight stages wanted beside the halo ring
+    if (P == 1 && a.na * (size_t)a.a_stage_bytes + min_b * (size_t)a.b_stage_bytes > budget) a.na = 2;
+    while (P == 2 && a.na > 2 && a.na * (size_t)a.a_stage_bytes + min_b * (size_t)a.b_stage_bytes > budget) a.na -= 2;
+    if (P == 2 && (a.na & 1)) --a.na;                       // streamed weights consume the planes in pairs
     int nb = (int)((budget - a.na * (size_t)a.a_stage_bytes) / a.b_stage_bytes);
     if (nb > MAX_NB) nb = MAX_NB;
-    if (nb < 2) { delete t; *rc = fail(CPB200_ERR_ARG, "tc3: tile does not fit shared memory"); return nullptr; }
+    if (nb < 2 || a.na < 2) { delete t; *rc = fail(CPB200_ERR_ARG, "tc3: tile does not fit shared memory"); return nullptr; }
     a.nb = nb;
     t->smem = a.na * (size_t)a.a_stage_bytes + nb * (size_t)a.b_stage_bytes + 1024;
   }
   const int nsm = num_sms();
   t->grid = a.total_tiles < nsm ? a.total_tiles : nsm;
+  const CUtensorMapDataType dt = a.fmt ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   {
-    const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.B};
+    // split activations: the lo plane follows the hi plane, i.e. a batch of 2B images
+    const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.B * P};
     const cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)op.W * cin * 2, (cuuint64_t)op.H * op.W * cin * 2};
     const cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)a.hw, (cuuint32_t)hh, 1};
     const cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = enc(&a.amap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(op.src[0]), dims, strides, box, es,
+    CUresult r = enc(&a.amap, dt, 4, const_cast<void *>(op.src[0]), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete t; *rc = fail(CPB200_ERR_CUDA, "tc3: cuTensorMapEncodeTiled(A) failed: %d", (int)r); return nullptr; }
   }
   {
-    // weights are packed slab-major [tap][K-slab][cout_pad][bk] (plan.py::_pack_conv_tc): a box is one dense run
+    // weights are packed slab-major [plane][tap][K-slab][cout_pad][bk] (plan.py::_pack_conv_tc): a box is one dense run
     const int cout_pad = (op.cout + 15) / 16 * 16;
-    const cuuint64_t dims[3] = {(cuuint64_t)bk, (cuuint64_t)cout_pad, (cuuint64_t)a.taps * (cuuint64_t)a.slabs};
+    const cuuint64_t dims[3] = {(cuuint64_t)bk, (cuuint64_t)cout_pad, (cuuint64_t)a.taps * (cuuint64_t)a.slabs * P};
     const cuuint64_t strides[2] = {(cuuint64_t)bk * 2, (cuuint64_t)cout_pad * bk * 2};
     const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)BN, 1};
     const cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&a.bmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(op.weight), dims, strides, box, es,
+    CUresult r = enc(&a.bmap, dt, 3, const_cast<void *>(op.weight), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete t; *rc = fail(CPB200_ERR_CUDA, "tc3: cuTensorMapEncodeTiled(B) failed: %d", (int)r); return nullptr; }
   }
@@ -409,15 +564,17 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
 
 void c3_release(void *h) { delete static_cast<C3Op *>(h); }
 
-int c3_run(const void *h, cudaStream_t st) {
+// `op` supplies the pointers that may be re-bound between runs (dst / res / bias); everything else was fixed at prepare.
+int c3_run(const void *h, const cpb200_op &op, cudaStream_t st) {
   const C3Op *t = static_cast<const C3Op *>(h);
+  C3Args args = t->args;
+  args.dst = op.dst; args.res = op.res; args.bias = op.bias;
+#define C3_CASE(N)                                                                                   \
+  case N: return t->P == 2 ? launch_c3<N, 2>(*t, args, st) : launch_c3<N, 1>(*t, args, st);
   switch (t->BN) {
-    case 16: return launch_c3<16>(*t, st);
-    case 32: return launch_c3<32>(*t, st);
-    case 64: return launch_c3<64>(*t, st);
-    case 128: return launch_c3<128>(*t, st);
-    case 256: return launch_c3<256>(*t, st);
+    C3_CASE(16) C3_CASE(32) C3_CASE(64) C3_CASE(128) C3_CASE(256)
   }
+#undef C3_CASE
   return fail(CPB200_ERR_STATE, "tc3: bad BN");
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 namespace tc {
 
@@ -81,10 +82,59 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t row_bytes
 }
 
 
+// ------------------------------------------------------------------------------------------------------------
+// Split-operand ("x2") arithmetic: every fp32 value v is carried as two 16-bit planes hi = rn16(v),
+// lo = rn16(v - hi); a product a*b is evaluated on the tensor core as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with fp32
+// accumulation in TMEM (the dropped a_lo*b_lo term is <= 2^-16 / 2^-22 of the product for bf16 / fp16 planes).
+// fmt: 0 = bf16 planes (8+8 significand bits, fp32 range), 1 = fp16 planes (11+11 bits, |v| <= 65504 — the epilogues
+// saturate; weights are pre-scaled by a power of two on the host so that their lo parts stay normal numbers).
+__device__ __forceinline__ uint32_t idesc_m128(uint32_t n, uint32_t fmt) {
+  // D = f32, A/B format (0 = f16, 1 = bf16), both K-major, N = n, M = 128
+  const uint32_t ab = fmt ? 0u : 1u;
+  return (1u << 4) | (ab << 7) | (ab << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void split2(float a, float b, uint32_t fmt, uint32_t &hi, uint32_t &lo) {
+  if (fmt) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
+  }
+}
+__device__ __forceinline__ float2 unpack2(uint32_t v, uint32_t fmt) {
+  if (fmt) return __half22float2(*reinterpret_cast<const __half2 *>(&v));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&v));
+}
+__device__ __forceinline__ float2 join2(uint32_t hi, uint32_t lo, uint32_t fmt) {
+  const float2 h = unpack2(hi, fmt), l = unpack2(lo, fmt);
+  return make_float2(h.x + l.x, h.y + l.y);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode();
-int num_sms();
+int num_sms();          // SM count of the CURRENT device (cached per device)
+int cur_device();
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): remember the largest value set on each device.
+constexpr int MAX_DEVICES = 64;
+struct SmemAttrCache { size_t v[MAX_DEVICES] = {}; };
+template <typename F>
+inline int ensure_smem(F *func, size_t smem, SmemAttrCache &cache) {
+  const int dev = cur_device();
+  if (dev < 0 || dev >= MAX_DEVICES) return cpb::fail(CPB200_ERR_STATE, "device index %d out of range", dev);
+  if (smem > cache.v[dev]) {
+    CPB_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cache.v[dev] = smem;
+  }
+  return CPB200_OK;
+}
 
 }  // namespace tc

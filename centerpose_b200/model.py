@@ -102,9 +102,17 @@ class BackBoneWithHead(nn.Module):
         self._plans = {}
 
     def set_precision(self, precision: str, tc=None):
-        """'fp32' (CUDA-core kernels, reference-precision) or 'bf16' (tcgen05 tensor-core kernels;
-        tc=False keeps bf16 activations but forces the CUDA-core kernels — debugging aid)."""
-        if precision not in ("fp32", "bf16"):
+        """Arithmetic of the forward pass (the reference is fp32 end to end):
+          'fp16x2'  tcgen05 tensor cores on split operands — every activation / weight is a pair of fp16 planes
+                    (hi + lo, 22 significand bits), a*b = a_hi*b_hi + a_hi*b_lo + a_lo*b_hi with fp32 accumulation:
+                    fp32-faithful (head maps within ~4e-6 relative L2 of the reference's fp32 result) at tensor-core
+                    speed; activations must stay within the fp16 range (|v| <= 65504, saturating);
+          'bf16x2'  same with bf16 planes: full fp32 range, 16 significand bits (~6e-5 relative L2);
+          'bf16'    plain bf16 operands (fastest; ~2e-2 relative L2 through the ~100 layers);
+          'fp32'    CUDA-core kernels, fp32 activations (reference arithmetic up to summation order; slow).
+        tc=False keeps bf16 activations but forces the CUDA-core kernels — a debugging aid."""
+        from .plan import PRECISIONS
+        if precision not in PRECISIONS:
             raise ValueError(precision)
         self.precision = precision
         self.tc = tc

@@ -25,11 +25,32 @@ import torch
 from . import _lib
 
 OP_CONV, OP_STEM, OP_MAXPOOL, OP_DWDECONV_ADD, OP_DCN, OP_IM2COL_W, OP_UPSAMPLE_ADD = 1, 2, 3, 4, 5, 6, 7
-OP_DWCONV, OP_AVGPOOL, OP_SCALE_ADD = 8, 9, 10
-FLAG_RELU, FLAG_OUT_NCHW_F32, FLAG_OUT_F32, FLAG_TC, FLAG_HSWISH, FLAG_HSIGMOID = 1, 2, 4, 8, 16, 32
+OP_DWCONV, OP_AVGPOOL, OP_SCALE_ADD, OP_CONVERT = 8, 9, 10, 11
+FLAG_RELU, FLAG_OUT_NCHW_F32, FLAG_OUT_F32, FLAG_TC, FLAG_HSWISH, FLAG_HSIGMOID, FLAG_TO_F32 = 1, 2, 4, 8, 16, 32, 64
 _ACT_FLAG = {None: 0, "relu": FLAG_RELU, "hswish": FLAG_HSWISH, "hsigmoid": FLAG_HSIGMOID}
-F32, BF16 = 0, 1
+F32, BF16, BF16X2, F16X2 = 0, 1, 2, 3
+PRECISIONS = {"fp32": F32, "bf16": BF16, "bf16x2": BF16X2, "fp16x2": F16X2}
 BN_EPS = 1e-5
+
+
+def split_planes(t: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
+    """fp32 tensor -> (2, ...) stack of 16-bit planes: hi = rn16(t), lo = rn16(t - hi)   (include/centerpose_b200.h)."""
+    t = t.float()
+    if dt == torch.float16:
+        t = t.clamp(-65504.0, 65504.0)
+    hi = t.to(dt)
+    lo = (t - hi.float()).to(dt)
+    return torch.stack([hi, lo]).contiguous()
+
+
+def pow2_scale(w: torch.Tensor, target_exp: int = 12) -> float:
+    """Power-of-two factor that moves max|w| into [2^target_exp, 2^(target_exp+1)): applied to the weights of fp16-plane
+    ops so that the lo parts are normal fp16 numbers; the kernels multiply the accumulator by its inverse (exact)."""
+    m = float(w.abs().max())
+    if not (m > 0.0) or m != m or m == float("inf"):
+        return 1.0
+    import math
+    return float(2.0 ** (target_exp - math.floor(math.log2(m))))
 
 
 class OpStruct(ctypes.Structure):
@@ -48,12 +69,13 @@ class OpStruct(ctypes.Structure):
         ("src", ctypes.c_void_p * 4), ("res", ctypes.c_void_p), ("aux", ctypes.c_void_p),
         ("dst", ctypes.c_void_p), ("weight", ctypes.c_void_p), ("bias", ctypes.c_void_p),
         ("tc", ctypes.c_void_p), ("src_pitch", ctypes.c_int32 * 4),
+        ("acc_scale", ctypes.c_float), ("reserved_", ctypes.c_int32),
     ]
 
 
 class Sym:
     """Symbolic activation tensor (NHWC unless kind says otherwise)."""
-    __slots__ = ("C", "H", "W", "kind", "name", "_buf", "producer", "_last_use", "fixed", "parent", "ch_off")
+    __slots__ = ("C", "H", "W", "kind", "name", "_buf", "producer", "_last_use", "fixed", "parent", "ch_off", "_f32", "_sp")
 
     def __init__(self, C, H, W, kind="act", name="", parent=None, ch_off=0):
         self.C, self.H, self.W, self.kind, self.name = C, H, W, kind, name
@@ -63,6 +85,8 @@ class Sym:
         self.fixed = False       # externally provided storage (network input / outputs)
         self.parent = parent     # channel slice [ch_off, ch_off + C) of `parent` (shares its storage)
         self.ch_off = ch_off
+        self._f32 = None         # split precisions: cached fp32 copy / split copy of this activation
+        self._sp = None
 
     # a slice lives in its parent's buffer and keeps the parent alive
     @property
@@ -107,19 +131,25 @@ def fold_bn(w: torch.Tensor, b: Optional[torch.Tensor], bn: Optional[dict]):
 
 class PlanBuilder:
     def __init__(self, B: int, H: int, W: int, precision: str, device: torch.device, tc: Optional[bool] = None):
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
         self.B, self.H, self.W = B, H, W
         self.device = device
-        self.act_dtype = F32 if precision == "fp32" else BF16
-        self.torch_act = torch.float32 if precision == "fp32" else torch.bfloat16
+        self.precision = precision
+        self.act_dtype = PRECISIONS[precision]
+        # split-operand precisions: activations are hi/lo 16-bit planes, every conv runs on tcgen05 as three products
+        self.split = precision in ("bf16x2", "fp16x2")
+        self.torch16 = torch.float16 if precision == "fp16x2" else torch.bfloat16
+        self.torch_act = torch.float32 if precision == "fp32" else self.torch16
         self.ops: List[_PendingOp] = []
         self.keep: List[torch.Tensor] = []      # weights / biases kept alive
         self.syms: List[Sym] = []
-        # tensor-core (tcgen05) path: bf16 only; CPB200_TC=0 forces the SIMT kernels (debugging)
+        # tensor-core (tcgen05) path: 16-bit operands only; CPB200_TC=0 forces the SIMT kernels (bf16: debugging)
         if tc is None:
             tc = os.environ.get("CPB200_TC", "1") != "0"
-        self.use_tc = bool(tc) and precision == "bf16"
+        if self.split and not tc:
+            raise ValueError("split precisions run on the tensor-core path only")
+        self.use_tc = bool(tc) and precision != "fp32"
 
     # ---- symbolic tensors -------------------------------------------------------------
     def _sym(self, C, H, W, kind="act", name=""):
@@ -133,12 +163,13 @@ class PlanBuilder:
         return s
 
     def external(self, t: torch.Tensor, kind="act"):
-        """Wrap an existing NHWC device tensor (B,H,W,C) as a program input (tests, partial graphs)."""
+        """Wrap an existing NHWC device tensor (B,H,W,C) as a program input (tests, partial graphs).  Split
+        precisions: ``t`` is fp32 and is split into the hi / lo planes here."""
         B, H, W, C = t.shape
         assert B == self.B and t.is_contiguous()
         s = self._sym(C, H, W, kind, "external")
         s.fixed = True
-        s.buf = t
+        s.buf = split_planes(t, self.torch16) if (self.split and kind == "act") else t
         return s
 
     def output(self, C, H, W, name):
@@ -146,7 +177,43 @@ class PlanBuilder:
         s.fixed = True
         return s
 
+    # ---- split precisions: fp32 islands for ops without a native split kernel ------------------
+    def _to_f32(self, x: Optional[Sym]) -> Optional[Sym]:
+        """fp32 NHWC copy of a split activation (cached; a channel slice converts its parent once)."""
+        if x is None or not self.split or x.kind != "act":
+            return x
+        if x.parent is not None:
+            pf = self._to_f32(x.parent)
+            v = Sym(x.C, x.H, x.W, "actf32", parent=pf, ch_off=x.ch_off)
+            v.producer = pf.producer
+            return v
+        if x._f32 is None:
+            y = self._sym(x.C, x.H, x.W, "actf32", x.name + ".f32")
+            self._emit(_PendingOp(type=OP_CONVERT, flags=FLAG_TO_F32, k=(1, 1), stride=1, pad=(0, 0), weight=None, bias=None,
+                                  cout=x.C, dtype=self.act_dtype), [x], y)
+            x._f32 = y; y._sp = x
+        return x._f32
+
+    def _to_split(self, y: Sym) -> Sym:
+        """split copy of an fp32 NHWC activation produced inside an fp32 island."""
+        if not self.split or y.kind != "actf32":
+            return y
+        if y._sp is None:
+            x = self._sym(y.C, y.H, y.W, "act", y.name + ".sp")
+            self._emit(_PendingOp(type=OP_CONVERT, flags=0, k=(1, 1), stride=1, pad=(0, 0), weight=None, bias=None,
+                                  cout=y.C, dtype=self.act_dtype), [y], x)
+            y._sp = x; x._f32 = y
+        return y._sp
+
+    def _island_sym(self, C, H, W):
+        """output of an op that runs on fp32 in split mode (kind 'actf32'), an ordinary activation otherwise."""
+        return self._sym(C, H, W, "actf32" if self.split else "act")
+
     def _emit(self, op: _PendingOp, srcs: Sequence[Sym], dst: Sym, extra: Sequence[Optional[Sym]] = ()):
+        if not hasattr(op, "dtype"):
+            op.dtype = self.act_dtype
+        if not hasattr(op, "acc_scale"):
+            op.acc_scale = 1.0
         idx = len(self.ops)
         for s in list(srcs) + [e for e in extra if e is not None]:
             s.last_use = max(s.last_use, idx)
@@ -180,6 +247,14 @@ class PlanBuilder:
         cop = (co + 15) // 16 * 16
         p = torch.zeros(kh * kw, ci // bk, cop, bk, dtype=torch.float32, device=w.device)
         p[:, :, :co, :] = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci // bk, bk).permute(0, 2, 1, 3)
+        if self.split:
+            # [plane][tap][slab][Co_pad][bk]: hi plane then lo plane; fp16 planes carry the weights times a power of two
+            # (pow2_scale) whose inverse the kernel applies to the accumulator (cpb200_op.acc_scale)
+            self._last_scale = pow2_scale(w) if self.torch16 == torch.float16 else 1.0
+            t = split_planes(p * self._last_scale, self.torch16).to(self.device)
+            self.keep.append(t)
+            return t
+        self._last_scale = 1.0
         return self._dev(p, torch.bfloat16)
 
     @staticmethod
@@ -225,6 +300,20 @@ class PlanBuilder:
         n_idx = torch.arange(N, device=w.device).view(1, N, 1, 1).expand(7, N, 4, 8)
         j_idx = torch.arange(4, device=w.device).view(1, 1, 4, 1).expand(7, N, 4, 8)
         img = torch.zeros(7, N, 4, 8, dtype=torch.float32, device=w.device)
+        if self.split:
+            # per tap [hi tile (N rows) | lo tile (N rows)]; row n' = plane * N + n of the 2N-row block is swizzled with
+            # (n' >> 1) & 3 == (n >> 1) & 3 (N is a multiple of 8)
+            self._last_scale = pow2_scale(w) if self.torch16 == torch.float16 else 1.0
+            planes = split_planes(blk * self._last_scale, self.torch16).float()       # (2, 7, N, 4, 8)
+            out = torch.zeros(7, 2, N, 4, 8, dtype=torch.float32, device=w.device)
+            for pl in range(2):
+                tmp = torch.zeros(7, N, 4, 8, dtype=torch.float32, device=w.device)
+                tmp.scatter_(2, (j_idx ^ ((n_idx >> 1) & 3)), planes[pl].contiguous())
+                out[:, pl] = tmp
+            t = out.to(self.torch16).to(self.device).contiguous()
+            self.keep.append(t)
+            return t
+        self._last_scale = 1.0
         img.scatter_(2, (j_idx ^ ((n_idx >> 1) & 3)), blk.contiguous())
         return self._dev(img, torch.bfloat16)
 
@@ -234,10 +323,14 @@ class PlanBuilder:
                 and (co % 16 == 0 or out in ("f32", "nchw")) and kh * kw <= 49)
 
     # ---- ops -------------------------------------------------------------------------------
+    # Split precisions (bf16x2 / fp16x2): convs, DCNs and the stride-1 stem run natively on the hi/lo planes (tensor-core
+    # kernels), max-pool and the IDAUp depthwise upsample have split kernels; everything else (and conv shapes the
+    # tensor-core kernels do not take, e.g. maps narrower than 8 pixels) runs on fp32 between two CONVERT ops — an
+    # "fp32 island": slower, never less precise.
     def stem(self, x: Sym, w, b, k, stride, pad, relu=True, act=None):
         co, ci = w.shape[0], w.shape[1]
         mode = os.environ.get("CPB200_TC_STEM", "1")
-        if (self.use_tc and mode == "im2col" and stride == 1 and k * ci <= 32 and co % 16 == 0 and pad == k // 2):
+        if (self.use_tc and not self.split and mode == "im2col" and stride == 1 and k * ci <= 32 and co % 16 == 0 and pad == k // 2):
             # first tensor-core stem (kept for the record, CPB200_TC_STEM=im2col): gather the k horizontal taps of
             # every pixel into 32 channels IN HBM, then a k x 1 conv with K = k * 32 on the halo-reuse kernel.
             # Correct (tests/test_net_gpu.py::test_stem_im2col_path) but measured SLOWER than the CUDA-core stem at
@@ -250,24 +343,26 @@ class PlanBuilder:
             w2[:, :k * ci, :, 0] = w.float().permute(0, 3, 1, 2).reshape(co, k * ci, k)
             return self.conv([t], w2, b.float(), stride=1, relu=relu, pad_hw=(pad, 0))
         flags = _ACT_FLAG[act] if act else (FLAG_RELU if relu else 0)
-        if (self.use_tc and mode != "0" and k == 7 and ci == 3 and pad == 3 and stride in (1, 2) and co in (16, 64)):
-            # tensor-core stem with the im2col done in shared memory (csrc/net_stem_tc.cu)
-            Ho = (x.H + 2 * pad - k) // stride + 1; Wo = (x.W + 2 * pad - k) // stride + 1
-            y = self._sym(co, Ho, Wo)
-            self._emit(_PendingOp(type=OP_STEM, flags=flags | FLAG_TC, k=(k, k), stride=stride, pad=(pad, pad),
-                                  weight=self._pack_stem_tc_h(w) if stride == 1 else self._pack_stem_tc(w),
-                                  bias=self._dev(b), cout=co), [x], y)
-            return y
         Ho = (x.H + 2 * pad - k) // stride + 1; Wo = (x.W + 2 * pad - k) // stride + 1
-        y = self._sym(co, Ho, Wo)
+        if (self.use_tc and mode != "0" and k == 7 and ci == 3 and pad == 3 and stride in (1, 2) and co in (16, 64)
+                and not (self.split and stride != 1)):
+            # tensor-core stem with the im2col done in shared memory (csrc/net_stem_tc.cu); split precisions: stride 1 only
+            y = self._sym(co, Ho, Wo)
+            wp = self._pack_stem_tc_h(w) if stride == 1 else self._pack_stem_tc(w)
+            self._emit(_PendingOp(type=OP_STEM, flags=flags | FLAG_TC, k=(k, k), stride=stride, pad=(pad, pad),
+                                  weight=wp, bias=self._dev(b), cout=co,
+                                  acc_scale=1.0 / getattr(self, "_last_scale", 1.0) if stride == 1 else 1.0), [x], y)
+            return y
+        y = self._island_sym(co, Ho, Wo)
         wp = self._dev(w.permute(2, 3, 1, 0).reshape(k * k * ci, co))
         self._emit(_PendingOp(type=OP_STEM, flags=flags, k=(k, k), stride=stride,
-                              pad=(pad, pad), weight=wp, bias=self._dev(b), cout=co), [x], y)
-        return y
+                              pad=(pad, pad), weight=wp, bias=self._dev(b), cout=co,
+                              dtype=F32 if self.split else self.act_dtype), [x], y)
+        return self._to_split(y)
 
     def conv(self, srcs: Sequence[Sym], w, b, stride=1, pad=0, relu=False, res: Optional[Sym] = None,
              out: str = "act", dst: Optional[Sym] = None, ch_off: int = 0, pad_hw=None,
-             out_map=None, act=None):
+             out_map=None, act=None, _island_dst: Optional[Sym] = None):
         """w (Co, sum(Ci), kh, kw) already BN-folded; b (Co).  out: 'act' | 'f32' | 'nchw'.
         pad_hw=(top,left) overrides symmetric padding; out_map=(Hd,Wd,sy,sx,oy,ox,Ho,Wo) writes a
         strided sub-lattice of a larger dst (used to lower dense ConvTranspose2d)."""
@@ -281,6 +376,11 @@ class PlanBuilder:
         else:
             Hd, Wd, sy, sx, oy, ox, Ho, Wo = out_map
         flags = _ACT_FLAG[act] if act else (FLAG_RELU if relu else 0)     # act: 'relu' | 'hswish' | 'hsigmoid'
+        tc = self._tc_ok(srcs, co, kh, kw, stride, out, out_map, Wo)
+        island = self.split and not tc                                     # fp32 island (see above)
+        if island:
+            srcs = [self._to_f32(s_) for s_ in srcs]
+            res = self._to_f32(res)
         if out == "nchw":
             assert dst is not None
             flags |= FLAG_OUT_NCHW_F32
@@ -288,16 +388,39 @@ class PlanBuilder:
         elif out == "f32":
             flags |= FLAG_OUT_F32
             y = dst if dst is not None else self._sym(co, Hd, Wd, "f32")
+        elif island:
+            assert dst is None, "strided-output convs go through deconv_k4s2"
+            y = _island_dst if _island_dst is not None else self._sym(co, Hd, Wd, "actf32")
         else:
             y = dst if dst is not None else self._sym(co, Hd, Wd)
-        tc = self._tc_ok(srcs, co, kh, kw, stride, out, out_map, Wo)
         if tc:
             flags |= FLAG_TC
+        wp = self._pack_conv_tc(w, self._tc_bk(srcs)) if tc else self._pack_conv(w)
         self._emit(_PendingOp(type=OP_CONV, flags=flags, k=(kh, kw), stride=stride, pad=(ph, pw),
-                              weight=self._pack_conv_tc(w, self._tc_bk(srcs)) if tc else self._pack_conv(w),
-                              bias=self._dev(b), cout=co, ch_off=ch_off,
-                              out_map=(Hd, Wd, sy, sx, oy, ox), HoWo=(Ho, Wo), w_raw=w), srcs, y, [res])
+                              weight=wp, bias=self._dev(b), cout=co, ch_off=ch_off,
+                              out_map=(Hd, Wd, sy, sx, oy, ox), HoWo=(Ho, Wo), w_raw=w,
+                              dtype=F32 if island else self.act_dtype,
+                              acc_scale=(1.0 / self._last_scale) if tc else 1.0), srcs, y, [res])
+        if island and out == "act" and _island_dst is None:
+            return self._to_split(y)
         return y
+
+    _KSEL = {0: [3, 1], 1: [2, 0]}        # kernel rows/cols feeding output parity 0 / 1, in input order
+
+    def deconv_k4s2(self, x: Sym, w_full, b, relu=True) -> Sym:
+        """Dense ConvTranspose2d(k4, s2, p1) (msra_resnet.py:168-193) as four 2x2 parity convs writing the strided
+        sub-lattices of one output tensor.  w_full (Cout, Cin, 4, 4) BN-folded."""
+        co = w_full.shape[0]
+        Ho, Wo = 2 * x.H, 2 * x.W
+        tc = self._tc_ok([x], co, 2, 2, 1, "act", (Ho, Wo, 2, 2, 0, 0, x.H, x.W), x.W)
+        island = self.split and not tc
+        y = self._sym(co, Ho, Wo, "actf32" if island else "act")
+        for a in (0, 1):
+            for bb in (0, 1):
+                w_sub = w_full[:, :, self._KSEL[a], :][:, :, :, self._KSEL[bb]].contiguous()        # (Cout, Cin, 2, 2)
+                self.conv([x], w_sub, b, stride=1, relu=relu, dst=None if island else y, _island_dst=y if island else None,
+                          pad_hw=(1 - a, 1 - bb), out_map=(Ho, Wo, 2, 2, a, bb, x.H, x.W))
+        return self._to_split(y) if island else y
 
     def maxpool(self, x: Sym, k=2, stride=2, pad=0):
         Ho = (x.H + 2 * pad - k) // stride + 1; Wo = (x.W + 2 * pad - k) // stride + 1
@@ -317,38 +440,40 @@ class PlanBuilder:
                               weight=wp, bias=None, cout=C), [x], y, [skip])
         return y
 
+    def _f32_op(self, op: _PendingOp, srcs, C, H, W, extra=()):
+        """emit an op that has no split kernel: on fp32 between CONVERT ops in split mode, natively otherwise."""
+        if self.split:
+            op.dtype = F32
+            srcs = [self._to_f32(s_) for s_ in srcs]
+            extra = [self._to_f32(e) for e in extra]
+        y = self._island_sym(C, H, W)
+        self._emit(op, srcs, y, list(extra))
+        return self._to_split(y)
+
     def dwconv(self, x: Sym, w, b, stride=1, act=None):
         """depthwise conv, w (C,1,k,k) BN-folded, pad k//2   (mobilenetv3.py:124-127)."""
         C, _, k, _ = w.shape
         assert C == x.C
         Ho = (x.H + 2 * (k // 2) - k) // stride + 1; Wo = (x.W + 2 * (k // 2) - k) // stride + 1
-        y = self._sym(C, Ho, Wo)
         wp = self._dev(w.float().reshape(C, k * k).t())          # [k*k][C]
-        self._emit(_PendingOp(type=OP_DWCONV, flags=_ACT_FLAG[act], k=(k, k), stride=stride, pad=(k // 2, k // 2),
-                              weight=wp, bias=self._dev(b), cout=C), [x], y)
-        return y
+        return self._f32_op(_PendingOp(type=OP_DWCONV, flags=_ACT_FLAG[act], k=(k, k), stride=stride, pad=(k // 2, k // 2),
+                                       weight=wp, bias=self._dev(b), cout=C), [x], C, Ho, Wo)
 
     def avgpool(self, x: Sym):
         """global average pool -> (C, 1, 1)   (mobilenetv3.py:100)."""
-        y = self._sym(x.C, 1, 1)
-        self._emit(_PendingOp(type=OP_AVGPOOL, flags=0, k=(x.H, x.W), stride=1, pad=(0, 0), weight=None, bias=None,
-                              cout=x.C), [x], y)
-        return y
+        return self._f32_op(_PendingOp(type=OP_AVGPOOL, flags=0, k=(x.H, x.W), stride=1, pad=(0, 0), weight=None, bias=None,
+                                       cout=x.C), [x], x.C, 1, 1)
 
     def scale_add(self, x: Sym, gate: Sym, skip: Optional[Sym] = None):
         """x * gate[b, c] (+ skip)   (mobilenetv3.py:111,146)."""
         assert gate.C == x.C and gate.H == 1 and gate.W == 1
-        y = self._sym(x.C, x.H, x.W)
-        self._emit(_PendingOp(type=OP_SCALE_ADD, flags=0, k=(1, 1), stride=1, pad=(0, 0), weight=None, bias=None,
-                              cout=x.C), [x], y, [gate, skip])
-        return y
+        return self._f32_op(_PendingOp(type=OP_SCALE_ADD, flags=0, k=(1, 1), stride=1, pad=(0, 0), weight=None, bias=None,
+                                       cout=x.C), [x], x.C, x.H, x.W, [gate, skip])
 
     def upsample_add(self, x: Sym, skip: Optional[Sym], f: int, relu=False):
         """nearest-neighbour upsample x f of ``x`` (+ skip)(+ReLU)   (pose_higher_hrnet.py:186-187,224-232)."""
-        y = self._sym(x.C, x.H * f, x.W * f)
-        self._emit(_PendingOp(type=OP_UPSAMPLE_ADD, flags=FLAG_RELU if relu else 0, k=(1, 1), stride=f, pad=(0, 0),
-                              weight=None, bias=None, cout=x.C), [x], y, [skip])
-        return y
+        return self._f32_op(_PendingOp(type=OP_UPSAMPLE_ADD, flags=FLAG_RELU if relu else 0, k=(1, 1), stride=f, pad=(0, 0),
+                                       weight=None, bias=None, cout=x.C), [x], x.C, x.H * f, x.W * f, [skip])
 
     def dcn(self, x: Sym, w, b, om_w, om_b, relu=True):
         """DCN module (dcn_v2.py:117-127) with BN already folded into (w, b)."""
@@ -357,17 +482,37 @@ class PlanBuilder:
         om_b32 = torch.zeros(32, dtype=torch.float32, device=om_b.device); om_b32[:27] = om_b.float()
         om = self.conv([x], om_w32, om_b32, stride=1, pad=1, relu=False, out="f32")
         co = w.shape[0]
-        y = self._sym(co, x.H, x.W)
         tc = (self.use_tc and x.kind == "act" and x.C % 64 == 0 and co % 16 == 0 and 32 <= co and x.W >= 8
               and os.environ.get("CPB200_TC_DCN", "1") != "0")
+        island = self.split and not tc
+        xin = self._to_f32(x) if island else x
+        y = self._sym(co, x.H, x.W, "actf32" if island else "act")
+        wp = self._pack_conv_tc(w, 64) if tc else self._pack_conv(w)
         self._emit(_PendingOp(type=OP_DCN, flags=(FLAG_RELU if relu else 0) | (FLAG_TC if tc else 0), k=(3, 3),
-                              stride=1, pad=(1, 1), weight=self._pack_conv_tc(w, 64) if tc else self._pack_conv(w),
-                              bias=self._dev(b), cout=co, w_raw=w), [x], y, [om])
-        return y
+                              stride=1, pad=(1, 1), weight=wp, bias=self._dev(b), cout=co, w_raw=w,
+                              dtype=F32 if island else self.act_dtype,
+                              acc_scale=(1.0 / self._last_scale) if tc else 1.0), [xin], y, [om])
+        return self._to_split(y) if island else y
 
     # ---- finalisation -----------------------------------------------------------------------
     def build(self) -> "Plan":
         return Plan(self)
+
+
+def _esize(pb: "PlanBuilder", kind: str) -> int:
+    """bytes per ELEMENT SLOT of an NHWC tensor of this kind (split activations: two 16-bit planes)."""
+    if kind in ("f32", "actf32"):
+        return 4
+    if kind == "act":
+        return 4 if (pb.act_dtype == F32 or pb.split) else 2
+    raise KeyError(kind)
+
+
+def _ptr_esize(pb: "PlanBuilder", kind: str) -> int:
+    """bytes per element for pointer arithmetic inside ONE plane (channel-slice offsets)."""
+    if kind in ("f32", "actf32"):
+        return 4
+    return 4 if pb.act_dtype == F32 else 2
 
 
 class Plan:
@@ -376,6 +521,7 @@ class Plan:
     def __init__(self, pb: PlanBuilder):
         self.pb = pb
         self.device = pb.device
+        self._prune(pb)
         self._allocate(pb)
         n = len(pb.ops)
         self.ops = (OpStruct * n)()
@@ -383,7 +529,8 @@ class Plan:
         self.out_slots = {}     # output name -> list of op indices writing it
         for i, po in enumerate(pb.ops):
             o = self.ops[i]
-            o.type = po.type; o.flags = po.flags; o.act_dtype = pb.act_dtype
+            o.type = po.type; o.flags = po.flags; o.act_dtype = po.dtype
+            o.acc_scale = float(getattr(po, "acc_scale", 1.0))
             s0 = po.srcs[0]
             o.B, o.H, o.W = pb.B, s0.H, s0.W
             o.nsrc = len(po.srcs)
@@ -392,7 +539,7 @@ class Plan:
                 if s.kind == "nchw_in":
                     self.in_slots.append((i, j))
                 else:
-                    o.src[j] = s.buf.data_ptr() + s.ch_off * (4 if pb.act_dtype == F32 else 2)
+                    o.src[j] = s.buf.data_ptr() + s.ch_off * _ptr_esize(pb, s.kind)
                     o.src_pitch[j] = s.pitch if s.parent is not None else 0
             o.cout = po.cout
             o.kh, o.kw = po.k; o.stride = po.stride; o.pad_h, o.pad_w = po.pad
@@ -428,17 +575,50 @@ class Plan:
         self.n = n
         self._prepared = False
 
+    @staticmethod
+    def _root(s: Sym) -> Sym:
+        while s.parent is not None:
+            s = s.parent
+        return s
+
+    def _prune(self, pb: PlanBuilder):
+        """Split precisions emit a CONVERT back to planes after every fp32-island op; inside a chain of island ops it is
+        dead.  Drop ops whose result nobody reads (outputs, externals and the program's last op are roots) and recompute
+        the producer / last-use indices the allocator works from."""
+        if not pb.split:
+            return
+        ops = pb.ops
+        consumers = {}                                  # id(root sym) -> op indices reading it
+        for i, po in enumerate(ops):
+            for s in list(po.srcs) + [e for e in po.extra if e is not None]:
+                consumers.setdefault(id(self._root(s)), []).append(i)
+        live = [False] * len(ops)
+        for i in range(len(ops) - 1, -1, -1):
+            d = self._root(ops[i].dst)
+            live[i] = i == len(ops) - 1 or d.fixed or any(live[c] for c in consumers.get(id(d), ()) if c > i)
+        pb.ops = [po for i, po in enumerate(ops) if live[i]]
+        for s in pb.syms:
+            s.producer = -1
+            if s.parent is None:
+                s._last_use = -1
+        for i, po in enumerate(pb.ops):
+            for s in list(po.srcs) + [e for e in po.extra if e is not None]:
+                s.last_use = max(s.last_use, i)
+            d = po.dst
+            if d.producer < 0:
+                d.producer = i
+            d.last_use = max(d.last_use, i)
+
     def _allocate(self, pb: PlanBuilder):
         """Liveness-based buffer reuse: a buffer returns to the pool after its last consumer."""
         pool = {}
         release_at = {}
-        esize = {"act": 4 if pb.act_dtype == F32 else 2, "f32": 4}
         self.buffers = []
         total = 0
         for i, po in enumerate(pb.ops):
             d = po.dst
             if not d.fixed and d.buf is None:
-                nbytes = pb.B * d.H * d.W * d.C * esize[d.kind]
+                nbytes = pb.B * d.H * d.W * d.C * _esize(pb, d.kind)
                 cand = [k for k in pool if k >= nbytes and pool[k]]
                 if cand:
                     raw = pool[min(cand)].pop()
@@ -452,12 +632,18 @@ class Plan:
         self.activation_bytes = total
 
     def tensor(self, sym: Sym) -> torch.Tensor:
-        """View of an internal NHWC activation (valid until a later op reuses its buffer)."""
-        dt = torch.float32 if (sym.kind == "f32" or self.pb.act_dtype == F32) else torch.bfloat16
+        """An internal NHWC activation (valid until a later op reuses its buffer): a view, or — split precisions —
+        the fp32 value hi + lo reassembled from the two planes."""
+        pb = self.pb
+        n = pb.B * sym.H * sym.W * sym.C
+        if pb.split and sym.kind == "act":
+            raw = sym.buf if not sym.fixed else sym.buf.view(torch.uint8).view(-1)
+            planes = raw[: 4 * n].view(pb.torch16).view(2, pb.B, sym.H, sym.W, sym.C)
+            return planes[0].float() + planes[1].float()
         if sym.fixed:
             return sym.buf
-        n = self.pb.B * sym.H * sym.W * sym.C
-        return sym.buf[: n * (4 if dt == torch.float32 else 2)].view(dt).view(self.pb.B, sym.H, sym.W, sym.C)
+        dt = torch.float32 if (sym.kind in ("f32", "actf32") or pb.act_dtype == F32) else torch.bfloat16
+        return sym.buf[: n * (4 if dt == torch.float32 else 2)].view(dt).view(pb.B, sym.H, sym.W, sym.C)
 
     def bind(self, x: torch.Tensor, outs: dict):
         """Point the program at this call's input and output tensors."""

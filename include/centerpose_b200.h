@@ -130,6 +130,14 @@ int cpb200_soft_nms_39(float *boxes, int N, float sigma, float Nt, float thresho
  * ---------------------------------------------------------------------------------- */
 #define CPB200_F32 0
 #define CPB200_BF16 1
+/* Split-operand activations ("x2" precisions): every fp32 value v is stored as TWO 16-bit planes, hi = rn16(v) and
+ * lo = rn16(v - hi); a tensor of shape (B,H,W,C) is the hi plane followed by the lo plane, each dense NHWC, i.e. a
+ * (2,B,H,W,C) array.  The tensor-core kernels evaluate a*b as a_hi*b_hi + a_hi*b_lo + a_lo*b_hi into one fp32
+ * accumulator, which reproduces the reference's fp32 arithmetic (dcn_v2_cuda.cu:58 `scalar_t = float`, cuDNN fp32
+ * convs) to ~2^-22 (fp16 planes; activations must stay within +-65504, the epilogues saturate) or ~2^-16 (bf16
+ * planes, full fp32 range).  Weights of such ops are packed as two planes as well (centerpose_b200/plan.py). */
+#define CPB200_BF16X2 2
+#define CPB200_F16X2 3
 
 enum cpb200_op_type {
   CPB200_OP_CONV = 1,        /* k x k conv (+bias)(+residual)(+ReLU); up to 4 channel-concatenated inputs */
@@ -146,8 +154,11 @@ enum cpb200_op_type {
   CPB200_OP_DWCONV = 8,      /* depthwise k x k conv, stride s, pad k/2 (+bias)(+activation); weight fp32 [k*k][C]
                                 (MobileNetV3 Block.conv2, mobilenetv3.py:124-127)                                   */
   CPB200_OP_AVGPOOL = 9,     /* global average pool (B,H,W,C) -> (B,1,1,C)  (SeModule, mobilenetv3.py:100)           */
-  CPB200_OP_SCALE_ADD = 10   /* dst = src[0] * res[b,c] (+ aux skip): SE gate + block shortcut (mobilenetv3.py:111,146);
+  CPB200_OP_SCALE_ADD = 10,  /* dst = src[0] * res[b,c] (+ aux skip): SE gate + block shortcut (mobilenetv3.py:111,146);
                                 `res` is the (B,1,1,C) gate vector                                                  */
+  CPB200_OP_CONVERT = 11     /* NHWC activation (B,H,W,cin[0]) between fp32 and the split 16-bit pair layout named by
+                                act_dtype (CPB200_BF16X2 / CPB200_F16X2): fp32 -> planes, or planes -> fp32 with
+                                CPB200_FLAG_TO_F32.  Lets ops without a native split kernel run on fp32 in between.   */
 };
 /* A dense ConvTranspose2d(k4,s2,p1) (msra_resnet.py:168-193) is lowered by the host into four
  * 2x2 CONV ops, one per output parity, using pad_h/pad_w and the strided-output fields below. */
@@ -158,11 +169,12 @@ enum cpb200_op_type {
 #define CPB200_FLAG_TC 8u            /* run on the tcgen05 tensor-core path (bf16 only)          */
 #define CPB200_FLAG_HSWISH 16u       /* x * relu6(x + 3) / 6 in the epilogue (mobilenetv3.py:84-87)   */
 #define CPB200_FLAG_HSIGMOID 32u     /* relu6(x + 3) / 6 in the epilogue     (mobilenetv3.py:90-93)   */
+#define CPB200_FLAG_TO_F32 64u       /* CPB200_OP_CONVERT direction: split planes -> fp32                    */
 
 typedef struct cpb200_op {
   int32_t type;              /* enum cpb200_op_type */
   uint32_t flags;
-  int32_t act_dtype;         /* CPB200_F32 / CPB200_BF16: dtype of src/res/dst activations */
+  int32_t act_dtype;         /* CPB200_F32 / CPB200_BF16 / CPB200_BF16X2 / CPB200_F16X2: dtype of src/res/dst activations */
   int32_t B, H, W;           /* input batch / spatial size  */
   int32_t Ho, Wo;            /* output spatial size         */
   int32_t nsrc;              /* number of concatenated inputs (1..4) */
@@ -184,10 +196,15 @@ typedef struct cpb200_op {
   int32_t src_pitch[4];      /* channel pitch (elements per pixel) of each input when it is a channel SLICE of a wider NHWC
                                 tensor (src[i] then points at the slice's first channel); 0 = dense (pitch == cin[i]).
                                 Used by the fused head: one 3x3 conv produces all six hidden maps, the 1x1 convs read slices */
+  float acc_scale;           /* split-operand ops: the accumulator is multiplied by this (a power of two) before the bias is
+                                added — the inverse of the scale the host applied to the weights; 0 is read as 1     */
+  int32_t reserved_;
 } cpb200_op;
 
 /* Validate the program and build device-side descriptors (TMA tensor maps) for ops flagged
- * CPB200_FLAG_TC.  Must be called once after the pointers in `ops` are final. */
+ * CPB200_FLAG_TC.  Must be called once after the INPUT activation / weight pointers in `ops` are final (they are
+ * baked into the tensor maps).  `dst`, `res`, `bias`, `aux` and the STEM op's `src[0]` are read from the op at every
+ * cpb200_run_ops call and may be re-pointed between runs (the model binds fresh output tensors per forward). */
 int cpb200_prepare_ops(cpb200_op *ops, int n);
 /* Release what cpb200_prepare_ops attached. */
 int cpb200_release_ops(cpb200_op *ops, int n);

@@ -126,6 +126,21 @@ def gen_dla(ns):
         print(f"dla34 {tag}: oracle max abs err {err:.2e} (scale {scale:.1f})")
 
 
+
+def _ref_dets(ns, ref_maps, oracle_maps):
+    """Reference decode (lib/models/decode.py:235-308 after the sigmoids of lib/detectors/multi_pose.py:35-37) of the
+    reference's own head maps; the oracle's decode of the oracle's maps must agree (end-to-end pin)."""
+    hm, wh, hps, reg, hm_hp, hp_off = [t.clone() for t in ref_maps]
+    dets = ns.multi_pose_decode(hm.sigmoid_(), wh, hps, reg=reg, hm_hp=hm_hp.sigmoid_(), hp_offset=hp_off, K=100).numpy()
+    o_in = [t.numpy() for t in oracle_maps]
+    sig = lambda a: torch.from_numpy(a).sigmoid().numpy()
+    dets_o = decode_ref.multi_pose_decode(sig(o_in[0]), o_in[1], o_in[2], o_in[3], sig(o_in[4]), o_in[5], K=100)
+    from tests.util import match_rows
+    rows, elems = match_rows(dets_o[0], dets[0], tol=1e-3, box_tol=2e-2)
+    assert rows >= 0.99 and elems >= 0.99, ("end-to-end oracle != reference", rows, elems)
+    return dets
+
+
 def gen_res50(ns):
     model, cfg = ref_create_model("res_50_512x512")
     sd = conditioned_state_dict(model.state_dict(), 317)
@@ -140,8 +155,9 @@ def gen_res50(ns):
         scale = max(float(a.abs().max()) for a in ref)
         assert err <= 1e-4 * scale, f"res50 oracle != reference ({err})"
         maps = torch.cat(ref, dim=1).numpy()[:, :, ::stride, ::stride]
+        extra = {"dets": _ref_dets(ns, ref, mine)} if tag == "512" else {}
         np.savez_compressed(os.path.join(GOLD, f"res50_{tag}.npz"), maps=maps.astype(np.float32), stride=np.array(stride),
-                            shape=np.array([B, H, W]), sd_sha=np.array(sd_sha), x_sha=np.array(sha(x.numpy())))
+                            shape=np.array([B, H, W]), sd_sha=np.array(sd_sha), x_sha=np.array(sha(x.numpy())), **extra)
         print(f"res50 {tag}: oracle max abs err {err:.2e} (scale {scale:.1f})")
 
 
@@ -159,8 +175,9 @@ def gen_hrnet(ns):
         scale = max(float(a.abs().max()) for a in ref)
         assert err <= 1e-4 * scale, f"hrnet oracle != reference ({err})"
         maps = torch.cat(ref, dim=1).numpy()[:, :, ::stride, ::stride]
+        extra = {"dets": _ref_dets(ns, ref, mine)} if tag == "512" else {}
         np.savez_compressed(os.path.join(GOLD, f"hrnet32_{tag}.npz"), maps=maps.astype(np.float32), stride=np.array(stride),
-                            shape=np.array([B, H, W]), sd_sha=np.array(sd_sha), x_sha=np.array(sha(x.numpy())))
+                            shape=np.array([B, H, W]), sd_sha=np.array(sd_sha), x_sha=np.array(sha(x.numpy())), **extra)
         print(f"hrnet_w32 {tag}: oracle max abs err {err:.2e} (scale {scale:.1f})")
 
 
@@ -178,8 +195,9 @@ def gen_mbv3(ns):
         scale = max(float(a.abs().max()) for a in ref)
         assert err <= 1e-4 * scale, f"mobilenetv3 oracle != reference ({err})"
         maps = torch.cat(ref, dim=1).numpy()[:, :, ::stride, ::stride]
+        extra = {"dets": _ref_dets(ns, ref, mine)} if tag == "512" else {}
         np.savez_compressed(os.path.join(GOLD, f"mbv3_{tag}.npz"), maps=maps.astype(np.float32), stride=np.array(stride),
-                            shape=np.array([B, H, W]), sd_sha=np.array(sd_sha), x_sha=np.array(sha(x.numpy())))
+                            shape=np.array([B, H, W]), sd_sha=np.array(sd_sha), x_sha=np.array(sha(x.numpy())), **extra)
         print(f"mobilenetv3 {tag}: oracle max abs err {err:.2e} (scale {scale:.1f})")
 
 

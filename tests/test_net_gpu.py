@@ -549,3 +549,85 @@ def test_forward_rejects_cpu_and_training():
     m.train()
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 64, 64, device=DEV))
+
+
+ARCH_GOLD_512 = {"dla_34": "dla34_512", "res_50": "res50_512", "hrnet": "hrnet32_512", "mobilenetv3": "mbv3_512"}
+
+
+@pytest.mark.parametrize("arch", ["res_50", "hrnet", "mobilenetv3"])
+def test_other_backbones_512_vs_reference_golden(arch):
+    """BASELINE.json configs 3-5 at their stated 512x512 shape (experiments/res_50_512x512.yaml:31-36,
+    hrnet_w32_512.yaml, mobilenetv3_512x512.yaml): fp32 path tight against the reference's own head maps and decoded
+    detections; the bf16 tensor-core path's relative L2 and matched-row statistics are reported (bounded loosely)."""
+    from centerpose_b200 import multi_pose_decode
+    from oracle.init_recipe import synth_images
+    from tests.util import match_rows
+    g = np.load(os.path.join(GOLD, ARCH_GOLD_512[arch] + ".npz"))
+    B, H, W = [int(v) for v in g["shape"]]
+    st = int(g["stride"])
+    x = synth_images(B, H, W, 317).to(DEV)
+    m, _ = _model("fp32", arch)
+    outs = m(x)
+    _net_close(torch.cat(outs, dim=1).cpu().numpy()[:, :, ::st, ::st], g["maps"])
+    dets = multi_pose_decode(outs[0], outs[1], outs[2], reg=outs[3], hm_hp=outs[4], hp_offset=outs[5], K=100, apply_sigmoid=True)
+    rows, elems = match_rows(dets[0].cpu().numpy(), g["dets"][0], tol=1e-3, box_tol=2e-2)
+    assert rows >= 0.9 and elems >= 0.97, (rows, elems)
+    m.set_precision("bf16")
+    outs16 = m(x)
+    maps16 = torch.cat(outs16, dim=1).cpu().numpy()[:, :, ::st, ::st]
+    rel = np.linalg.norm(maps16 - g["maps"]) / np.linalg.norm(g["maps"])
+    d16 = multi_pose_decode(outs16[0], outs16[1], outs16[2], reg=outs16[3], hm_hp=outs16[4], hp_offset=outs16[5], K=100, apply_sigmoid=True)
+    r16, e16 = match_rows(d16[0].cpu().numpy(), g["dets"][0], tol=1e-3, box_tol=0.5)
+    print(f"{arch} 512 bf16: relL2 {rel:.3e}, rows matched within 0.5 px {r16:.3f}, elements within 1e-3 on those {e16:.4f}")
+    assert rel <= 4e-2, rel
+
+
+def test_dla34_512_bf16_detection_parity_reported():
+    """End-to-end detection parity of the plain-bf16 tensor-core path on the config image (reported, loosely bounded):
+    how many reference rows have a counterpart within half an output pixel, and the error on those."""
+    from centerpose_b200 import multi_pose_decode
+    from oracle.init_recipe import synth_images
+    from tests.util import match_rows
+    g = np.load(os.path.join(GOLD, "dla34_512.npz"))
+    m, _ = _model("bf16")
+    outs = m(synth_images(1, 512, 512, 317).to(DEV))
+    dets = multi_pose_decode(outs[0], outs[1], outs[2], reg=outs[3], hm_hp=outs[4], hp_offset=outs[5], K=100, apply_sigmoid=True)
+    got = dets[0].cpu().numpy()
+    rows, elems = match_rows(got, g["dets"][0], tol=1e-3, box_tol=0.5)
+    rows_l, elems_l = match_rows(got, g["dets"][0], tol=5e-2, box_tol=0.5)
+    print(f"dla_34 512 bf16: rows matched within 0.5 px {rows:.3f}; elements within 1e-3: {elems:.4f}, within 5e-2: {elems_l:.4f}")
+    assert rows >= 0.5
+
+
+ARCH_BATCH = {"dla_34": 32, "res_50": 16, "hrnet": 16, "mobilenetv3": 64}
+
+
+@pytest.mark.parametrize("arch", ["dla_34", "res_50", "hrnet", "mobilenetv3"])
+def test_batch_consistency_and_output_rebinding(arch):
+    """(1) Image i of a BASELINE-sized batch (32 / 16 / 16 / 64) equals the same image run alone, bit for bit (tiles never
+    mix images).  (2) The tensor-core ops read dst / res / bias from the live op at every launch: a second forward on the
+    SAME plan while the first call's outputs are still held must return independent, correct tensors (round-1 bug:
+    `Plan.bind` re-pointed ops[i].dst after the one-time prepare had cached it)."""
+    from oracle.init_recipe import synth_images
+    B = ARCH_BATCH[arch]
+    m, _ = _model("bf16", arch)
+    x1 = synth_images(B, 128, 160, seed=21).to(DEV)
+    x2 = synth_images(B, 128, 160, seed=22).to(DEV)
+    ref1 = [t.clone() for t in m(x1)]
+    m.invalidate()
+    ref2 = [t.clone() for t in m(x2)]
+    m.invalidate()
+    o1 = m(x1)
+    o2 = m(x2)                       # same plan, o1 still alive
+    o3 = m(x1)
+    for a, b in zip(o1, ref1):
+        assert torch.equal(a, b)
+    for a, b in zip(o2, ref2):
+        assert torch.equal(a, b)
+    for a, b in zip(o3, ref1):
+        assert torch.equal(a, b)
+    assert len({t.data_ptr() for t in o1 + o2 + o3}) == 18
+    for i in (0, B // 2, B - 1):
+        alone = m(x1[i:i + 1])
+        for a, b in zip(ref1, alone):
+            assert torch.equal(a[i:i + 1], b), (arch, i)
