@@ -55,7 +55,7 @@ _DEFAULT = {
     "TEST": {"MODEL_PATH": "", "TASK": "multi_pose", "FLIP_TEST": False, "TEST_SCALES": [1],
              "TOPK": 100, "NMS": False, "FIX_RES": True, "VIS_THRESH": 0.3},
     # additive (not in the reference): activation precision of the CUDA backbone
-    "B200": {"PRECISION": "bf16"},
+    "B200": {"PRECISION": "fp16x2"},      # parity-qualified tensor-core precision; "bf16" = fast mode, "fp32" = CUDA cores
 }
 
 

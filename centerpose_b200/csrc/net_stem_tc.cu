@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) stem_tc_h_kernel(const StemArgs 
             const uint32_t first = (s > 0 || k > 0) ? 1u : 0u;
             if constexpr (P == 2) {
               umma_bf16(d_tmem, ad0 + (uint32_t)(s * 4 + 2 * k), bd0 + (uint32_t)(s * (B_TAP_BYTES >> 4) + 2 * k), idesc2, first);
-              umma_bf16(d_tmem, ad0 + (uint32_t)((HA_PLANE_BYTES >> 4) + s * 4 + 2 * k), bd0 + (uint32_t)(s * (B_TAP_BYTES >> 4) + 2 * k), idesc, 1u);
+              umma_bf16(d_tmem + N, ad0 + (uint32_t)((HA_PLANE_BYTES >> 4) + s * 4 + 2 * k), bd0 + (uint32_t)(s * (B_TAP_BYTES >> 4) + 2 * k), idesc, 1u);
             } else {
               umma_bf16(d_tmem, ad0 + (uint32_t)(s * 4 + 2 * k), bd0 + (uint32_t)(s * (B_TAP_BYTES >> 4) + 2 * k), idesc, first);
             }

@@ -183,7 +183,9 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
                 umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, first);                  // A_hi x W_hi
                 umma_bf16(d_tmem, ad + 2 * k, bd + bplane + 2 * k, idesc, 1u);            // A_hi x W_lo
               }
-              umma_bf16(d_tmem, ad + aplane + 2 * k, bd + 2 * k, idesc, 1u);              // A_lo x W_hi
+              // A_lo x W_hi joins the other small term in the second accumulator half (see net_tc3.cu: the fp32
+              // accumulator truncates per instruction in proportion to its magnitude)
+              umma_bf16(d_tmem + (NCAT ? BN : 0), ad + aplane + 2 * k, bd + 2 * k, idesc, 1u);
             }
           }
           umma_commit(empty0 + 8 * stage);              // frees the smem slot when these MMAs retire
@@ -598,7 +600,8 @@ int tc_prepare_op(cpb200_op &op) {
   a.tiles_h = (op.Ho + a.TH - 1) / a.TH; a.tiles_w = (op.Wo + a.TW - 1) / a.TW;
   int BN = 16;
   while (BN < op.cout && BN < 256) BN <<= 1;
-  if (dcn && P == 2 && BN > 128) BN = 128;     // split DCN: two stages of [A_hi|A_lo|W_hi|W_lo] must fit beside 39 KB of sampling parameters
+  if (P == 2 && BN > 128) BN = 128;            // split operands: two accumulator halves of BN columns each (2 * BN <= 256); also lets two
+                                               // DCN stages of [A_hi|A_lo|W_hi|W_lo] fit beside 39 KB of sampling parameters
   t->BN = BN; t->dcn = dcn;
   a.dcn_src = static_cast<const __nv_bfloat16 *>(op.src[0]); a.dcn_om = static_cast<const float *>(op.aux);
   a.H = op.H; a.W = op.W; a.om_pitch = op.aux_pitch > 0 ? op.aux_pitch : 27;
@@ -674,12 +677,14 @@ int tc_run_op(const cpb200_op &op, cudaStream_t st) {
   case N: return t->P == 2 ? launch_tc<N, D, 2>(*t, args, st) : launch_tc<N, D, 1>(*t, args, st);
   if (t->dcn) {
     switch (t->BN) {
-      TC_CASE(32, true) TC_CASE(64, true) TC_CASE(128, true) TC_CASE(256, true)
+      TC_CASE(32, true) TC_CASE(64, true) TC_CASE(128, true)
+      case 256: if (t->P == 1) return launch_tc<256, true, 1>(*t, args, st); break;
     }
     return fail(CPB200_ERR_STATE, "tc: DCN supports cout 32/64/128/256 tiles only");
   }
   switch (t->BN) {
-    TC_CASE(16, false) TC_CASE(32, false) TC_CASE(64, false) TC_CASE(128, false) TC_CASE(256, false)
+    TC_CASE(16, false) TC_CASE(32, false) TC_CASE(64, false) TC_CASE(128, false)
+    case 256: if (t->P == 1) return launch_tc<256, false, 1>(*t, args, st); break;
   }
 #undef TC_CASE
   return fail(CPB200_ERR_STATE, "tc: bad BN");

@@ -251,7 +251,10 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
                         umma_bf16(d_tmem, ad + 2 * k, bd + btile + 2 * k, idesc, 1u);
                       }
                     } else {
-                      umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, 1u);
+                      // the small cross term joins A_hi x W_lo in the SECOND accumulator half: the tensor core's fp32
+                      // accumulator truncates (round toward zero) at every instruction, an error proportional to the
+                      // accumulator's magnitude — the large hi x hi sum must see as few additions as possible
+                      umma_bf16(d_tmem + (NCAT ? BN : 0), ad + 2 * k, bd + 2 * k, idesc, 1u);
                     }
                   }
                 }
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
                   umma_bf16(d_tmem, adh + 2 * k, bd + 2 * k, idesc, first);
                   umma_bf16(d_tmem, adh + 2 * k, bd + btile + 2 * k, idesc, 1u);
                 }
-                umma_bf16(d_tmem, adl + 2 * k, bd + 2 * k, idesc, 1u);
+                umma_bf16(d_tmem + (NCAT ? BN : 0), adl + 2 * k, bd + 2 * k, idesc, 1u);   // small terms share the second half
               }
               umma_commit(bempty0 + 8 * sb);
             }
@@ -484,7 +487,7 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   const int P = op.act_dtype == CPB200_BF16 ? 1 : 2;
   t->P = P;
   a.fmt = op.act_dtype == CPB200_F16X2 ? 1u : 0u;
-  a.acc_scale = op.acc_scale != 0.f ? op.acc_scale : 1.f;
+  a.acc_scale = (op.acc_scale != 0.f ? op.acc_scale : 1.f);
   a.dst_plane = (long long)op.B * op.Ho * op.Wo * op.cout;
   const int cin = op.cin[0];
   const int bk = (cin % 64 == 0) ? 64 : (cin % 32 == 0) ? 32 : 16;
@@ -496,6 +499,7 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   int BN = 16;
   while (BN < op.cout && BN < 256) BN <<= 1;
   if (const char *e = getenv("CPB200_C3_BN")) { int v = atoi(e); if (v >= BN && v <= 256 && (v & (v - 1)) == 0) BN = v; }   // experiments
+  if (P == 2 && BN > 128) BN = 128;       // split operands: [hi x hi | hi x lo + lo x hi] accumulator halves need 2 * BN <= 256 columns
   t->BN = BN;
   a.n_tiles = (op.cout + BN - 1) / BN;
   a.cout = op.cout; a.cout_store = op.cout;
@@ -572,7 +576,8 @@ int c3_run(const void *h, const cpb200_op &op, cudaStream_t st) {
 #define C3_CASE(N)                                                                                   \
   case N: return t->P == 2 ? launch_c3<N, 2>(*t, args, st) : launch_c3<N, 1>(*t, args, st);
   switch (t->BN) {
-    C3_CASE(16) C3_CASE(32) C3_CASE(64) C3_CASE(128) C3_CASE(256)
+    C3_CASE(16) C3_CASE(32) C3_CASE(64) C3_CASE(128)
+    case 256: if (t->P == 1) return launch_c3<256, 1>(*t, args, st); break;
   }
 #undef C3_CASE
   return fail(CPB200_ERR_STATE, "tc3: bad BN");

@@ -225,8 +225,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_sp_kernel(const SpArgs a) 
                                       : (((r & 1) * 2 + (s & 1)) * G::PLANE_ROWS + (r >> 1) * G::PLANE_W + (s >> 1));
 #pragma unroll
             for (int k = 0; k < C / 16; ++k)
-              umma_bf16(d_tmem, ad0 + (uint32_t)(row0 * (G::PIX_B >> 4) + 2 * k), bd0 + (uint32_t)(tap * (B_TAP_BYTES >> 4) + 2 * k),
-                        (P == 2 && pl == 0) ? idesc2 : idesc, (pl > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              umma_bf16(d_tmem + (pl ? N : 0), ad0 + (uint32_t)(row0 * (G::PIX_B >> 4) + 2 * k), bd0 + (uint32_t)(tap * (B_TAP_BYTES >> 4) + 2 * k),
+                        (P == 2 && pl == 0) ? idesc2 : idesc, (pl > 0 || tap > 0 || k > 0) ? 1u : 0u);   // lo x hi -> second half
           }
           umma_commit(empty0 + 8 * stage);
           if (pl == P - 1) umma_commit(tfull0 + 8 * acc);

@@ -82,7 +82,7 @@ class BackBoneWithHead(nn.Module):
         self.head_conv = int(cfg.MODEL.HEAD_CONV)
         self.head_model = _build_head(inter, self.head_conv)
         b200 = cfg.get("B200", None) if hasattr(cfg, "get") else getattr(cfg, "B200", None)
-        self.precision = (b200 or {}).get("PRECISION", "bf16") if isinstance(b200, dict) else "bf16"
+        self.precision = (b200 or {}).get("PRECISION", "fp16x2") if isinstance(b200, dict) else "fp16x2"
         self._plans = {}
         self.tc = None
         self.eval()
@@ -124,10 +124,13 @@ class BackBoneWithHead(nn.Module):
         plan = self._plans.get(key)
         if plan is None:
             pb = PlanBuilder(B, H, W, self.precision, device, tc=self.tc)
-            sd = self.state_dict()
+            # BatchNorm folding, re-layout and hi/lo splitting of the weights run on the HOST (one-time, a few ms): the
+            # device only ever sees the packed operands, and the process launches no torch kernels before its own
+            host = torch.device("cpu")
+            sd = {k: v.detach().to(host) for k, v in self.state_dict().items()}
             x = pb.input(3)
-            feat = self._arch_mod.lower(pb, StateView(sd, "backbone_model.", device), x)
-            P = StateView(sd, "head_model.", device)
+            feat = self._arch_mod.lower(pb, StateView(sd, "backbone_model.", host), x)
+            P = StateView(sd, "head_model.", host)
 
             def w0_of(name):
                 w0 = P(f"{name}.0.weight").float()

@@ -33,6 +33,23 @@ PRECISIONS = {"fp32": F32, "bf16": BF16, "bf16x2": BF16X2, "fp16x2": F16X2}
 BN_EPS = 1e-5
 
 
+# The tcgen05 fp32 accumulator rounds TOWARD ZERO at every instruction.  For dot products of random-sign operands this
+# shrinks the result by a factor that is linear in the number of K = 16 accumulation steps — measured on B200 with iid
+# Gaussian and post-ReLU operands (tools/rz_probe.py, profiles/r02_rz_probe.log): -1.6e-8 per step with fp16 planes
+# (K = 256 .. 4608, residual 0.6x the coherent part), -1.2e-8 with bf16 planes.  Uncorrected it is the dominant error of
+# the split precisions through a deep network because it is COHERENT: ~40 layers of DLA-34 add up to 7e-5, which the 16
+# chained DCNs amplify to 3e-4 at the heads (profiles/r02_layer_err_*.log).  The host therefore folds the expected
+# factor 1 + beta * K/16 into cpb200_op.acc_scale (a multiplication the epilogue performs anyway).  CPB200_RZ_COMP
+# overrides beta (0 disables); all-positive dot products shrink ~6x more and stay under-corrected.
+RZ_BETA = {"fp16x2": 1.6e-8, "bf16x2": 1.2e-8}
+
+
+def rz_compensation(precision: str, k_total: int) -> float:
+    e = os.environ.get("CPB200_RZ_COMP")
+    beta = float(e) if e is not None else RZ_BETA.get(precision, 0.0)
+    return 1.0 + beta * (k_total / 16.0)
+
+
 def split_planes(t: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
     """fp32 tensor -> (2, ...) stack of 16-bit planes: hi = rn16(t), lo = rn16(t - hi)   (include/centerpose_b200.h)."""
     t = t.float()
@@ -351,7 +368,8 @@ class PlanBuilder:
             wp = self._pack_stem_tc_h(w) if stride == 1 else self._pack_stem_tc(w)
             self._emit(_PendingOp(type=OP_STEM, flags=flags | FLAG_TC, k=(k, k), stride=stride, pad=(pad, pad),
                                   weight=wp, bias=self._dev(b), cout=co,
-                                  acc_scale=1.0 / getattr(self, "_last_scale", 1.0) if stride == 1 else 1.0), [x], y)
+                                  acc_scale=(rz_compensation(self.precision, 7 * 32) / getattr(self, "_last_scale", 1.0))
+                                  if (stride == 1 and self.split) else 1.0), [x], y)
             return y
         y = self._island_sym(co, Ho, Wo)
         wp = self._dev(w.permute(2, 3, 1, 0).reshape(k * k * ci, co))
@@ -400,7 +418,8 @@ class PlanBuilder:
                               weight=wp, bias=self._dev(b), cout=co, ch_off=ch_off,
                               out_map=(Hd, Wd, sy, sx, oy, ox), HoWo=(Ho, Wo), w_raw=w,
                               dtype=F32 if island else self.act_dtype,
-                              acc_scale=(1.0 / self._last_scale) if tc else 1.0), srcs, y, [res])
+                              acc_scale=(rz_compensation(self.precision, kh * kw * ci) / self._last_scale) if (tc and self.split) else 1.0),
+                   srcs, y, [res])
         if island and out == "act" and _island_dst is None:
             return self._to_split(y)
         return y
@@ -491,7 +510,8 @@ class PlanBuilder:
         self._emit(_PendingOp(type=OP_DCN, flags=(FLAG_RELU if relu else 0) | (FLAG_TC if tc else 0), k=(3, 3),
                               stride=1, pad=(1, 1), weight=wp, bias=self._dev(b), cout=co, w_raw=w,
                               dtype=F32 if island else self.act_dtype,
-                              acc_scale=(1.0 / self._last_scale) if tc else 1.0), [xin], y, [om])
+                              acc_scale=(rz_compensation(self.precision, 9 * x.C) / self._last_scale) if (tc and self.split) else 1.0),
+                   [xin], y, [om])
         return self._to_split(y) if island else y
 
     # ---- finalisation -----------------------------------------------------------------------
@@ -615,6 +635,7 @@ class Plan:
         release_at = {}
         self.buffers = []
         total = 0
+        no_reuse = os.environ.get("CPB200_NO_REUSE", "0") == "1"      # diagnostics: keep every intermediate (tools/layer_err.py)
         for i, po in enumerate(pb.ops):
             d = po.dst
             if not d.fixed and d.buf is None:
@@ -628,7 +649,8 @@ class Plan:
                 d.buf = raw
                 release_at.setdefault(d.last_use, []).append(d)
             for s in release_at.pop(i, []):
-                pool.setdefault(s.buf.numel(), []).append(s.buf)
+                if not no_reuse:
+                    pool.setdefault(s.buf.numel(), []).append(s.buf)
         self.activation_bytes = total
 
     def tensor(self, sym: Sym) -> torch.Tensor:
