@@ -786,6 +786,76 @@ __global__ void __launch_bounds__(256) dwdeconv_add_split_kernel(const uint16_t 
   }
 }
 
+// Fast path for the shapes IDAUp uses (k == 2f, f and C/8 powers of two, 256 % (f * C/8) == 0), mirroring
+// dwdeconv_add_fast_kernel: thread = (wo, 8 channels) with 16-byte loads per plane, its four (kh, kw) tap weight vectors
+// live in registers for the whole output row.  ~9 bytes of HBM traffic per output element (skip 4 + x 4/f^2 + out 4).
+__global__ void __launch_bounds__(256) dwdeconv_add_split_fast_kernel(const uint16_t *__restrict__ x, const uint16_t *__restrict__ skip,
+                                                                      uint16_t *__restrict__ y, const float *__restrict__ w, int B, int H, int W,
+                                                                      int C, int Ho, int Wo, int k, int f, int pad, int lf, int lcv, uint32_t fmt) {
+  constexpr int VEC = 8;
+  const int CV = C / VEC;
+  const int b = blockIdx.x / Ho, ho = blockIdx.x % Ho;
+  const int i0 = threadIdx.x;
+  const int wo_first = i0 >> lcv, cv = i0 & (CV - 1);
+  const int kh0 = (ho + pad) & (f - 1), kw0 = (wo_first + pad) & (f - 1);
+  const size_t xplane = (size_t)B * H * W * C, yplane = (size_t)B * Ho * Wo * C;
+  float wt[2][2][VEC];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const float *wp = w + (size_t)((kh0 + a * f) * k + kw0 + c * f) * C + cv * VEC;
+#pragma unroll
+      for (int q = 0; q < VEC; q += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(wp + q));
+        wt[a][c][q] = v.x; wt[a][c][q + 1] = v.y; wt[a][c][q + 2] = v.z; wt[a][c][q + 3] = v.w;
+      }
+    }
+  const uint16_t *xb = x + (size_t)b * H * W * C + cv * VEC;
+  const int hn0 = ho + pad - kh0;                               // >= 0; tap a reads input row (hn0 >> lf) - a
+  const int hi0 = hn0 >> lf;
+  const size_t orow = ((size_t)b * Ho + ho) * Wo;
+  auto ld8 = [&](const uint16_t *p, size_t plane, float (&o)[VEC]) {
+    const uint4 h = __ldg(reinterpret_cast<const uint4 *>(p)), l = __ldg(reinterpret_cast<const uint4 *>(p + plane));
+    const uint32_t hw_[4] = {h.x, h.y, h.z, h.w}, lw_[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 a = Sp16::up(hw_[j], fmt), c = Sp16::up(lw_[j], fmt);
+      o[2 * j] = a.x + c.x; o[2 * j + 1] = a.y + c.y;
+    }
+  };
+  for (int i = i0; i < Wo * CV; i += 256) {
+    const int wo = i >> lcv;
+    const size_t opix = (orow + wo) * C + cv * VEC;
+    float acc[VEC];
+    if (skip) ld8(skip + opix, yplane, acc);
+    else {
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
+    }
+    const int wi0 = (wo + pad - kw0) >> lf;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int hi = hi0 - a;
+      if (hi < 0 || hi >= H) continue;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int wi = wi0 - c;
+        if (wi < 0 || wi >= W) continue;
+        float v[VEC];
+        ld8(xb + ((size_t)hi * W + wi) * C, xplane, v);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc[q] = fmaf(v[q], wt[a][c][q], acc[q]);
+      }
+    }
+    uint4 oh, ol;
+    Sp16::split2(acc[0], acc[1], fmt, oh.x, ol.x); Sp16::split2(acc[2], acc[3], fmt, oh.y, ol.y);
+    Sp16::split2(acc[4], acc[5], fmt, oh.z, ol.z); Sp16::split2(acc[6], acc[7], fmt, oh.w, ol.w);
+    *reinterpret_cast<uint4 *>(y + opix) = oh;
+    *reinterpret_cast<uint4 *>(y + opix + yplane) = ol;
+  }
+}
+
 int run_op_split(const cpb200_op &op, cudaStream_t st) {
   const uint32_t fmt = op.act_dtype == CPB200_F16X2 ? 1u : 0u;
   switch (op.type) {
@@ -809,6 +879,18 @@ int run_op_split(const cpb200_op &op, cudaStream_t st) {
     }
     case CPB200_OP_DWDECONV_ADD: {
       if (op.cin[0] % 4 || op.kh != 2 * op.stride) return cpb::fail(CPB200_ERR_ARG, "dwdeconv (split): needs C %% 4 == 0 and k == 2 * stride");
+      {
+        auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
+        const int C = op.cin[0];
+        const int lf = ilog2(op.stride), lcv = (C % 8 == 0) ? ilog2(C / 8) : -1;
+        const int CVv = C / 8;
+        if (lf >= 0 && lcv >= 0 && CVv <= 256 && (256 / CVv) % op.stride == 0 && getenv("CPB200_DWDECONV_GENERIC") == nullptr) {
+          dwdeconv_add_split_fast_kernel<<<(unsigned)(op.B * op.Ho), 256, 0, st>>>(static_cast<const uint16_t *>(op.src[0]),
+              static_cast<const uint16_t *>(op.aux), static_cast<uint16_t *>(op.dst), static_cast<const float *>(op.weight),
+              op.B, op.H, op.W, C, op.Ho, op.Wo, op.kh, op.stride, op.pad_h, lf, lcv, fmt);
+          return cpb::check_launch("dwdeconv_add_split_fast_kernel");
+        }
+      }
       dwdeconv_add_split_kernel<<<(unsigned)(op.B * op.Ho), 256, 0, st>>>(static_cast<const uint16_t *>(op.src[0]),
           static_cast<const uint16_t *>(op.aux), static_cast<uint16_t *>(op.dst), static_cast<const float *>(op.weight),
           op.B, op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h, fmt);

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
   if (warp == 0 && lane == 0) {
     if (!DCN) for (int s = 0; s < a.nsrc; ++s) tmap_prefetch(&a.amap[s]);
     tmap_prefetch(&a.bmap);
-    for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, DCN ? 1 + DCN_GW * 32 : 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < a.stages; ++s) { mbar_init(full0 + 8 * s, DCN ? 1 + DCN_GW : 1); mbar_init(empty0 + 8 * s, 1); }
     for (int s = 0; s < 8; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -302,7 +302,8 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
           }
           if (k + 1 < nk) issue(tap_n, c0_n);                // next stage's corners fly across the fence / arrive / wait
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(full0 + 8 * stage);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full0 + 8 * stage);       // one arrival per gather warp (512 per-thread arrivals serialise on one word)
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       } else {
@@ -345,14 +346,15 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
             else if (k + 1 < nk) issue(tap_n, c0_n, 0);
             uint32_t oh[4], ol[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) split2(f[2 * j], f[2 * j + 1], a.fmt, oh[j], ol[j]);
+            for (int j = 0; j < 4; ++j) split2_bounded(f[2 * j], f[2 * j + 1], a.fmt, oh[j], ol[j]);   // |blend| <= max|x|: no saturation needed
             const int row = gw * 8 + i * 4 + rsub;
             const uint32_t dst = sa + row * 128 + ((chunk ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(oh[0]), "r"(oh[1]), "r"(oh[2]), "r"(oh[3]) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + a_bytes), "r"(ol[0]), "r"(ol[1]), "r"(ol[2]), "r"(ol[3]) : "memory");
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(full0 + 8 * stage);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(full0 + 8 * stage);       // one arrival per gather warp (512 per-thread arrivals serialise on one word)
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
           tap_c = tap_n; c0_c = c0_n;
         }

@@ -107,6 +107,20 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t fmt, uint32_t 
     hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
   }
 }
+// same without the fp16 saturation, for values known to lie within +-65504 (convex combinations of stored activations)
+__device__ __forceinline__ void split2_bounded(float a, float b, uint32_t fmt, uint32_t &hi, uint32_t &lo) {
+  if (fmt) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
+  }
+}
 __device__ __forceinline__ float2 unpack2(uint32_t v, uint32_t fmt) {
   if (fmt) return __half22float2(*reinterpret_cast<const __half2 *>(&v));
   return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&v));

@@ -26,7 +26,10 @@ def main():
     dev = torch.device("cuda:0")
     spec = OPS[name]
     g = torch.Generator().manual_seed(0)
-    pb = PlanBuilder(B, 512, 512, "bf16", dev, tc=True)
+    prec = os.environ.get("PROF_PREC", "bf16")
+    split = prec in ("fp16x2", "bf16x2")
+    adt = torch.float32 if split else torch.bfloat16          # split precisions: external() takes fp32 and splits it
+    pb = PlanBuilder(B, 512, 512, prec, dev, tc=True)
     flops = 0.0
     if spec[0] == "stem":
         x = torch.randn(B, 3, 512, 512, generator=g).to(dev)
@@ -35,13 +38,13 @@ def main():
         name = name + ("(tc)" if (pb.ops[0].flags & 8 or len(pb.ops) == 2) else "(simt)")
     elif spec[0] == "dcn":
         _, ci, co, hw = spec
-        xin = torch.randn(B, hw, hw, ci, generator=g).to(dev, torch.bfloat16)
+        xin = torch.randn(B, hw, hw, ci, generator=g).to(dev, adt)
         y = pb.dcn(pb.external(xin), torch.randn(co, ci, 3, 3, generator=g).to(dev) * 0.05, torch.zeros(co, device=dev),
                    torch.randn(27, ci, 3, 3, generator=g).to(dev) * 0.01, torch.randn(27, generator=g).to(dev) * 0.5)
         flops = 2.0 * B * hw * hw * co * ci * 9
     else:
         _, ci, co, hw, k, s = spec
-        xin = torch.randn(B, hw, hw, ci, generator=g).to(dev, torch.bfloat16)
+        xin = torch.randn(B, hw, hw, ci, generator=g).to(dev, adt)
         out = "f32" if co == 27 else ("nchw" if co == 34 else "act")
         dst = pb.output(co, hw // s, hw // s, "o") if out == "nchw" else None
         y = pb.conv([pb.external(xin)], torch.randn(co, ci, k, k, generator=g).to(dev) * 0.05, torch.zeros(co, device=dev),
@@ -61,7 +64,7 @@ def main():
         plan.run(st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print(f"PROFOP {name}: {ms * 1e3:.1f} us per plan run ({plan.n} ops), {flops / ms / 1e9:.1f} TFLOP/s on the main op's flops")
+    print(f"PROFOP {name} [{prec}]: {ms * 1e3:.1f} us per plan run ({plan.n} ops), {flops / ms / 1e9:.1f} TFLOP/s on the main op's flops")
 
 
 if __name__ == "__main__":
