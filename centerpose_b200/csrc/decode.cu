@@ -21,8 +21,11 @@
 //            counting) — keypoint-candidate order never reaches the output.  Degenerate inputs
 //            (candidate overflow, massive ties, negative maps) take an exact but slow K-round
 //            arg-max path so results stay defined everywhere.
-//   phase 3  keypoint grouping for joint j is done by whichever of {centre CTA, joint-j CTA}
-//            finishes second (one atomic per pair; deadlock-free, no second launch).
+//   phase 3  keypoint grouping for joint j is done by the joint-j CTA itself, after the centre CTA of its image
+//            has published its K rows (release/acquire flag in the workspace; the centre CTA has the LOWEST block
+//            index of its image, is therefore dispatched first and never waits — no deadlock, no second launch).
+//            Round 1 let whichever CTA of a {centre, joint} pair finished second do the grouping; a centre CTA that
+//            finished last then ran all J groupings serially (~50 of the 120 us the kernel took at B = 32).
 #include "common.cuh"
 
 namespace {
@@ -615,30 +618,32 @@ __global__ void __launch_bounds__(TPB) decode_kernel(const DecodeParams p) {
     __syncthreads();
   }
 
-  // publish this channel's list, then pair up with the partner CTA(s)
+  // publish this channel's list
   float *tv = p.tk_val + ((size_t)b * C1 + ch) * p.K;
   int *ti = p.tk_idx + ((size_t)b * C1 + ch) * p.K;
   for (int i = tid; i < p.K; i += TPB) { tv[i] = s.topv[i]; ti[i] = s.topi[i]; }
-  __threadfence();
+  // One word per image: bit 16 = "centre list published", low bits = joint CTAs finished.  Zero between launches
+  // (the last joint CTA of the image restores it).
+  int *flag = p.sync + (size_t)b * p.J;
   __syncthreads();
-  if (tid == 0) {
-    unsigned todo = 0u;
-    if (is_centre) {
-      for (int j = 0; j < p.J; ++j)
-        if (atomicAdd(&p.sync[(size_t)b * p.J + j], 1) == 1) todo |= (1u << j);
-    } else {
-      if (atomicAdd(&p.sync[(size_t)b * p.J + (ch - 1)], 1) == 1) todo = 1u << (ch - 1);
+  if (is_centre) {
+    if (tid == 0) {
+      __threadfence();                                   // the K rows above are visible before the flag
+      atomicAdd(flag, 1 << 16);
     }
+    return;
+  }
+  if (tid == 0) {
+    // joint CTA: its own list is in shared memory AND in the workspace (group_joint reads the workspace copy, written by
+    // this CTA: visible after the barrier below); wait for the centre rows of this image
+    while ((atomicAdd(flag, 0) >> 16) == 0) __nanosleep(64);
     __threadfence();
-    s.todo_mask = todo;
   }
   __syncthreads();
-  const unsigned todo = s.todo_mask;
-  for (int j = 0; j < p.J; ++j) {
-    if (todo & (1u << j)) {
-      group_joint(s, p, b, j);
-      if (tid == 0) p.sync[(size_t)b * p.J + j] = 0;    // restore the zero state for the next launch
-    }
+  group_joint(s, p, b, ch - 1);
+  if (tid == 0) {
+    const int done = atomicAdd(flag, 1) & 0xffff;
+    if (done == p.J - 1) atomicExch(flag, 0);            // last joint of the image: restore the zero state
   }
 }
 

@@ -86,6 +86,9 @@ def multi_pose_decode(heat, wh, kps, reg=None, hm_hp=None, hp_offset=None, K=100
                 ptr(heat), ptr(wh), ptr(kps), ptr(reg), ptr(hm_hp), ptr(hp_offset), affine.data_ptr(),
                 out.data_ptr(), B, H, W, J, K, 1 if apply_sigmoid else 0, ws.data_ptr(), ws.numel(),
                 torch.cuda.current_stream(dev).cuda_stream)
+    if st != 0:
+        # a failed / aborted launch may leave the workspace's pair counters non-zero: never reuse it
+        _ws_cache.pop((dev.index, torch.cuda.current_stream(dev).cuda_stream, B, J, K), None)
     _lib.check(st, "multi_pose_decode")
     return out
 

@@ -22,7 +22,7 @@ import torch
 from .decode import flip_merge, multi_pose_decode, sigmoid_
 from .image import get_affine_transform, multi_pose_post_process
 from .model import create_model, load_model
-from .soft_nms import soft_nms_39
+from .soft_nms import soft_nms_39, soft_nms_39_cuda
 
 FLIP_IDX = [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10], [11, 12], [13, 14], [15, 16]]   # multi_pose.py:27
 
@@ -44,6 +44,12 @@ class BaseDetector(object):
         self.scales = cfg.TEST.TEST_SCALES
         self.cfg = cfg
         self.pause = True
+        if int(cfg.TEST.TOPK) > 128 or int(cfg.TEST.TOPK) < 1:
+            # the fused decode kernel keeps K candidates per channel on chip (CPB200_DECODE_MAX_K, include/centerpose_b200.h);
+            # the reference accepts any TOPK (lib/models/decode.py:235) — say so here instead of failing at the first image
+            raise ValueError("centerpose_b200: TEST.TOPK must be in 1..128 (got %d); the reference default is 100" % int(cfg.TEST.TOPK))
+        if int(cfg.MODEL.NUM_CLASSES) != 1:
+            raise ValueError("centerpose_b200: multi_pose decoding supports NUM_CLASSES == 1 (COCO person), got %d" % int(cfg.MODEL.NUM_CLASSES))
         b200 = cfg.get("B200", None) if hasattr(cfg, "get") else getattr(cfg, "B200", None)
         # additive: cfg.B200.DEVICE_PREPROCESS (default on) — warp / normalise / transpose on the GPU (same values)
         self.device_preprocess = bool((b200 or {}).get("DEVICE_PREPROCESS", True)) if isinstance(b200, dict) else True
@@ -229,6 +235,23 @@ class MultiPoseDetector(BaseDetector):
             return outputs, dets, forward_time
         return outputs, dets
 
+    def _decode_heads(self, outputs, affine=None):
+        """Decode one forward's head maps with the cfg gating of ``process()`` (multi_pose.py:35-41): REG_OFFSET /
+        REG_HP_OFFSET switch the sub-pixel offsets off, MSE_LOSS means ``hm_hp`` is used raw (no logistic), HM_HP
+        must be on (the reference's decode needs the keypoint heat-maps, decode.py:307).  Leaves ``outputs`` untouched
+        unless a logistic has to be applied to only one of the two heat-maps."""
+        cfg = self.cfg
+        hm, wh, hps, reg, hm_hp, hp_offset = outputs
+        reg = reg if cfg.LOSS.REG_OFFSET else None
+        hp_offset = hp_offset if cfg.LOSS.REG_HP_OFFSET else None
+        if not cfg.LOSS.HM_HP:
+            raise NameError("name 'hm_score' is not defined")       # what the reference raises (decode.py:307)
+        if cfg.LOSS.MSE_LOSS:                                       # hm sigmoid'ed, hm_hp raw
+            hm = sigmoid_(hm.clone())
+            return multi_pose_decode(hm, wh, hps, reg=reg, hm_hp=hm_hp, hp_offset=hp_offset, K=cfg.TEST.TOPK, affine=affine)
+        return multi_pose_decode(hm, wh, hps, reg=reg, hm_hp=hm_hp, hp_offset=hp_offset, K=cfg.TEST.TOPK,
+                                 apply_sigmoid=True, affine=affine)
+
     def post_process(self, dets, meta, scale=1):
         """multi_pose.py:62-71 (single image: a batch is flattened into one image's rows, as there)."""
         dets = dets.detach().cpu().numpy().reshape(1, -1, dets.shape[2])
@@ -252,35 +275,67 @@ class MultiPoseDetector(BaseDetector):
     def show_results(self, debugger, image, results):
         raise NotImplementedError("visualisation (lib/utils/debugger.py) is outside the B200 hot path")
 
-    # -- additive: batched throughput path ---------------------------------------------------
+    # -- additive: batched / device-resident paths ------------------------------------------------
+    def merge_outputs_device(self, detections, nms=None, return_keep=False):
+        """Device-resident ``merge_outputs`` (multi_pose.py:73-79): ``detections`` is a list of CUDA ``(N_i, 56)``
+        tensors of ONE image already in original-image pixels (one per test scale, from the fused decode +
+        back-projection).  Concatenates them and, with ``TEST.NMS`` or several scales, runs ``soft_nms_39`` as ONE CUDA
+        kernel (``cpb200_soft_nms_39``, pinned to the reference's compiled Cython routine).  Like the reference — which
+        ignores the keep list ``soft_nms_39`` returns and hands back the WHOLE array it mutated in place (decayed scores,
+        suppressed rows swapped to the tail) — this returns all rows as a CUDA ``(N, 56)`` tensor; ``return_keep=True``
+        additionally returns how many leading rows survived.  No host round trip until the caller asks for numbers."""
+        rows = torch.cat([d.reshape(-1, d.shape[-1]) for d in detections], dim=0).contiguous().float()
+        if nms is None:
+            nms = bool(self.cfg.TEST.NMS) or len(self.cfg.TEST.TEST_SCALES) > 1
+        keep = rows.shape[0]
+        if nms:
+            keep = soft_nms_39_cuda(rows, Nt=0.5, method=2)
+        return (rows, keep) if return_keep else rows
+
     @torch.no_grad()
     def run_batch(self, images: torch.Tensor, metas=None):
         """images (B,3,H,W) pre-processed (host or device).  Returns the (B,K,56) detections in
         output-grid units on the device, or per-image post-processed dicts when ``metas`` is given."""
         images = images.to(torch.device("cuda"), non_blocking=True)
-        hm, wh, hps, reg, hm_hp, hp_offset = self.model(images)
-        cfg = self.cfg
-        dets = multi_pose_decode(hm, wh, hps, reg=reg if cfg.LOSS.REG_OFFSET else None, hm_hp=hm_hp,
-                                 hp_offset=hp_offset if cfg.LOSS.REG_HP_OFFSET else None,
-                                 K=cfg.TEST.TOPK, apply_sigmoid=True)
+        dets = self._decode_heads(self.model(images))
         if metas is None:
             return dets
         host = dets.cpu().numpy()
         return [self.post_process(torch.from_numpy(host[i:i + 1]), metas[i]) for i in range(host.shape[0])]
 
     @torch.no_grad()
-    def run_batch_fused(self, images: torch.Tensor, metas, scale=1.0):
+    def run_batch_fused(self, images: torch.Tensor, metas, scale=1.0, nms=None):
         """Like ``run_batch(images, metas)`` but with ``post_process`` fused into the decode kernel: returns a
-        ``(B, K, 56)`` float32 numpy array already in original-image pixels (one D2H copy, no host math)."""
+        ``(B, K, 56)`` float32 numpy array already in original-image pixels (one D2H copy, no host math).  With
+        ``TEST.NMS`` (or ``nms=True``) every image's rows additionally go through the CUDA ``soft_nms_39`` on the
+        device (multi_pose.py:73-79: rows re-ordered / scores decayed in place, all K rows returned as the reference does)."""
         from .decode import affine_for_meta
         images = images.to(torch.device("cuda"), non_blocking=True)
-        hm, wh, hps, reg, hm_hp, hp_offset = self.model(images)
-        cfg = self.cfg
         aff = affine_for_meta(metas, scale).to(images.device, non_blocking=True)
-        dets = multi_pose_decode(hm, wh, hps, reg=reg if cfg.LOSS.REG_OFFSET else None, hm_hp=hm_hp,
-                                 hp_offset=hp_offset if cfg.LOSS.REG_HP_OFFSET else None,
-                                 K=cfg.TEST.TOPK, apply_sigmoid=True, affine=aff)
+        dets = self._decode_heads(self.model(images), affine=aff)
+        if nms is None:
+            nms = bool(self.cfg.TEST.NMS)
+        if nms:
+            for i in range(dets.shape[0]):
+                soft_nms_39_cuda(dets[i], Nt=0.5, method=2)          # in place on the image's (K, 56) rows
         return dets.cpu().numpy()
+
+    @torch.no_grad()
+    def run_multiscale_fused(self, image):
+        """Additive: the multi-scale test of ``run()`` (base_detector.py:99-127 with ``TEST_SCALES [1, 2]``-style
+        configs, experiments/hrnet_w32_512.yaml:142) kept on the device end to end: per scale pre_process -> network ->
+        decode with the back-projection fused, then ONE soft-NMS kernel over the concatenated rows.  Returns the merged
+        ``(N, 56)`` rows (numpy) in original-image pixels, like ``run()['results'][1]``."""
+        from .decode import affine_for_meta
+        per_scale = []
+        for scale in self.scales:
+            images, meta = self.pre_process(image, scale, None)
+            images = images.to(torch.device("cuda"), non_blocking=True)
+            if self.cfg.TEST.FLIP_TEST:
+                raise NotImplementedError("run_multiscale_fused: use run() for FLIP_TEST")
+            aff = affine_for_meta([meta], scale).to(images.device, non_blocking=True)
+            per_scale.append(self._decode_heads(self.model(images), affine=aff)[0])
+        return self.merge_outputs_device(per_scale).cpu().numpy()
 
 
 detector_factory = {"multi_pose": MultiPoseDetector}     # detector_factory.py:5-7

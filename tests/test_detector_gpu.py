@@ -125,3 +125,58 @@ def _shared_detector(cfg):
         _DET["d"] = MultiPoseDetector(cfg)
     _DET["d"].cfg = cfg
     return _DET["d"]
+
+
+def test_device_merge_with_cuda_soft_nms_matches_host_path():
+    """run_batch_fused(nms=True) / merge_outputs_device: decode + back-projection + soft_nms_39 entirely on the device
+    vs the host pipeline (post_process in numpy + the pinned host port of lib/external/nms.pyx:172-275).  Same kept
+    rows; values within 2e-3 px (the fused affine evaluates the 2x3 map in fp32)."""
+    from oracle import post_process_ref
+    det, sd, cfg = _detector("fp16x2", nms=True)
+    x = torch.randn(2, 3, 512, 512, generator=torch.Generator().manual_seed(3))
+    metas = [post_process_ref.make_meta(480, 640), post_process_ref.make_meta(720, 1280)]
+    host = det.run_batch(x, metas)                       # per image {1: (100, 56)} in image pixels, no NMS yet
+    fused = det.run_batch_fused(x, metas)                # (B, 100, 56), soft-NMS applied per image on the device
+    assert fused.shape == (2, 100, 56)
+    for i in range(2):
+        want = np.asarray(det.merge_outputs([host[i]]), dtype=np.float32)
+        got = fused[i]
+        assert got.shape == want.shape, (got.shape, want.shape)
+        assert np.abs(got - want).max() <= 2e-3 * max(1.0, np.abs(want).max()), float(np.abs(got - want).max())
+
+
+def test_multiscale_fused_matches_run():
+    """TEST_SCALES [1, 0.75] (the multi-scale merge of lib/detectors/multi_pose.py:73-79): device-resident pipeline vs
+    run() — rows matched on bbox + score (top-K / NMS are discontinuous), then compared."""
+    from tests.util import match_rows
+    det, sd, cfg = _detector("fp16x2")
+    cfg.TEST.TEST_SCALES = [1, 0.75]
+    det.scales = cfg.TEST.TEST_SCALES
+    rng = np.random.RandomState(11)
+    image = rng.randint(0, 256, size=(384, 512, 3)).astype(np.uint8)
+    want = np.asarray(det.run(image)["results"][1], dtype=np.float32)
+    got = det.run_multiscale_fused(image)
+    assert abs(len(got) - len(want)) <= 2
+    rows, elems = match_rows(got, want, tol=2e-3, box_tol=5e-2)
+    assert rows >= 0.97 and elems >= 0.99, (rows, elems)
+
+
+def test_batched_paths_honour_loss_flags_and_topk_is_validated():
+    """run_batch* apply the same cfg gating as process() (MSE_LOSS: hm_hp used raw; REG_* off: +0.5), and a TOPK the
+    fused decode cannot serve is rejected at construction."""
+    from centerpose_b200 import multi_pose_decode
+    from centerpose_b200.config import default_cfg
+    from centerpose_b200.detector import detector_factory
+    det, sd, cfg = _detector("fp16x2")
+    x = torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(5)).cuda()
+    cfg.LOSS.MSE_LOSS = True; cfg.LOSS.REG_OFFSET = False
+    got = det.run_batch(x)
+    hm, wh, hps, reg, hm_hp, hp_off = det.model(x)
+    from centerpose_b200.decode import sigmoid_
+    want = multi_pose_decode(sigmoid_(hm.clone()), wh, hps, reg=None, hm_hp=hm_hp, hp_offset=hp_off, K=100)
+    assert torch.equal(got, want)
+    _, dets = det.process(x)
+    assert torch.equal(dets, want)
+    bad = default_cfg("dla_34"); bad.TEST.TOPK = 200
+    with pytest.raises(ValueError):
+        detector_factory[bad.TEST.TASK](bad)
