@@ -59,6 +59,9 @@ struct alignas(64) C3Args {
   float acc_scale;             // accumulator multiplier (inverse of the host's power-of-two weight scale)
   long long dst_plane;         // elements between the hi and lo planes of dst / res
   unsigned b_tile_bytes;       // bytes of one weight tile (BN x BK x 2); a P = 2 weight stage is [hi tile | lo tile]
+  // CTA pairs (mcast = 1 -> conv3x3_tc_kernel<BN, P, 2>): the two CTAs of a cluster walk the same (pixel-tile pair, N tile)
+  // sequence; every weight operand is split between them (bmap box = BN/2 rows)
+  int mcast, n_pix_tiles;
 };
 
 __device__ __forceinline__ uint64_t desc_sbo(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
@@ -71,9 +74,16 @@ __device__ __forceinline__ uint64_t desc_sbo(uint32_t saddr, uint32_t sbo_bytes,
   return d;
 }
 
-template <int BN, int P>
+// CG = 2: CTA PAIRS (cluster of two, cta_group::2).  One tcgen05.mma then covers 256 output pixels — the two pixel tiles of
+// the pair, each CTA's own halo as its half of A — against weights of which each CTA holds only HALF the rows (its half of
+// B), and is issued by the leader CTA alone.  Per SM that halves the instructions the single issuing thread has to emit
+// (~90 cycles each, the bound for N <= 128) and the shared-memory bytes the tensor core reads and TMA writes for B
+// (ncu on the 64->256 head conv, profiles/r02_ncu_head3x3_fp16x2_cg1.txt: tensor pipe 54 % busy with nothing else
+// saturated and the weight stages full: issue / smem-read bound).  Used for the streamed-weight convs with enough tiles.
+template <int BN, int P, int CG>
 __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_constant__ C3Args a) {
   constexpr bool NCAT = (P == 2) && (2 * BN <= 256);       // hi*[hi;lo] as one N = 2*BN instruction
+  static_assert(CG == 1 || P == 1 || NCAT, "CTA pairs with split operands use the N-concatenated form");
   constexpr int ACC_COLS = NCAT ? 2 * BN : BN;             // TMEM columns per accumulator stage
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -86,6 +96,16 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
   const uint32_t ball = smem_u32(&bars[2 * MAX_NA + 2 * MAX_NB]);
   const uint32_t tfull0 = ball + 8, tempty0 = ball + 8 + 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr bool mc = CG == 2;
+  // Two accumulator stages only (ACC_COLS = 256): tile t+2 reuses the stage tile t is being read out of, so ONE read-out must
+  // fit into ONE tile's MMA time whatever the number of epilogue groups — alternating tiles between the groups does not help
+  // (measured: the 64->256 head conv 420 us, 338 us with the epilogue switched off).  Both groups then share every tile,
+  // each reading half of its column chunks: bf16 head conv 166 -> 161 us together with the single-thread issue loop; with
+  // split operands (two TMEM reads per chunk from eight warps at once) it measured SLOWER, 424 -> 456 us, so P = 2 keeps
+  // the alternating scheme.
+  const bool esplit = P == 1 && a.nacc == 2 && BN >= 32;
+  const uint32_t crank = mc ? cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
   const uint32_t need_cols = (uint32_t)a.nacc * ACC_COLS;
   const uint32_t TMEM_COLS = need_cols <= 32 ? 32u : need_cols <= 64 ? 64u : need_cols <= 128 ? 128u : need_cols <= 256 ? 256u : 512u;
 
@@ -94,38 +114,67 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
     for (int s = 0; s < MAX_NA; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
     for (int s = 0; s < MAX_NB; ++s) { mbar_init(bfull0 + 8 * s, 1); mbar_init(bempty0 + 8 * s, 1); }
     mbar_init(ball, 1);
-    for (int s = 0; s < 8; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, 4); }
+    // accumulator-empty barriers: 4 epilogue warps per tile, 8 when both groups share every tile (esplit); CTA pairs: the
+    // leader's barriers collect the epilogue warps of BOTH CTAs
+    for (int s = 0; s < 8; ++s) { mbar_init(tfull0 + 8 * s, 1); mbar_init(tempty0 + 8 * s, (mc ? 2 : 1) * (esplit ? 8 : 4)); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (mc) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (mc) cluster_sync_all();       // the peer's barriers and tensor memory exist before anything is signalled across
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
   const uint32_t pix_bytes = a.BK * 2;
 
-  auto decode_tile = [&](int t, int &n, int &h0, int &w0, int &nt) {
-    nt = t % a.n_tiles; t /= a.n_tiles;
-    const int tw = t % a.tiles_w; t /= a.tiles_w;
-    const int th = t % a.tiles_h; n = t / a.tiles_h;
+  // it-th tile of this CTA.  Plain: tiles blockIdx.x + it * gridDim.x of (pixel tile, N tile) pairs, N fastest.  CTA pairs: the two
+  // CTAs of a cluster take the two pixel tiles of pair pp = u / n_tiles with the SAME N tile nt = u % n_tiles, u = cluster + it *
+  // clusters; an odd tail pair re-computes the last pixel tile on rank 1 without storing it (valid = false)
+  auto tile_at = [&](int it, int &n, int &h0, int &w0, int &nt, bool &valid) -> bool {
+    int pt;
+    if (!mc) {
+      int t = blockIdx.x + it * gridDim.x;
+      if (t >= a.total_tiles) return false;
+      nt = t % a.n_tiles; pt = t / a.n_tiles; valid = true;
+    } else {
+      const int u = (int)(blockIdx.x >> 1) + it * (int)(gridDim.x >> 1);
+      if (u >= ((a.n_pix_tiles + 1) >> 1) * a.n_tiles) return false;
+      nt = u % a.n_tiles; pt = 2 * (u / a.n_tiles) + (int)crank;
+      valid = pt < a.n_pix_tiles;
+      if (!valid) pt = a.n_pix_tiles - 1;
+    }
+    const int tw = pt % a.tiles_w; pt /= a.tiles_w;
+    const int th = pt % a.tiles_h; n = pt / a.tiles_h;
     h0 = th * TH; w0 = tw * TW;
+    return true;
   };
 
   if (warp == 0) {
     // =============================== halo producer ===============================
     if (elect_one()) {
       int sa = 0; uint32_t pha = 0;
-      for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-        int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
+      int n, h0, w0, nt; bool valid;
+      for (int it = 0; tile_at(it, n, h0, w0, nt, valid); ++it) {
         for (int sl = 0; sl < a.slabs; ++sl) {
 #pragma unroll
           for (int pl = 0; pl < P; ++pl) {                 // plane-granular stages: hi then lo (batch coordinate n + B)
             mbar_wait(aempty0 + 8 * sa, pha ^ 1);
-            mbar_expect_tx(afull0 + 8 * sa, a.a_tx_bytes);
-            tma_load_4d(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, w0 - (a.kw >> 1), h0 - (a.kh >> 1), n + pl * a.B);
+            if constexpr (mc) {
+              // both halos of the pair complete on the LEADER's barrier (its MMA thread is the only consumer)
+              if (leader) mbar_expect_tx(afull0 + 8 * sa, 2 * a.a_tx_bytes);
+              tma_load_4d_cg2(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, w0 - (a.kw >> 1), h0 - (a.kh >> 1), n + pl * a.B);
+            } else {
+              mbar_expect_tx(afull0 + 8 * sa, a.a_tx_bytes);
+              tma_load_4d(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, w0 - (a.kw >> 1), h0 - (a.kh >> 1), n + pl * a.B);
+            }
             if (++sa == a.na) { sa = 0; pha ^= 1; }
           }
         }
@@ -145,16 +194,37 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
                           pl * wplane + tap * a.slabs + sl);
       } else {
         int sb = 0; uint32_t phb = 0;
-        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-          const int nt = t % a.n_tiles;
+        int n, h0, w0, nt; bool valid;
+        for (int it = 0; tile_at(it, n, h0, w0, nt, valid); ++it) {
           for (int sl = 0; sl < a.slabs; ++sl)
             for (int tap = 0; tap < a.taps; ++tap) {
               mbar_wait(bempty0 + 8 * sb, phb ^ 1);
-              mbar_expect_tx(bfull0 + 8 * sb, P * a.b_tx_bytes);
+              if constexpr (mc) {
+                // Each CTA holds HALF of every B operand (bmap box = BN/2 rows), all loads complete on the leader's barrier:
+                //   P = 1: rows [rank*BN/2, +BN/2) of the weight tile;
+                //   P = 2: region Y (BN rows) = the hi plane's tile on rank 0, the lo plane's on rank 1 -> the two halves of the
+                //          2*BN-row operand [W_hi ; W_lo] of A_hi x [W_hi ; W_lo];  region X (BN/2 rows) = rows [rank*BN/2, +BN/2)
+                //          of the hi plane -> this CTA's half of W_hi for A_lo x W_hi.
+                const uint32_t half = a.b_tile_bytes >> 1;
+                const uint32_t sbase = b_base + sb * a.b_stage_bytes;
+                const int blk = tap * a.slabs + sl;
+                if constexpr (P == 1) {
+                  if (leader) mbar_expect_tx(bfull0 + 8 * sb, a.b_tile_bytes);
+                  tma_load_3d_cg2(sbase, &a.bmap, bfull0 + 8 * sb, 0, nt * BN + (int)crank * (BN / 2), blk);
+                } else {
+                  if (leader) mbar_expect_tx(bfull0 + 8 * sb, 3 * a.b_tile_bytes);
+                  const int plane_blk = (int)crank * wplane + blk;
+                  tma_load_3d_cg2(sbase, &a.bmap, bfull0 + 8 * sb, 0, nt * BN, plane_blk);
+                  tma_load_3d_cg2(sbase + half, &a.bmap, bfull0 + 8 * sb, 0, nt * BN + BN / 2, plane_blk);
+                  tma_load_3d_cg2(sbase + 2 * half, &a.bmap, bfull0 + 8 * sb, 0, nt * BN + (int)crank * (BN / 2), blk);
+                }
+              } else {
+                mbar_expect_tx(bfull0 + 8 * sb, P * a.b_tile_bytes);
 #pragma unroll
-              for (int pl = 0; pl < P; ++pl)
-                tma_load_3d(b_base + sb * a.b_stage_bytes + pl * a.b_tile_bytes, &a.bmap, bfull0 + 8 * sb, 0, nt * BN,
-                            pl * wplane + tap * a.slabs + sl);
+                for (int pl = 0; pl < P; ++pl)
+                  tma_load_3d(b_base + sb * a.b_stage_bytes + pl * a.b_tile_bytes, &a.bmap, bfull0 + 8 * sb, 0, nt * BN,
+                              pl * wplane + tap * a.slabs + sl);
+              }
               if (++sb == a.nb) { sb = 0; phb ^= 1; }
             }
         }
@@ -170,7 +240,124 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
     if (a.b_resident) { mbar_wait(ball, 0); tc_fence_after(); }
     const int ksteps = a.BK / 16;
     const uint32_t bstep = a.b_stage_bytes >> 4, pstep = pix_bytes >> 4, btile = a.b_tile_bytes >> 4;
-    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+    int n_, h0_, w0_, nt_; bool valid_;
+    if constexpr (mc) {
+      // ---- CTA pair: the leader issues 256-row MMAs for both CTAs (streamed weights only) ----
+      if (leader) {
+        const uint32_t abf = (P == 1 || a.fmt == 0) ? 1u : 0u;
+        const uint32_t idN = idesc_mn(256, BN, abf), id2N = idesc_mn(256, NCAT ? 2 * BN : BN, abf);
+        for (int it = 0; tile_at(it, n_, h0_, w0_, nt_, valid_); ++it) {
+          mbar_wait(tempty0 + 8 * acc, accphase ^ 1);          // the epilogue warps of BOTH CTAs have drained this accumulator
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+          for (int sl = 0; sl < a.slabs; ++sl) {
+            const int sa_h = sa; const uint32_t pha_h = pha;
+            if (++sa == a.na) { sa = 0; pha ^= 1; }
+            int sa_l = sa_h; uint32_t pha_l = pha_h;
+            if constexpr (P == 2) {
+              sa_l = sa; pha_l = pha;
+              if (++sa == a.na) { sa = 0; pha ^= 1; }
+            }
+            mbar_wait(afull0 + 8 * sa_h, pha_h);               // both CTAs' halos of this slab (and plane) have landed
+            if constexpr (P == 2) mbar_wait(afull0 + 8 * sa_l, pha_l);
+            tc_fence_after();
+            const uint32_t halo_h = a_base + sa_h * a.a_stage_bytes, halo_l = a_base + sa_l * a.a_stage_bytes;
+            for (int tap = 0; tap < a.taps; ++tap) {
+              mbar_wait(bfull0 + 8 * sb, phb);
+              tc_fence_after();
+              if (elect_one()) {
+                const int r = tap / a.kw, s = tap - a.kw * r;
+                const uint32_t toff = (r * a.hw + s) * pix_bytes;
+                const uint64_t adh = desc_sbo(halo_h + toff, a.hw * pix_bytes, a.swizzle_bits);
+                const uint64_t adl = desc_sbo(halo_l + toff, a.hw * pix_bytes, a.swizzle_bits);
+                const uint64_t bdy = desc_sbo(b_base + sb * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint32_t first = (sl > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                  if constexpr (P == 1) {
+                    umma_f16_cg2(d_tmem, adh + 2 * k, bdy + 2 * k, idN, first);
+                  } else {
+                    umma_f16_cg2(d_tmem, adh + 2 * k, bdy + 2 * k, id2N, first);                 // A_hi x [W_hi ; W_lo]
+                    umma_f16_cg2(d_tmem + BN, adl + 2 * k, bdy + btile + 2 * k, idN, 1u);       // A_lo x W_hi -> small-term half
+                  }
+                }
+                umma_commit_cg2(bempty0 + 8 * sb, (uint16_t)3);
+              }
+              __syncwarp();
+              if (++sb == a.nb) { sb = 0; phb ^= 1; }
+            }
+            if (elect_one()) {
+              umma_commit_cg2(aempty0 + 8 * sa_h, (uint16_t)3);
+              if constexpr (P == 2) umma_commit_cg2(aempty0 + 8 * sa_l, (uint16_t)3);
+              if (sl == a.slabs - 1) umma_commit_cg2(tfull0 + 8 * acc, (uint16_t)3);
+            }
+            __syncwarp();
+          }
+          if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
+        }
+      }
+    } else if (!a.b_resident) {
+      // ---- streamed weights: ONE elected thread runs the whole issue loop.  Measured with loads and epilogue switched off
+      // (profiles/r02_head3x3_whatif.md): the loop that re-elected a lane, rebuilt three descriptors and re-converged the warp
+      // for every tap took 1.27k cycles per 8-MMA stage against 0.84k of tensor time — the issuing thread, not the operands,
+      // bounded the streamed convs.  Here the descriptors are templates plus a 14-bit start address, and nothing but the two
+      // mbarrier waits and the MMAs themselves sits between stages.
+      if (elect_one()) {
+        const uint64_t dA = desc_sbo(0u, a.hw * pix_bytes, a.swizzle_bits), dB = desc_sbo(0u, 8 * pix_bytes, a.swizzle_bits);
+        const uint32_t a_lo14 = (a_base & 0x3FFFFu) >> 4, b_lo14 = (b_base & 0x3FFFFu) >> 4;
+        const uint32_t astep = a.a_stage_bytes >> 4, rowstep = (uint32_t)a.hw * pstep;
+        for (int it = 0; tile_at(it, n_, h0_, w0_, nt_, valid_); ++it) {
+          mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+          for (int sl = 0; sl < a.slabs; ++sl) {
+            const int sa_h = sa; const uint32_t pha_h = pha;
+            if (++sa == a.na) { sa = 0; pha ^= 1; }
+            int sa_l = sa_h; uint32_t pha_l = pha_h;
+            if constexpr (P == 2) {
+              sa_l = sa; pha_l = pha;
+              if (++sa == a.na) { sa = 0; pha ^= 1; }
+            }
+            mbar_wait(afull0 + 8 * sa_h, pha_h);
+            if constexpr (P == 2) mbar_wait(afull0 + 8 * sa_l, pha_l);
+            tc_fence_after();
+            const uint64_t ah0 = dA + (a_lo14 + (uint32_t)sa_h * astep), al0 = dA + (a_lo14 + (uint32_t)sa_l * astep);
+            int tap = 0;
+            for (int r = 0; r < a.kh; ++r) {
+              for (int q2 = 0; q2 < a.kw; ++q2, ++tap) {
+                const uint32_t toff = (uint32_t)r * rowstep + (uint32_t)q2 * pstep;
+                mbar_wait(bfull0 + 8 * sb, phb);
+                tc_fence_after();
+                const uint64_t bd = dB + (b_lo14 + (uint32_t)sb * bstep);
+                const uint64_t adh = ah0 + toff, adl = al0 + toff;
+#pragma unroll 4
+                for (int k = 0; k < ksteps; ++k) {
+                  const uint32_t first = (sl > 0 || tap > 0 || k > 0) ? 1u : 0u;
+                  if constexpr (P == 1) {
+                    umma_bf16(d_tmem, adh + 2 * k, bd + 2 * k, idesc, first);
+                  } else {
+                    if constexpr (NCAT) {
+                      umma_bf16(d_tmem, adh + 2 * k, bd + 2 * k, idesc2, first);
+                    } else {
+                      umma_bf16(d_tmem, adh + 2 * k, bd + 2 * k, idesc, first);
+                      umma_bf16(d_tmem, adh + 2 * k, bd + btile + 2 * k, idesc, 1u);
+                    }
+                    umma_bf16(d_tmem + (NCAT ? BN : 0), adl + 2 * k, bd + 2 * k, idesc, 1u);   // small terms share the second half
+                  }
+                }
+                umma_commit(bempty0 + 8 * sb);
+                if (++sb == a.nb) { sb = 0; phb ^= 1; }
+              }
+            }
+            umma_commit(aempty0 + 8 * sa_h);
+            if constexpr (P == 2) umma_commit(aempty0 + 8 * sa_l);
+            if (sl == a.slabs - 1) umma_commit(tfull0 + 8 * acc);
+          }
+          if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
+        }
+      }
+      __syncwarp();
+    } else
+    for (int it = 0; tile_at(it, n_, h0_, w0_, nt_, valid_); ++it) {
       mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
@@ -309,21 +496,22 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
     }
   } else {
-    // =============================== epilogue (two groups of four warps, alternate tiles) ===============================
-    // With N = 256 tiles the read-out of one accumulator (128 x 256 fp32 -> bias, activation, bf16, 512 B per thread)
-    // takes as long as the MMAs of the next tile; two groups working on alternate tiles (= alternate accumulator
-    // stages) keep the tensor pipe from waiting for a free accumulator.
+    // =============================== epilogue (two groups of four warps) ===============================
+    // >= 4 accumulator stages: the groups take alternate tiles (a read-out may then last two tiles' MMA time).
+    // 2 accumulator stages (esplit): both groups read out every tile, half of the column chunks each.
     const int grp = warp >= 7 ? 1 : 0;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int et = grp ? (int)threadIdx.x - 224 : (int)threadIdx.x - 64;
     const uint32_t act = a.flags & CPB_ACT_MASK;
     const bool out_f32 = a.flags & CPB200_FLAG_OUT_F32;
-    int acc = grp; uint32_t accphase = 0;
+    int acc = esplit ? 0 : grp; uint32_t accphase = 0;
     int par = 0;                                            // tile parity within this group (bias double buffer)
     bool bias_loaded = false;
-    for (int t = blockIdx.x + grp * gridDim.x; t < a.total_tiles; t += 2 * gridDim.x) {
-      int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
+    int n, h0, w0, nt; bool valid;
+    const int c_first = esplit ? grp * (BN / 32) : 0, c_last = esplit ? c_first + BN / 32 : BN / 16;
+    const int tstep = esplit ? 1 : 2;
+    for (int it = esplit ? 0 : grp; tile_at(it, n, h0, w0, nt, valid); it += tstep) {
       const int n0 = nt * BN;
       float *sbias = s_bias[grp][par];
       if (a.n_tiles > 1 || !bias_loaded) {      // one N tile: the bias never changes — load it once
@@ -338,11 +526,11 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       mbar_wait(tfull0 + 8 * acc, accphase);
       tc_fence_after();
       const int ho = h0 + (row >> 3), wo = w0 + (row & 7);
-      const bool ok = ho < a.Ho && wo < a.Wo;
+      const bool ok = valid && ho < a.Ho && wo < a.Wo;
       const size_t pix = ((size_t)n * a.Ho + ho) * a.Wo + wo;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
 #pragma unroll 1
-      for (int c = 0; c < BN / 16; ++c) {
+      for (int c = c_first; c < c_last; ++c) {
         uint32_t v[16];
         tmem_ld16(taddr + c * 16, v);
         if constexpr (NCAT) {
@@ -432,17 +620,19 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-      acc += 2; par ^= 1;
+      if (lane == 0) { if constexpr (mc) mbar_arrive_leader(tempty0 + 8 * acc); else mbar_arrive(tempty0 + 8 * acc); }
+      acc += tstep; par ^= 1;
       if (acc >= a.nacc) { acc -= a.nacc; accphase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (mc) cluster_sync_all();       // no CTA leaves while its peer may still signal its barriers / use its tensor memory
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (mc) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -454,9 +644,23 @@ struct C3Op {
 
 template <int BN, int P>
 int launch_c3(const C3Op &t, const C3Args &args, cudaStream_t st) {
+  if constexpr (BN >= 32 && (P == 1 || 2 * BN <= 256)) {
+    if (args.mcast) {                                   // CTA pairs (cta_group::2): cluster of two
+      static SmemAttrCache cache2;
+      if (int rc = ensure_smem(conv3x3_tc_kernel<BN, P, 2>, t.smem, cache2)) return rc;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)t.grid); cfg.blockDim = dim3(C3_THREADS); cfg.dynamicSmemBytes = t.smem; cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      CPB_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc_kernel<BN, P, 2>, args));
+      return cpb::check_launch("conv3x3_tc_kernel");
+    }
+  }
   static SmemAttrCache cache;
-  if (int rc = ensure_smem(conv3x3_tc_kernel<BN, P>, t.smem, cache)) return rc;
-  conv3x3_tc_kernel<BN, P><<<t.grid, C3_THREADS, t.smem, st>>>(args);
+  if (int rc = ensure_smem(conv3x3_tc_kernel<BN, P, 1>, t.smem, cache)) return rc;
+  conv3x3_tc_kernel<BN, P, 1><<<t.grid, C3_THREADS, t.smem, st>>>(args);
   return cpb::check_launch("conv3x3_tc_kernel");
 }
 
@@ -541,6 +745,26 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   }
   const int nsm = num_sms();
   t->grid = a.total_tiles < nsm ? a.total_tiles : nsm;
+  a.n_pix_tiles = op.B * a.tiles_h * a.tiles_w;
+  // streamed weights + enough tiles to keep every pair of SMs busy: CTA pairs (cta_group::2), each CTA holding half of B
+  a.mcast = 0;
+  {
+    // Opt-in (CPB200_C3_CG2=1): correct (tests/test_split_gpu.py::test_conv_cta_pair_path) but not faster than single CTAs —
+    // measured 422 vs 420 us on the 64->256 head conv: the streamed convs were bound by the issuing thread's per-stage
+    // overhead and by the accumulator read-out, neither of which a CTA pair shortens (profiles/r02_head3x3_whatif.md)
+    const char *e = getenv("CPB200_C3_CG2");
+    const bool want = e && e[0] == '1';
+    if (want && !a.b_resident && BN >= 32 && nsm >= 2 && a.n_pix_tiles >= nsm) {
+      a.mcast = 1;
+      t->grid = nsm & ~1;
+      // per-CTA weight stage: P = 1: half a tile;  P = 2: [this CTA's plane tile (BN rows) | its half of the hi tile (BN/2 rows)]
+      a.b_stage_bytes = (((unsigned)(P == 2 ? 3 : 1) * a.b_tile_bytes) / 2 + 1023u) & ~1023u;
+      int nb = (int)((budget - a.na * (size_t)a.a_stage_bytes) / a.b_stage_bytes);
+      if (nb > MAX_NB) nb = MAX_NB;
+      a.nb = nb;
+      t->smem = a.na * (size_t)a.a_stage_bytes + nb * (size_t)a.b_stage_bytes + 1024;
+    }
+  }
   const CUtensorMapDataType dt = a.fmt ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   {
     // split activations: the lo plane follows the hi plane, i.e. a batch of 2B images
@@ -557,7 +781,7 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
     const int cout_pad = (op.cout + 15) / 16 * 16;
     const cuuint64_t dims[3] = {(cuuint64_t)bk, (cuuint64_t)cout_pad, (cuuint64_t)a.taps * (cuuint64_t)a.slabs * P};
     const cuuint64_t strides[2] = {(cuuint64_t)bk * 2, (cuuint64_t)cout_pad * bk * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)BN, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)(a.mcast ? BN / 2 : BN), 1};      // mcast: each CTA loads half the rows
     const cuuint32_t es[3] = {1, 1, 1};
     CUresult r = enc(&a.bmap, dt, 3, const_cast<void *>(op.weight), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -278,3 +278,40 @@ def test_split_batch_consistency_and_rebinding():
         o_i = m(x[i:i + 1])
         for a, b in zip(o_all, o_i):
             assert torch.equal(a[i:i + 1], b), i
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16x2", "bf16x2"])
+@pytest.mark.parametrize("B,ci,co,H,W,res", [(5, 64, 256, 64, 64, False),      # head conv shape: two N tiles, streamed weights
+                                              (11, 128, 128, 48, 40, True),     # 165 pixel tiles: odd pair count (ghost tile), partial tiles
+                                              (10, 256, 256, 32, 32, True)])    # four K slabs
+def test_conv_cta_pair_path(precision, B, ci, co, H, W, res):
+    """3x3 convs big enough (>= 148 pixel tiles, streamed weights) to take the cta_group::2 kernel: CTA pairs, 256-row
+    MMAs issued by the leader CTA, every weight operand split between the two CTAs (csrc/net_tc3.cu, CG = 2)."""
+    g = torch.Generator().manual_seed(B * 7 + ci + co)
+    x = torch.randn(B, ci, H, W, generator=g)
+    w = torch.randn(co, ci, 3, 3, generator=g) / (ci * 9) ** 0.5
+    b = torch.randn(co, generator=g)
+    r = torch.randn(B, co, H, W, generator=g) if res else None
+    if precision == "bf16":
+        x = x.bfloat16().float(); w = w.bfloat16().float()
+        r = r.bfloat16().float() if res else None
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    if res:
+        ref = ref + r.double()
+    ref = F.relu(ref)
+    from centerpose_b200.plan import PlanBuilder
+    os.environ["CPB200_C3_CG2"] = "1"            # read by cpb200_prepare_ops (inside _run)
+    pb = PlanBuilder(B, 1, 1, precision, torch.device(DEV))
+    if precision == "bf16":
+        sx = pb.external(x.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16))
+        sr = pb.external(r.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16)) if res else None
+    else:
+        sx = pb.external(_nhwc(x)); sr = pb.external(_nhwc(r)) if res else None
+    y = pb.conv([sx], w.to(DEV), b.to(DEV), stride=1, pad=1, relu=True, res=sr)
+    try:
+        got = _nchw(_run(pb, y))
+    finally:
+        os.environ.pop("CPB200_C3_CG2", None)
+    err = (got - ref).abs().max().item(); scale = ref.abs().max().item()
+    tol = 1e-2 if precision == "bf16" else OP_TOL[precision]
+    assert err <= tol * scale, (precision, err, scale, err / scale)
