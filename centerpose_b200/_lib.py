@@ -47,15 +47,8 @@ def lib() -> ctypes.CDLL:
     L.cpb200_soft_nms_39.restype = ctypes.c_int
     L.cpb200_soft_nms_39.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
-    _bind_optional(L)
     _lib = L
     return L
-
-
-def _bind_optional(L):
-    """Entry points added by later translation units (network ops) — bound when present."""
-    from . import _lib_net
-    _lib_net.bind(L)
 
 
 def check(status: int, what: str = "centerpose_b200"):
