@@ -45,6 +45,61 @@ template <> struct Act<bf16> {
   __device__ static void st(bf16 *p, float v) { *p = __float2bfloat16_rn(v); }
 };
 
+// ------------------------------------------------------------------------------------------------------------
+// Split-operand activations (CPB200_BF16X2 / CPB200_F16X2): a value is hi + lo, two 16-bit planes `plane` elements apart
+// (include/centerpose_b200.h).  hi + lo is exact in fp32 and split(hi + lo) reproduces the value exactly, so max-pooling
+// and copies are lossless; arithmetic happens in fp32 and the result is re-split.
+struct Sp16 {
+  __device__ static float2 up(uint32_t v, uint32_t fmt) {
+    if (fmt) return __half22float2(*reinterpret_cast<const __half2 *>(&v));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&v));
+  }
+  __device__ static float4 ld4(const uint16_t *p, size_t plane, uint32_t fmt) {
+    const uint2 h = __ldg(reinterpret_cast<const uint2 *>(p)), l = __ldg(reinterpret_cast<const uint2 *>(p + plane));
+    const float2 h0 = up(h.x, fmt), h1 = up(h.y, fmt), l0 = up(l.x, fmt), l1 = up(l.y, fmt);
+    return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
+  }
+  __device__ static void split2(float a, float b, uint32_t fmt, uint32_t &hi, uint32_t &lo) {
+    if (fmt) {
+      a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
+      const __half2 h = __floats2half2_rn(a, b);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+      hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
+    } else {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      const float2 hf = __bfloat1622float2(h);
+      const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+      hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
+    }
+  }
+  __device__ static void st4(uint16_t *p, size_t plane, uint32_t fmt, float4 v) {
+    uint2 h, l;
+    split2(v.x, v.y, fmt, h.x, l.x); split2(v.z, v.w, fmt, h.y, l.y);
+    *reinterpret_cast<uint2 *>(p) = h;
+    *reinterpret_cast<uint2 *>(p + plane) = l;
+  }
+};
+
+
+// Pointer-like handles of split activations, so the element-wise kernels below take fp32, bf16 or split tensors on
+// either side through the same source: `p + n` advances both planes, io_ld4 joins hi + lo, io_st4 re-splits.
+struct SpC {
+  const uint16_t *p; size_t plane; uint32_t fmt;
+  __host__ __device__ SpC operator+(size_t n) const { return SpC{p + n, plane, fmt}; }
+  __host__ __device__ explicit operator bool() const { return p != nullptr; }
+};
+struct SpM {
+  uint16_t *p; size_t plane; uint32_t fmt;
+  __host__ __device__ SpM operator+(size_t n) const { return SpM{p + n, plane, fmt}; }
+};
+__device__ __forceinline__ float4 io_ld4(const float *p) { return Act<float>::ld4(p); }
+__device__ __forceinline__ float4 io_ld4(const bf16 *p) { return Act<bf16>::ld4(p); }
+__device__ __forceinline__ float4 io_ld4(SpC p) { return Sp16::ld4(p.p, p.plane, p.fmt); }
+__device__ __forceinline__ void io_st4(float *p, float4 v) { Act<float>::st4(p, v); }
+__device__ __forceinline__ void io_st4(bf16 *p, float4 v) { Act<bf16>::st4(p, v); }
+__device__ __forceinline__ void io_st4(SpM p, float4 v) { Sp16::st4(p.p, p.plane, p.fmt, v); }
+
 struct ConvArgs {
   const void *src[4];
   int cin[4];
@@ -504,8 +559,8 @@ __global__ void __launch_bounds__(256) dwdeconv_add_fast_kernel(const T *__restr
 // ---- nearest-neighbour upsample x f (+ skip add)(+ReLU), NHWC ----
 // out[b,ho,wo,c] = act(skip[b,ho,wo,c] + x[b,ho/f,wo/f,c])     (HRNet fuse_layers, pose_higher_hrnet.py:186-187,224-232)
 // Thread = 4 channels of one output pixel; f is a power of two (shift).
-template <typename T>
-__global__ void __launch_bounds__(256) upsample_add_kernel(const T *__restrict__ x, const T *__restrict__ skip, T *__restrict__ y,
+template <typename T, typename PI = const T *, typename PO = T *>
+__global__ void __launch_bounds__(256) upsample_add_kernel(PI x, PI skip, PO y,
                                                            long long total, int H, int W, int C4, int Ho, int Wo, int sh, uint32_t act) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
@@ -513,13 +568,13 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(const T *__restrict__
     const int wo = (int)(p % Wo); p /= Wo;
     const int ho = (int)(p % Ho);
     const int b = (int)(p / Ho);
-    float4 v = Act<T>::ld4(x + ((((size_t)b * H + (ho >> sh)) * W + (wo >> sh)) * C4 + c4) * 4);
+    float4 v = io_ld4(x + ((((size_t)b * H + (ho >> sh)) * W + (wo >> sh)) * C4 + c4) * 4);
     if (skip) {
-      const float4 s4 = Act<T>::ld4(skip + (size_t)i * 4);
+      const float4 s4 = io_ld4(skip + (size_t)i * 4);
       v.x += s4.x; v.y += s4.y; v.z += s4.z; v.w += s4.w;
     }
     if (act) { v.x = cpb::act_out<T>(v.x, act); v.y = cpb::act_out<T>(v.y, act); v.z = cpb::act_out<T>(v.z, act); v.w = cpb::act_out<T>(v.w, act); }
-    Act<T>::st4(y + (size_t)i * 4, v);
+    io_st4(y + (size_t)i * 4, v);
   }
 }
 
@@ -527,8 +582,8 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(const T *__restrict__
 // y[b,ho,wo,c] = act(bias[c] + sum_{r,q} x[b, ho*s-p+r, wo*s-p+q, c] * w[r,q,c]).  Thread = VEC channels of one
 // output pixel (VEC * sizeof(T) = 16 bytes); consecutive threads walk the channels of a pixel, so every tap is
 // a coalesced row read that the neighbouring output pixels re-read from L1.  HBM-bound: 2 bytes in + out per MAC x k^2.
-template <typename T, int VEC>
-__global__ void __launch_bounds__(256) dwconv_kernel(const T *__restrict__ x, T *__restrict__ y, const float *__restrict__ w,
+template <typename T, int VEC, typename PI = const T *, typename PO = T *>
+__global__ void __launch_bounds__(256) dwconv_kernel(PI x, PO y, const float *__restrict__ w,
                                                      const float *__restrict__ bias, long long total, int H, int W, int C,
                                                      int Ho, int Wo, int k, int stride, int pad, uint32_t act) {
   const int CV = C / VEC;
@@ -552,21 +607,21 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T *__restrict__ x, T 
       for (int s = 0; s < k; ++s) {
         const int wi = wi0 + s;
         if (wi < 0 || wi >= W) continue;
-        const T *xp = x + (((size_t)b * H + hi) * W + wi) * C + c0;
+        const PI xp = x + (((size_t)b * H + hi) * W + wi) * C + c0;
         const float *wp = w + (size_t)(r * k + s) * C + c0;
 #pragma unroll
         for (int q = 0; q < VEC; q += 4) {
-          const float4 v = Act<T>::ld4(xp + q);
+          const float4 v = io_ld4(xp + q);
           const float4 ww = __ldg(reinterpret_cast<const float4 *>(wp + q));
           acc[q] = fmaf(v.x, ww.x, acc[q]); acc[q + 1] = fmaf(v.y, ww.y, acc[q + 1]);
           acc[q + 2] = fmaf(v.z, ww.z, acc[q + 2]); acc[q + 3] = fmaf(v.w, ww.w, acc[q + 3]);
         }
       }
     }
-    T *o = y + (size_t)i * VEC;
+    const PO o = y + (size_t)i * VEC;
 #pragma unroll
     for (int q = 0; q < VEC; q += 4)
-      Act<T>::st4(o + q, make_float4(cpb::act_out<T>(acc[q], act), cpb::act_out<T>(acc[q + 1], act), cpb::act_out<T>(acc[q + 2], act),
+      io_st4(o + q, make_float4(cpb::act_out<T>(acc[q], act), cpb::act_out<T>(acc[q + 1], act), cpb::act_out<T>(acc[q + 2], act),
                                      cpb::act_out<T>(acc[q + 3], act)));
   }
 }
@@ -574,8 +629,8 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T *__restrict__ x, T 
 // Register-tiled variant for the shapes MobileNetV3 uses (k in {3,5}, stride in {1,2}): a thread produces PXW
 // adjacent output pixels of one row for VEC channels, so each input vector of the row segment is loaded once and
 // each tap's weight vector feeds PXW pixels (the generic kernel above issues 3 loads per tap per pixel).
-template <typename T, int VEC, int K, int S, int PXW>
-__global__ void __launch_bounds__(256) dwconv_tiled_kernel(const T *__restrict__ x, T *__restrict__ y, const float *__restrict__ w,
+template <typename T, int VEC, int K, int S, int PXW, typename PI = const T *, typename PO = T *>
+__global__ void __launch_bounds__(256) dwconv_tiled_kernel(PI x, PO y, const float *__restrict__ w,
                                                            const float *__restrict__ bias, long long total, int H, int W, int C,
                                                            int Ho, int Wo, uint32_t act) {
   constexpr int NIN = (PXW - 1) * S + K, PAD = K / 2;
@@ -599,7 +654,7 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const T *__restrict__
     for (int r = 0; r < K; ++r) {
       const int hi = ho * S - PAD + r;
       if (hi < 0 || hi >= H) continue;
-      const T *xr = x + (((size_t)b * H + hi) * W) * C + c0;
+      const PI xr = x + (((size_t)b * H + hi) * W) * C + c0;
       float in[NIN][VEC];
 #pragma unroll
       for (int j = 0; j < NIN; ++j) {
@@ -607,7 +662,7 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const T *__restrict__
         const bool okw = wi >= 0 && wi < W;
 #pragma unroll
         for (int q = 0; q < VEC; q += 4) {
-          const float4 v = okw ? Act<T>::ld4(xr + (size_t)wi * C + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 v = okw ? io_ld4(xr + ((size_t)wi * C + q)) : make_float4(0.f, 0.f, 0.f, 0.f);
           in[j][q] = v.x; in[j][q + 1] = v.y; in[j][q + 2] = v.z; in[j][q + 3] = v.w;
         }
       }
@@ -630,10 +685,10 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const T *__restrict__
 #pragma unroll
     for (int px = 0; px < PXW; ++px) {
       if (wo0 + px >= Wo) break;
-      T *o = y + ((((size_t)b * Ho + ho) * Wo) + wo0 + px) * C + c0;
+      const PO o = y + (((((size_t)b * Ho + ho) * Wo) + wo0 + px) * C + c0);
 #pragma unroll
       for (int q = 0; q < VEC; q += 4)
-        Act<T>::st4(o + q, make_float4(cpb::act_out<T>(acc[px][q], act), cpb::act_out<T>(acc[px][q + 1], act),
+        io_st4(o + q, make_float4(cpb::act_out<T>(acc[px][q], act), cpb::act_out<T>(acc[px][q + 1], act),
                                        cpb::act_out<T>(acc[px][q + 2], act), cpb::act_out<T>(acc[px][q + 3], act)));
     }
   }
@@ -641,15 +696,15 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const T *__restrict__
 
 // ---- global average pool (B,H,W,C) -> (B,1,1,C)   (SeModule's AdaptiveAvgPool2d(1), mobilenetv3.py:100) ----
 // CTA = (image b, 64-channel chunk): 16 channel quads x 16 pixel lanes, fp32 partial sums, shared-memory tree.
-template <typename T>
-__global__ void __launch_bounds__(256) avgpool_kernel(const T *__restrict__ x, T *__restrict__ y, int HW, int C) {
+template <typename T, typename PI = const T *, typename PO = T *>
+__global__ void __launch_bounds__(256) avgpool_kernel(PI x, PO y, int HW, int C) {
   __shared__ float4 part[16][16];
   const int b = blockIdx.x, cq = blockIdx.y * 16 + (threadIdx.x & 15), lane = threadIdx.x >> 4;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (cq * 4 < C) {
-    const T *xp = x + (size_t)b * HW * C + cq * 4;
+    const PI xp = x + ((size_t)b * HW * C + cq * 4);
     for (int p = lane; p < HW; p += 16) {
-      const float4 v = Act<T>::ld4(xp + (size_t)p * C);
+      const float4 v = io_ld4(xp + (size_t)p * C);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
   }
@@ -658,62 +713,25 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const T *__restrict__ x, T
   if (lane == 0 && cq * 4 < C) {
     for (int l = 1; l < 16; ++l) { const float4 v = part[l][threadIdx.x & 15]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
     const float inv = 1.f / (float)HW;
-    Act<T>::st4(y + (size_t)b * C + cq * 4, make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv));
+    io_st4(y + ((size_t)b * C + cq * 4), make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv));
   }
 }
 
 // ---- y[b,h,w,c] = x[b,h,w,c] * scale[b,c] (+ skip[b,h,w,c])   (SeModule gate + Block shortcut, mobilenetv3.py:111,146) ----
-template <typename T>
-__global__ void __launch_bounds__(256) scale_add_kernel(const T *__restrict__ x, const T *__restrict__ scale, const T *__restrict__ skip,
-                                                        T *__restrict__ y, long long total, long long per_image, int C4) {
+template <typename T, typename PI = const T *, typename PS = const T *, typename PO = T *>
+__global__ void __launch_bounds__(256) scale_add_kernel(PI x, PS scale, PI skip, PO y, long long total, long long per_image, int C4) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int b = (int)(i / per_image), c4 = (int)(i % C4);
-    float4 v = Act<T>::ld4(x + (size_t)i * 4);
-    const float4 g = Act<T>::ld4(scale + ((size_t)b * C4 + c4) * 4);
+    float4 v = io_ld4(x + (size_t)i * 4);
+    const float4 g = io_ld4(scale + ((size_t)b * C4 + c4) * 4);
     v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
     if (skip) {
-      const float4 s4 = Act<T>::ld4(skip + (size_t)i * 4);
+      const float4 s4 = io_ld4(skip + (size_t)i * 4);
       v.x += s4.x; v.y += s4.y; v.z += s4.z; v.w += s4.w;
     }
-    Act<T>::st4(y + (size_t)i * 4, v);
+    io_st4(y + (size_t)i * 4, v);
   }
 }
-
-// ------------------------------------------------------------------------------------------------------------
-// Split-operand activations (CPB200_BF16X2 / CPB200_F16X2): a value is hi + lo, two 16-bit planes `plane` elements apart
-// (include/centerpose_b200.h).  hi + lo is exact in fp32 and split(hi + lo) reproduces the value exactly, so max-pooling
-// and copies are lossless; arithmetic happens in fp32 and the result is re-split.
-struct Sp16 {
-  __device__ static float2 up(uint32_t v, uint32_t fmt) {
-    if (fmt) return __half22float2(*reinterpret_cast<const __half2 *>(&v));
-    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&v));
-  }
-  __device__ static float4 ld4(const uint16_t *p, size_t plane, uint32_t fmt) {
-    const uint2 h = __ldg(reinterpret_cast<const uint2 *>(p)), l = __ldg(reinterpret_cast<const uint2 *>(p + plane));
-    const float2 h0 = up(h.x, fmt), h1 = up(h.y, fmt), l0 = up(l.x, fmt), l1 = up(l.y, fmt);
-    return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
-  }
-  __device__ static void split2(float a, float b, uint32_t fmt, uint32_t &hi, uint32_t &lo) {
-    if (fmt) {
-      a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
-      const __half2 h = __floats2half2_rn(a, b);
-      const float2 hf = __half22float2(h);
-      const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-      hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
-    } else {
-      const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-      const float2 hf = __bfloat1622float2(h);
-      const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-      hi = *reinterpret_cast<const uint32_t *>(&h); lo = *reinterpret_cast<const uint32_t *>(&l);
-    }
-  }
-  __device__ static void st4(uint16_t *p, size_t plane, uint32_t fmt, float4 v) {
-    uint2 h, l;
-    split2(v.x, v.y, fmt, h.x, l.x); split2(v.z, v.w, fmt, h.y, l.y);
-    *reinterpret_cast<uint2 *>(p) = h;
-    *reinterpret_cast<uint2 *>(p + plane) = l;
-  }
-};
 
 // fp32 NHWC <-> split planes (CPB200_OP_CONVERT), 4 elements per thread
 __global__ void __launch_bounds__(256) convert_to_split_kernel(const float *__restrict__ x, uint16_t *__restrict__ y, long long n4, size_t plane, uint32_t fmt) {
@@ -895,6 +913,62 @@ int run_op_split(const cpb200_op &op, cudaStream_t st) {
           static_cast<const uint16_t *>(op.aux), static_cast<uint16_t *>(op.dst), static_cast<const float *>(op.weight),
           op.B, op.H, op.W, op.cin[0], op.Ho, op.Wo, op.kh, op.stride, op.pad_h, fmt);
       return cpb::check_launch("dwdeconv_add_split_kernel");
+    }
+    // The element-wise MobileNetV3 / HRNet ops run their fp32 kernels straight on the planes (SpC / SpM handles):
+    // no fp32 island, no CONVERT passes.  fp32 arithmetic on hi + lo, exact division in the h-swish, result re-split.
+    case CPB200_OP_DWCONV: {
+      constexpr int VEC = 4;
+      const int C = op.cin[0];
+      if (C % VEC || op.kh != op.kw || op.cout != C || (op.src_pitch[0] != 0 && op.src_pitch[0] != C)) return cpb::fail(CPB200_ERR_ARG, "dwconv (split): C %% 4 != 0, non-square kernel or sliced input");
+      const SpC x{static_cast<const uint16_t *>(op.src[0]), (size_t)op.B * op.H * op.W * C, fmt};
+      const SpM y{static_cast<uint16_t *>(op.dst), (size_t)op.B * op.Ho * op.Wo * C, fmt};
+#define DW_TILED(KK, SS, PX)                                                                                   \
+  if (op.kh == KK && op.stride == SS && op.pad_h == KK / 2) {                                                    \
+    const long long tot = (long long)op.B * op.Ho * ((op.Wo + PX - 1) / PX) * (C / VEC);                         \
+    const unsigned g = (unsigned)std::min<long long>((tot + 255) / 256, 148LL * 32);                            \
+    dwconv_tiled_kernel<float, VEC, KK, SS, PX, SpC, SpM><<<g, 256, 0, st>>>(x, y, static_cast<const float *>(op.weight), \
+        op.bias, tot, op.H, op.W, C, op.Ho, op.Wo, op.flags & CPB_ACT_MASK);                                    \
+    return cpb::check_launch("dwconv_tiled_kernel");                                                            \
+  }
+      DW_TILED(3, 1, 4) DW_TILED(5, 1, 4) DW_TILED(3, 2, 2) DW_TILED(5, 2, 2)
+#undef DW_TILED
+      const long long total = (long long)op.B * op.Ho * op.Wo * (C / VEC);
+      const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 32);
+      dwconv_kernel<float, VEC, SpC, SpM><<<grid, 256, 0, st>>>(x, y, static_cast<const float *>(op.weight), op.bias, total,
+          op.H, op.W, C, op.Ho, op.Wo, op.kh, op.stride, op.pad_h, op.flags & CPB_ACT_MASK);
+      return cpb::check_launch("dwconv_kernel");
+    }
+    case CPB200_OP_AVGPOOL: {                           // split planes in, fp32 (B,1,1,C) out: the SE convs that follow run on fp32
+      const int C = op.cin[0];
+      if (C % 4 || op.Ho != 1 || op.Wo != 1 || (op.src_pitch[0] != 0 && op.src_pitch[0] != C)) return cpb::fail(CPB200_ERR_ARG, "avgpool (split): C %% 4 != 0, output not 1x1 or sliced input");
+      const SpC x{static_cast<const uint16_t *>(op.src[0]), (size_t)op.B * op.H * op.W * C, fmt};
+      avgpool_kernel<float, SpC, float *><<<dim3((unsigned)op.B, (unsigned)((C + 63) / 64)), 256, 0, st>>>(x, static_cast<float *>(op.dst), op.H * op.W, C);
+      return cpb::check_launch("avgpool_kernel");
+    }
+    case CPB200_OP_SCALE_ADD: {                         // x, skip, y: split planes; the gate vector (B,1,1,C) is fp32
+      const int C = op.cin[0];
+      if (C % 4 || !op.res || (op.src_pitch[0] != 0 && op.src_pitch[0] != C)) return cpb::fail(CPB200_ERR_ARG, "scale_add (split): C %% 4 != 0, missing scale vector or sliced input");
+      const size_t plane = (size_t)op.B * op.H * op.W * C;
+      const long long per_image = (long long)op.H * op.W * (C / 4), total = per_image * op.B;
+      const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
+      scale_add_kernel<float, SpC, const float *, SpM><<<grid, 256, 0, st>>>(SpC{static_cast<const uint16_t *>(op.src[0]), plane, fmt},
+          static_cast<const float *>(op.res), SpC{static_cast<const uint16_t *>(op.aux), plane, fmt},
+          SpM{static_cast<uint16_t *>(op.dst), plane, fmt}, total, per_image, C / 4);
+      return cpb::check_launch("scale_add_kernel");
+    }
+    case CPB200_OP_UPSAMPLE_ADD: {
+      const int f = op.stride, C = op.cin[0];
+      int sh = 0;
+      while ((1 << sh) < f) ++sh;
+      if (f < 1 || (1 << sh) != f || op.Ho != op.H * f || op.Wo != op.W * f || C % 4 || (op.src_pitch[0] != 0 && op.src_pitch[0] != C))
+        return cpb::fail(CPB200_ERR_ARG, "upsample_add (split): factor %d must be a power of two, C %% 4 == 0, whole-tensor input", f);
+      const size_t plane_o = (size_t)op.B * op.Ho * op.Wo * C;
+      const long long total = (long long)op.B * op.Ho * op.Wo * (C / 4);
+      const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
+      upsample_add_kernel<float, SpC, SpM><<<grid, 256, 0, st>>>(SpC{static_cast<const uint16_t *>(op.src[0]), (size_t)op.B * op.H * op.W * C, fmt},
+          SpC{static_cast<const uint16_t *>(op.aux), plane_o, fmt}, SpM{static_cast<uint16_t *>(op.dst), plane_o, fmt},
+          total, op.H, op.W, C / 4, op.Ho, op.Wo, sh, op.flags & CPB_ACT_MASK);
+      return cpb::check_launch("upsample_add_kernel");
     }
     default:
       return cpb::fail(CPB200_ERR_ARG, "op type %d has no split-precision kernel (the host must route it through fp32)", op.type);

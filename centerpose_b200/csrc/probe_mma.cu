@@ -7,18 +7,23 @@
 namespace {
 using namespace tc;
 
-struct MmaProbeArgs { int n, iters, nacc, stride_bytes; };
+struct MmaProbeArgs { int n, iters, nacc, stride_bytes, a_sbo, a_shift, alt, pipe, ksteps, mode; };
 
 template <int CG>
 __global__ void __launch_bounds__(128, 1) mma_probe_kernel(const MmaProbeArgs a) {
   extern __shared__ __align__(1024) uint8_t raw[];
   const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t ring[16];          // pipe mode: full[0..7], empty[8..15]
   __shared__ uint32_t s_tmem;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 96 * 1024 / 16; i += 128)
     asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + i * 16), "r"(0u) : "memory");
-  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&bar), 1);
+    for (int i = 0; i < 16; ++i) mbar_init(smem_u32(&ring[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (warp == 0) {
     if constexpr (CG == 2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
@@ -40,18 +45,60 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(const MmaProbeArgs a)
       const uint32_t idesc = idesc_mn(128 * CG, a.n, 1u);
       // K-major, 128-byte rows (SW128): A = 128 rows at base, B = n (or n/2 per CTA) rows at base + 32 KB; successive MMAs step
       // through `stride_bytes` so that operand fetches are not all the same lines
-      const uint64_t ad0 = make_desc(base, 128, 2), bd0 = make_desc(base + 32 * 1024, 128, 2);
+      // a_sbo != 0: the A operand is a shifted window of a halo tile (net_tc3.cu): 8-row groups a_sbo bytes apart
+      // (10 pixels x 128 B = 1280 for a 16x8 tile of 64-channel pixels) starting a_shift bytes into the tile.
+      uint64_t ad0 = make_desc(base + (uint32_t)a.a_shift, 128, 2);
+      if (a.a_sbo) ad0 = (ad0 & ~((uint64_t)0x3FFF << 32)) | ((uint64_t)((uint32_t)a.a_sbo >> 4) << 32);
+      const uint64_t bd0 = make_desc(base + 32 * 1024, 128, 2);
+      const uint32_t idesc_half = idesc_mn(128 * CG, a.n / 2, 1u);
+      if (a.pipe > 0 && CG == 1) {
+        // pipe mode: the issue loop of the conv kernels — per "stage" wait a full barrier (armed by the stand-in producer
+        // in warp 2), issue `ksteps` K steps, tcgen05.commit to the stage's empty barrier; `iters` counts stages.
+        // mode bits: 1 = no full-barrier wait, 2 = plain mbarrier.arrive instead of tcgen05.commit, 4 = wait for the NEXT stage's
+        // full barrier before the last K step of this one (its latency then overlaps queued MMAs), 8 = no fence after the wait
+        int stage = 0; uint32_t phase = 0;
+        const bool nowait = a.mode & 1, nocommit = a.mode & 2, early = a.mode & 4, nofence = a.mode & 8;
+        if (early) mbar_wait(smem_u32(&ring[0]), 0);
+        for (int i = 0; i < a.iters; ++i) {
+          if (!nowait && !early) mbar_wait(smem_u32(&ring[stage]), phase);
+          if (!nofence) tc_fence_after();
+          const uint32_t d = tmem + (uint32_t)(i % a.nacc) * (uint32_t)a.n;
+          int nstage = stage + 1; uint32_t nphase = phase;
+          if (nstage == a.pipe) { nstage = 0; nphase ^= 1; }
+          for (int k = 0; k < a.ksteps; ++k) {
+            if (early && k == a.ksteps - 1 && i + 1 < a.iters) mbar_wait(smem_u32(&ring[nstage]), nphase);
+            const uint32_t off = (uint32_t)(k * 32) >> 4;
+            umma_bf16(d, ad0 + off, bd0 + off, idesc, (i >= a.nacc || k > 0) ? 1u : 0u);
+            if (a.alt) umma_bf16(d + (uint32_t)a.n / 2, ad0 + off + 2, bd0 + off, idesc_half, 1u);
+          }
+          if (nocommit) mbar_arrive(smem_u32(&ring[8 + stage]));
+          else umma_commit(smem_u32(&ring[8 + stage]));
+          stage = nstage; phase = nphase;
+        }
+      } else
       for (int i = 0; i < a.iters; ++i) {
         const uint32_t off = ((uint32_t)(i & 3) * (uint32_t)a.stride_bytes) >> 4;
         const uint32_t d = tmem + (uint32_t)(i % a.nacc) * (uint32_t)a.n;
         if constexpr (CG == 2) umma_f16_cg2(d, ad0 + off, bd0 + off, idesc, i >= a.nacc ? 1u : 0u);
-        else umma_bf16(d, ad0 + off, bd0 + off, idesc, i >= a.nacc ? 1u : 0u);
+        else {
+          // alt: the split-operand K step — A_hi x [W_hi|W_lo] (N) followed by A_lo x W_hi (N/2) into the upper half
+          umma_bf16(d, ad0 + off, bd0 + off, idesc, i >= a.nacc ? 1u : 0u);
+          if (a.alt) umma_bf16(d + (uint32_t)a.n / 2, ad0 + off + 2, bd0 + off, idesc_half, 1u);
+        }
       }
       if constexpr (CG == 2) umma_commit_cg2(smem_u32(&bar), (uint16_t)1);
       else umma_commit(smem_u32(&bar));
     }
     __syncwarp();
     mbar_wait(smem_u32(&bar), 0);
+  }
+  if (warp == 2 && a.pipe > 0 && CG == 1 && (threadIdx.x & 31) == 0) {
+    int stage = 0; uint32_t phase = 0;
+    for (int i = 0; i < a.iters; ++i) {
+      mbar_wait(smem_u32(&ring[8 + stage]), phase ^ 1);
+      mbar_arrive(smem_u32(&ring[stage]));
+      if (++stage == a.pipe) { stage = 0; phase ^= 1; }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -64,10 +111,24 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(const MmaProbeArgs a)
 }
 }  // namespace
 
+extern "C" int cpb200_probe_mma_ex(int n, int cg, int iters, int nacc, int stride_bytes, int a_sbo, int a_shift, int alt, void *stream);
+extern "C" int cpb200_probe_mma_pipe(int n, int iters, int nacc, int alt, int stages, int ksteps, int mode, void *stream);
 extern "C" int cpb200_probe_mma(int n, int cg, int iters, int nacc, int stride_bytes, void *stream) {
-  if (n < 16 || n > 256 || n % 16 || (cg != 1 && cg != 2) || nacc < 1 || nacc * n > 512 || iters < 1)
+  return cpb200_probe_mma_ex(n, cg, iters, nacc, stride_bytes, 0, 0, 0, stream);
+}
+static int g_pipe = 0, g_ksteps = 0, g_mode = 0;
+extern "C" int cpb200_probe_mma_pipe(int n, int iters, int nacc, int alt, int stages, int ksteps, int mode, void *stream) {
+  if (stages < 1 || stages > 8 || ksteps < 1 || ksteps > 64) return cpb::fail(CPB200_ERR_ARG, "probe_mma_pipe: bad arguments");
+  g_pipe = stages; g_ksteps = ksteps; g_mode = mode;
+  const int rc = cpb200_probe_mma_ex(n, 1, iters, nacc, 32, 0, 0, alt, stream);
+  g_pipe = 0; g_ksteps = 0; g_mode = 0;
+  return rc;
+}
+extern "C" int cpb200_probe_mma_ex(int n, int cg, int iters, int nacc, int stride_bytes, int a_sbo, int a_shift, int alt, void *stream) {
+  if (n < 16 || n > 256 || n % 32 || (cg != 1 && cg != 2) || nacc < 1 || nacc * n > 512 || iters < 1 || a_sbo % 16 || a_shift % 16 ||
+      a_sbo > 1536 || a_shift > 4096)
     return cpb::fail(CPB200_ERR_ARG, "probe_mma: bad arguments");
-  MmaProbeArgs a{n, iters, nacc, stride_bytes};
+  MmaProbeArgs a{n, iters, nacc, stride_bytes, a_sbo, a_shift, alt, g_pipe, g_ksteps, g_mode};
   const size_t smem = 100 * 1024;
   const int sms = tc::num_sms() & ~1;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

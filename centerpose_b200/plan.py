@@ -92,7 +92,7 @@ class OpStruct(ctypes.Structure):
 
 class Sym:
     """Symbolic activation tensor (NHWC unless kind says otherwise)."""
-    __slots__ = ("C", "H", "W", "kind", "name", "_buf", "producer", "_last_use", "fixed", "parent", "ch_off", "_f32", "_sp")
+    __slots__ = ("C", "H", "W", "kind", "name", "_buf", "producer", "_last_use", "fixed", "parent", "ch_off", "_f32", "_sp", "keep")
 
     def __init__(self, C, H, W, kind="act", name="", parent=None, ch_off=0):
         self.C, self.H, self.W, self.kind, self.name = C, H, W, kind, name
@@ -104,6 +104,7 @@ class Sym:
         self.ch_off = ch_off
         self._f32 = None         # split precisions: cached fp32 copy / split copy of this activation
         self._sp = None
+        self.keep = False        # PlanBuilder.keep_result(): never pruned, buffer never recycled (tests / diagnostics read it)
 
     # a slice lives in its parent's buffer and keeps the parent alive
     @property
@@ -187,6 +188,17 @@ class PlanBuilder:
         s = self._sym(C, H, W, kind, "external")
         s.fixed = True
         s.buf = split_planes(t, self.torch16) if (self.split and kind == "act") else t
+        return s
+
+    def keep_result(self, s: Sym) -> Sym:
+        """mark an intermediate as a program result: its producer is not pruned and its buffer is not recycled."""
+        self._root_of(s).keep = True
+        return s
+
+    @staticmethod
+    def _root_of(s: Sym) -> Sym:
+        while s.parent is not None:
+            s = s.parent
         return s
 
     def output(self, C, H, W, name):
@@ -469,30 +481,54 @@ class PlanBuilder:
         self._emit(op, srcs, y, list(extra))
         return self._to_split(y)
 
+    def _native_split(self, *syms) -> bool:
+        """split mode and every operand a whole split-plane tensor: the element-wise kernels then read / write the planes
+        directly (csrc/net_simt.cu: SpC / SpM handles) and no fp32 island is needed."""
+        return self.split and all(s is None or (s.kind == "act" and s.parent is None) for s in syms)
+
     def dwconv(self, x: Sym, w, b, stride=1, act=None):
         """depthwise conv, w (C,1,k,k) BN-folded, pad k//2   (mobilenetv3.py:124-127)."""
         C, _, k, _ = w.shape
         assert C == x.C
         Ho = (x.H + 2 * (k // 2) - k) // stride + 1; Wo = (x.W + 2 * (k // 2) - k) // stride + 1
         wp = self._dev(w.float().reshape(C, k * k).t())          # [k*k][C]
-        return self._f32_op(_PendingOp(type=OP_DWCONV, flags=_ACT_FLAG[act], k=(k, k), stride=stride, pad=(k // 2, k // 2),
-                                       weight=wp, bias=self._dev(b), cout=C), [x], C, Ho, Wo)
+        op = _PendingOp(type=OP_DWCONV, flags=_ACT_FLAG[act], k=(k, k), stride=stride, pad=(k // 2, k // 2),
+                        weight=wp, bias=self._dev(b), cout=C)
+        if self._native_split(x):
+            y = self._sym(C, Ho, Wo, "act")
+            self._emit(op, [x], y)
+            return y
+        return self._f32_op(op, [x], C, Ho, Wo)
 
     def avgpool(self, x: Sym):
-        """global average pool -> (C, 1, 1)   (mobilenetv3.py:100)."""
-        return self._f32_op(_PendingOp(type=OP_AVGPOOL, flags=0, k=(x.H, x.W), stride=1, pad=(0, 0), weight=None, bias=None,
-                                       cout=x.C), [x], x.C, 1, 1)
+        """global average pool -> (C, 1, 1)   (mobilenetv3.py:100).  Split mode: planes in, fp32 out (the 1x1-map SE convs
+        that follow run on fp32 anyway)."""
+        op = _PendingOp(type=OP_AVGPOOL, flags=0, k=(x.H, x.W), stride=1, pad=(0, 0), weight=None, bias=None, cout=x.C)
+        if self._native_split(x):
+            y = self._island_sym(x.C, 1, 1)
+            self._emit(op, [x], y)
+            return self._to_split(y)                                # dead unless someone wants the planes; pruned
+        return self._f32_op(op, [x], x.C, 1, 1)
 
     def scale_add(self, x: Sym, gate: Sym, skip: Optional[Sym] = None):
-        """x * gate[b, c] (+ skip)   (mobilenetv3.py:111,146)."""
+        """x * gate[b, c] (+ skip)   (mobilenetv3.py:111,146).  Split mode: x / skip / result are planes, the gate is fp32."""
         assert gate.C == x.C and gate.H == 1 and gate.W == 1
-        return self._f32_op(_PendingOp(type=OP_SCALE_ADD, flags=0, k=(1, 1), stride=1, pad=(0, 0), weight=None, bias=None,
-                                       cout=x.C), [x], x.C, x.H, x.W, [gate, skip])
+        op = _PendingOp(type=OP_SCALE_ADD, flags=0, k=(1, 1), stride=1, pad=(0, 0), weight=None, bias=None, cout=x.C)
+        if self._native_split(x, skip) and gate.parent is None:
+            y = self._sym(x.C, x.H, x.W, "act")
+            self._emit(op, [x], y, [self._to_f32(gate), skip])
+            return y
+        return self._f32_op(op, [x], x.C, x.H, x.W, [gate, skip])
 
     def upsample_add(self, x: Sym, skip: Optional[Sym], f: int, relu=False):
         """nearest-neighbour upsample x f of ``x`` (+ skip)(+ReLU)   (pose_higher_hrnet.py:186-187,224-232)."""
-        return self._f32_op(_PendingOp(type=OP_UPSAMPLE_ADD, flags=FLAG_RELU if relu else 0, k=(1, 1), stride=f, pad=(0, 0),
-                                       weight=None, bias=None, cout=x.C), [x], x.C, x.H * f, x.W * f, [skip])
+        op = _PendingOp(type=OP_UPSAMPLE_ADD, flags=FLAG_RELU if relu else 0, k=(1, 1), stride=f, pad=(0, 0),
+                        weight=None, bias=None, cout=x.C)
+        if self._native_split(x, skip):
+            y = self._sym(x.C, x.H * f, x.W * f, "act")
+            self._emit(op, [x], y, [skip])
+            return y
+        return self._f32_op(op, [x], x.C, x.H * f, x.W * f, [skip])
 
     def dcn(self, x: Sym, w, b, om_w, om_b, relu=True):
         """DCN module (dcn_v2.py:117-127) with BN already folded into (w, b)."""
@@ -615,7 +651,7 @@ class Plan:
         live = [False] * len(ops)
         for i in range(len(ops) - 1, -1, -1):
             d = self._root(ops[i].dst)
-            live[i] = i == len(ops) - 1 or d.fixed or any(live[c] for c in consumers.get(id(d), ()) if c > i)
+            live[i] = i == len(ops) - 1 or d.fixed or d.keep or any(live[c] for c in consumers.get(id(d), ()) if c > i)
         pb.ops = [po for i, po in enumerate(ops) if live[i]]
         for s in pb.syms:
             s.producer = -1
@@ -647,7 +683,8 @@ class Plan:
                     raw = torch.empty(nbytes, dtype=torch.uint8, device=pb.device)
                     self.buffers.append(raw); total += nbytes
                 d.buf = raw
-                release_at.setdefault(d.last_use, []).append(d)
+                if not d.keep:
+                    release_at.setdefault(d.last_use, []).append(d)
             for s in release_at.pop(i, []):
                 if not no_reuse:
                     pool.setdefault(s.buf.numel(), []).append(s.buf)

@@ -264,6 +264,41 @@ def test_network_split_512_end_to_end(precision, arch, tag):
         assert rows >= 0.9 and elems >= 0.95, (rows, elems)
 
 
+@pytest.mark.parametrize("precision", PRECS)
+def test_elementwise_ops_on_planes(precision):
+    """CPB200_OP_DWCONV / AVGPOOL / SCALE_ADD / UPSAMPLE_ADD take split planes directly (no fp32 island: the program holds
+    no CONVERT): fp32 arithmetic on hi + lo, result re-split   (mobilenetv3.py:84-147, pose_higher_hrnet.py:186-232)."""
+    from centerpose_b200.plan import OP_CONVERT
+    from oracle.mobilenet_ref import hswish
+    g = torch.Generator().manual_seed(23)
+    B, C, H, W = 2, 48, 13, 18
+    x = torch.randn(B, C, H, W, generator=g) * 2
+    for k, stride, act, fn in ((3, 1, "relu", F.relu), (5, 2, "hswish", hswish), (5, 1, None, lambda t: t), (3, 2, "hswish", hswish),
+                                (7, 1, "relu", F.relu)):
+        w = torch.randn(C, 1, k, k, generator=g) * 0.3; b = torch.randn(C, generator=g)
+        pb = _builder(B, precision)
+        y = pb.dwconv(pb.external(_nhwc(x)), w.to(DEV), b.to(DEV), stride=stride, act=act)
+        assert [o.type for o in pb.ops] == [8] and pb.ops[0].dtype == pb.act_dtype
+        _close(_nchw(_run(pb, y)), fn(F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=k // 2, groups=C)), precision, f"dwconv k{k} s{stride}")
+    gate = torch.rand(B, C, 1, 1, generator=g); skip = torch.randn(B, C, H, W, generator=g)
+    for with_skip in (True, False):
+        pb = _builder(B, precision)
+        sx = pb.external(_nhwc(x))
+        pooled = pb.keep_result(pb._to_f32(pb.avgpool(sx)))                 # planes in, fp32 (B,1,1,C) out
+        y = pb.scale_add(sx, pb.external(_nhwc(gate)), pb.external(_nhwc(skip)) if with_skip else None)
+        plan = pb.build(); plan.run(torch.cuda.current_stream().cuda_stream); torch.cuda.synchronize()
+        assert sum(o.type == OP_CONVERT for o in plan.pb.ops) == 1    # only the externally supplied gate is converted to fp32
+        _close(_nchw(plan.tensor(pooled)), x.double().mean(dim=(2, 3), keepdim=True), precision, "avgpool")
+        _close(_nchw(plan.tensor(y)), x.double() * gate.double() + (skip.double() if with_skip else 0), precision, "scale_add")
+    for f, relu, with_skip in ((2, True, True), (4, False, True), (8, True, False)):
+        xt = torch.randn(B, 32, 5, 7, generator=g); st = torch.randn(B, 32, 5 * f, 7 * f, generator=g)
+        pb = _builder(B, precision)
+        y = pb.upsample_add(pb.external(_nhwc(xt)), pb.external(_nhwc(st)) if with_skip else None, f, relu=relu)
+        assert [o.type for o in pb.ops] == [7]
+        ref = F.interpolate(xt.double(), scale_factor=f, mode="nearest") + (st.double() if with_skip else 0)
+        _close(_nchw(_run(pb, y)), F.relu(ref) if relu else ref, precision, f"upsample_add x{f}")
+
+
 def test_split_batch_consistency_and_rebinding():
     """Image i of a batch == the same image alone (bit for bit), and a second forward on the same plan with the first
     call's outputs still held returns independent, correct tensors (outputs are re-bound per call)."""
