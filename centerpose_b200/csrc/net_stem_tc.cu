@@ -210,8 +210,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const StemArgs a
             ob1[j] = __floats2bfloat162_rn(cpb::act_out<__nv_bfloat16>(__uint_as_float(v[8 + 2 * j]) + s_bias[c * 16 + 8 + 2 * j], a.act),
                                            cpb::act_out<__nv_bfloat16>(__uint_as_float(v[8 + 2 * j + 1]) + s_bias[c * 16 + 8 + 2 * j + 1], a.act));
           }
-          reinterpret_cast<uint4 *>(o + c * 16)[0] = o0;
-          reinterpret_cast<uint4 *>(o + c * 16)[1] = o1;
+          { const uint32_t ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w}; st_global_32B(o + c * 16, ow); }
         }
       }
       tc_fence_before();
@@ -446,10 +445,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) stem_tc_h_kernel(const StemArgs 
               split2(cpb::act_fn(x0, a.act), cpb::act_fn(x1, a.act), a.fmt, oh[j], ol[j]);
             }
             uint16_t *op_ = reinterpret_cast<uint16_t *>(o) + c * 16;
-            reinterpret_cast<uint4 *>(op_)[0] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-            reinterpret_cast<uint4 *>(op_)[1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
-            reinterpret_cast<uint4 *>(op_ + a.y_plane)[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-            reinterpret_cast<uint4 *>(op_ + a.y_plane)[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+            st_global_32B(op_, oh);
+            st_global_32B(op_ + a.y_plane, ol);
           }
           continue;
         }
@@ -464,8 +461,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) stem_tc_h_kernel(const StemArgs 
             ob1[j] = __floats2bfloat162_rn(cpb::act_out<__nv_bfloat16>(__uint_as_float(v[8 + 2 * j]) + s_bias[c * 16 + 8 + 2 * j], a.act),
                                            cpb::act_out<__nv_bfloat16>(__uint_as_float(v[8 + 2 * j + 1]) + s_bias[c * 16 + 8 + 2 * j + 1], a.act));
           }
-          reinterpret_cast<uint4 *>(o + c * 16)[0] = o0;
-          reinterpret_cast<uint4 *>(o + c * 16)[1] = o1;
+          { const uint32_t ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w}; st_global_32B(o + c * 16, ow); }
         }
       }
       tc_fence_before();

@@ -415,11 +415,20 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
           } else if (out_f32) {
             float *o = static_cast<float *>(a.dst) + pix * a.cout_store + nb;
             if (nb + 16 <= a.cout && (a.cout_store & 3) == 0) {
+              if (act) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                float4 v4 = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                if (act) { v4.x = cpb::act_out<__nv_bfloat16>(v4.x, act); v4.y = cpb::act_out<__nv_bfloat16>(v4.y, act); v4.z = cpb::act_out<__nv_bfloat16>(v4.z, act); v4.w = cpb::act_out<__nv_bfloat16>(v4.w, act); }
-                *reinterpret_cast<float4 *>(o + j) = v4;
+                for (int j = 0; j < 16; ++j) f[j] = cpb::act_out<__nv_bfloat16>(f[j], act);
+              }
+              if ((a.cout_store & 7) == 0) {            // 32-byte rows: two sector-sized stores
+#pragma unroll
+                for (int j = 0; j < 16; j += 8) {
+                  const uint32_t ow[8] = {__float_as_uint(f[j]), __float_as_uint(f[j + 1]), __float_as_uint(f[j + 2]), __float_as_uint(f[j + 3]),
+                                          __float_as_uint(f[j + 4]), __float_as_uint(f[j + 5]), __float_as_uint(f[j + 6]), __float_as_uint(f[j + 7])};
+                  st_global_32B(o + j, ow);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
               }
             } else {
 #pragma unroll
@@ -445,10 +454,8 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               split2(cpb::act_fn(f[2 * j], act), cpb::act_fn(f[2 * j + 1], act), a.fmt, oh[j], ol[j]);
-            reinterpret_cast<uint4 *>(o)[0] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-            reinterpret_cast<uint4 *>(o)[1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
-            reinterpret_cast<uint4 *>(o + a.dst_plane)[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-            reinterpret_cast<uint4 *>(o + a.dst_plane)[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+            st_global_32B(o, oh);                       // 32-byte stores: see net_tc3.cu's epilogue
+            st_global_32B(o + a.dst_plane, ol);
           } else {
             __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(a.dst) + pix * a.cout_store + nb;
             if (a.res) {
@@ -473,8 +480,8 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
               ob0[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
               ob1[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
             }
-            reinterpret_cast<uint4 *>(o)[0] = o0;
-            reinterpret_cast<uint4 *>(o)[1] = o1;
+            const uint32_t ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+            st_global_32B(o, ow);
           }
         }
       }

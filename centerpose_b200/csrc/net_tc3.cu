@@ -31,6 +31,7 @@
 // products A_hi*[W_hi ; W_lo] are ONE tcgen05.mma of N = 2*BN into two adjacent accumulator halves (the issuing thread
 // is the bottleneck for N <= 128, ~90 cycles per instruction whatever N) and A_lo*W_hi a second one into the first
 // half; the epilogue adds the halves, scales by acc_scale, and writes hi / lo planes.  BN = 256: three N = 256 MMAs.
+#include <type_traits>
 #include "tc_common.cuh"
 #include <cstdlib>
 
@@ -58,6 +59,7 @@ struct alignas(64) C3Args {
   unsigned fmt;                // 0 = bf16 planes, 1 = fp16 planes
   float acc_scale;             // accumulator multiplier (inverse of the host's power-of-two weight scale)
   long long dst_plane;         // elements between the hi and lo planes of dst / res
+  unsigned dbg;                // timing experiments only (CPB200_C3_DBG): see profiles/r02_head3x3_whatif.md
   unsigned b_tile_bytes;       // bytes of one weight tile (BN x BK x 2); a P = 2 weight stage is [hi tile | lo tile]
   // CTA pairs (mcast = 1 -> conv3x3_tc_kernel<BN, P, 2>): the two CTAs of a cluster walk the same (pixel-tile pair, N tile)
   // sequence; every weight operand is split between them (bmap box = BN/2 rows)
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
 
   if (warp == 0) {
     // =============================== halo producer ===============================
-    if (elect_one()) {
+    if (elect_one() && !(a.dbg & 16u)) {
       int sa = 0; uint32_t pha = 0;
       int n, h0, w0, nt; bool valid;
       for (int it = 0; tile_at(it, n, h0, w0, nt, valid); ++it) {
@@ -171,6 +173,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
               // both halos of the pair complete on the LEADER's barrier (its MMA thread is the only consumer)
               if (leader) mbar_expect_tx(afull0 + 8 * sa, 2 * a.a_tx_bytes);
               tma_load_4d_cg2(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, w0 - (a.kw >> 1), h0 - (a.kh >> 1), n + pl * a.B);
+            } else if (a.dbg & 1u) {
+              mbar_arrive(afull0 + 8 * sa);
             } else {
               mbar_expect_tx(afull0 + 8 * sa, a.a_tx_bytes);
               tma_load_4d(a_base + sa * a.a_stage_bytes, &a.amap, afull0 + 8 * sa, sl * a.BK, w0 - (a.kw >> 1), h0 - (a.kh >> 1), n + pl * a.B);
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
             for (int pl = 0; pl < P; ++pl)
               tma_load_3d(b_base + (sl * a.taps + tap) * a.b_stage_bytes + pl * a.b_tile_bytes, &a.bmap, ball, 0, 0,
                           pl * wplane + tap * a.slabs + sl);
-      } else {
+      } else if (!(a.dbg & 16u)) {
         int sb = 0; uint32_t phb = 0;
         int n, h0, w0, nt; bool valid;
         for (int it = 0; tile_at(it, n, h0, w0, nt, valid); ++it) {
@@ -218,6 +222,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
                   tma_load_3d_cg2(sbase + half, &a.bmap, bfull0 + 8 * sb, 0, nt * BN + BN / 2, plane_blk);
                   tma_load_3d_cg2(sbase + 2 * half, &a.bmap, bfull0 + 8 * sb, 0, nt * BN + (int)crank * (BN / 2), blk);
                 }
+              } else if (a.dbg & 1u) {
+                mbar_arrive(bfull0 + 8 * sb);
               } else {
                 mbar_expect_tx(bfull0 + 8 * sb, P * a.b_tile_bytes);
 #pragma unroll
@@ -296,204 +302,145 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
         }
       }
     } else if (!a.b_resident) {
-      // ---- streamed weights: ONE elected thread runs the whole issue loop.  Measured with loads and epilogue switched off
-      // (profiles/r02_head3x3_whatif.md): the loop that re-elected a lane, rebuilt three descriptors and re-converged the warp
-      // for every tap took 1.27k cycles per 8-MMA stage against 0.84k of tensor time — the issuing thread, not the operands,
-      // bounded the streamed convs.  Here the descriptors are templates plus a 14-bit start address, and nothing but the two
-      // mbarrier waits and the MMAs themselves sits between stages.
+      // ---- streamed weights: ONE elected thread runs the whole issue loop, written the way tools/mma_probe.py's `pipe2`
+      // mode shows to run at the back-to-back MMA rate (profiles/r02_mma_probe_pipe*.log: 422 ns per 4-K-step split stage
+      // against 530-630 ns for a loop with a run-time K trip count and the barrier wait directly in front of the MMAs):
+      // K steps unrolled at compile time, descriptors = templates + a 14-bit start address, the accumulate flag a register
+      // (no per-instruction compare chain), and the NEXT stage's full barrier polled once before this stage's MMAs so that
+      // its round trip overlaps queued tensor work.
       if (elect_one()) {
         const uint64_t dA = desc_sbo(0u, a.hw * pix_bytes, a.swizzle_bits), dB = desc_sbo(0u, 8 * pix_bytes, a.swizzle_bits);
         const uint32_t a_lo14 = (a_base & 0x3FFFFu) >> 4, b_lo14 = (b_base & 0x3FFFFu) >> 4;
         const uint32_t astep = a.a_stage_bytes >> 4, rowstep = (uint32_t)a.hw * pstep;
-        for (int it = 0; tile_at(it, n_, h0_, w0_, nt_, valid_); ++it) {
-          mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-          for (int sl = 0; sl < a.slabs; ++sl) {
-            const int sa_h = sa; const uint32_t pha_h = pha;
-            if (++sa == a.na) { sa = 0; pha ^= 1; }
-            int sa_l = sa_h; uint32_t pha_l = pha_h;
-            if constexpr (P == 2) {
-              sa_l = sa; pha_l = pha;
-              if (++sa == a.na) { sa = 0; pha ^= 1; }
-            }
-            mbar_wait(afull0 + 8 * sa_h, pha_h);
-            if constexpr (P == 2) mbar_wait(afull0 + 8 * sa_l, pha_l);
+        auto run = [&](auto KS_) {
+          constexpr int KS = decltype(KS_)::value;
+          const bool dbg_noacc = a.dbg & 4u, dbg_nofull = a.dbg & 16u;
+          uint32_t peek = mbar_try_once(bfull0 + 8 * sb, phb);
+          for (int it = 0; tile_at(it, n_, h0_, w0_, nt_, valid_); ++it) {
+            if (!dbg_noacc) mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
             tc_fence_after();
-            const uint64_t ah0 = dA + (a_lo14 + (uint32_t)sa_h * astep), al0 = dA + (a_lo14 + (uint32_t)sa_l * astep);
-            int tap = 0;
-            for (int r = 0; r < a.kh; ++r) {
-              for (int q2 = 0; q2 < a.kw; ++q2, ++tap) {
-                const uint32_t toff = (uint32_t)r * rowstep + (uint32_t)q2 * pstep;
-                mbar_wait(bfull0 + 8 * sb, phb);
-                tc_fence_after();
-                const uint64_t bd = dB + (b_lo14 + (uint32_t)sb * bstep);
-                const uint64_t adh = ah0 + toff, adl = al0 + toff;
-#pragma unroll 4
-                for (int k = 0; k < ksteps; ++k) {
-                  const uint32_t first = (sl > 0 || tap > 0 || k > 0) ? 1u : 0u;
-                  if constexpr (P == 1) {
-                    umma_bf16(d_tmem, adh + 2 * k, bd + 2 * k, idesc, first);
-                  } else {
-                    if constexpr (NCAT) {
-                      umma_bf16(d_tmem, adh + 2 * k, bd + 2 * k, idesc2, first);
-                    } else {
-                      umma_bf16(d_tmem, adh + 2 * k, bd + 2 * k, idesc, first);
-                      umma_bf16(d_tmem, adh + 2 * k, bd + btile + 2 * k, idesc, 1u);
-                    }
-                    umma_bf16(d_tmem + (NCAT ? BN : 0), adl + 2 * k, bd + 2 * k, idesc, 1u);   // small terms share the second half
-                  }
-                }
-                umma_commit(bempty0 + 8 * sb);
-                if (++sb == a.nb) { sb = 0; phb ^= 1; }
+            const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+            uint32_t accf = 0u;                                  // 0 for the tile's very first MMA, 1 afterwards
+            for (int sl = 0; sl < a.slabs; ++sl) {
+              const int sa_h = sa; const uint32_t pha_h = pha;
+              if (++sa == a.na) { sa = 0; pha ^= 1; }
+              int sa_l = sa_h; uint32_t pha_l = pha_h;
+              if constexpr (P == 2) {
+                sa_l = sa; pha_l = pha;
+                if (++sa == a.na) { sa = 0; pha ^= 1; }
               }
+              if (!dbg_nofull) {
+                mbar_wait(afull0 + 8 * sa_h, pha_h);
+                if constexpr (P == 2) mbar_wait(afull0 + 8 * sa_l, pha_l);
+              }
+              const uint64_t ah0 = dA + (a_lo14 + (uint32_t)sa_h * astep), al0 = dA + (a_lo14 + (uint32_t)sa_l * astep);
+              uint32_t roff = 0u;
+              for (int r = 0; r < a.kh; ++r, roff += rowstep) {
+                uint32_t toff = roff;
+                for (int q2 = 0; q2 < a.kw; ++q2, toff += pstep) {
+                  if (!peek && !dbg_nofull) mbar_wait(bfull0 + 8 * sb, phb);
+                  tc_fence_after();
+                  const uint64_t bd = dB + (b_lo14 + (uint32_t)sb * bstep);
+                  const uint64_t adh = ah0 + toff, adl = al0 + toff;
+                  const uint32_t bempty = bempty0 + 8 * sb;
+                  if (++sb == a.nb) { sb = 0; phb ^= 1; }
+                  peek = mbar_try_once(bfull0 + 8 * sb, phb);        // next stage (possibly of the next tile): poll early
+#pragma unroll
+                  for (int k = 0; k < KS; ++k) {
+                    const uint32_t first = k == 0 ? accf : 1u;
+                    if constexpr (P == 1) {
+                      umma_bf16(d_tmem, adh + 2 * k, bd + 2 * k, idesc, first);
+                    } else {
+                      if constexpr (NCAT) {
+                        umma_bf16(d_tmem, adh + 2 * k, bd + 2 * k, idesc2, first);
+                      } else {
+                        umma_bf16(d_tmem, adh + 2 * k, bd + 2 * k, idesc, first);
+                        umma_bf16(d_tmem, adh + 2 * k, bd + btile + 2 * k, idesc, 1u);
+                      }
+                      umma_bf16(d_tmem + (NCAT ? BN : 0), adl + 2 * k, bd + 2 * k, idesc, 1u);   // small terms share the second half
+                    }
+                  }
+                  accf = 1u;
+                  umma_commit(bempty);
+                }
+              }
+              umma_commit(aempty0 + 8 * sa_h);
+              if constexpr (P == 2) umma_commit(aempty0 + 8 * sa_l);
+              if (sl == a.slabs - 1 && !dbg_noacc) umma_commit(tfull0 + 8 * acc);
             }
-            umma_commit(aempty0 + 8 * sa_h);
-            if constexpr (P == 2) umma_commit(aempty0 + 8 * sa_l);
-            if (sl == a.slabs - 1) umma_commit(tfull0 + 8 * acc);
+            if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
           }
-          if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
-        }
+          if (dbg_noacc) { umma_commit(tfull0); mbar_wait(tfull0, 0); }
+        };
+        if (ksteps == 4) run(std::integral_constant<int, 4>{});
+        else if (ksteps == 2) run(std::integral_constant<int, 2>{});
+        else run(std::integral_constant<int, 1>{});
       }
       __syncwarp();
-    } else
-    for (int it = 0; tile_at(it, n_, h0_, w0_, nt_, valid_); ++it) {
-      mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-      for (int sl = 0; sl < a.slabs; ++sl) {
-        if constexpr (P == 1) {
-          mbar_wait(afull0 + 8 * sa, pha);
-          tc_fence_after();
-          const uint32_t halo = a_base + sa * a.a_stage_bytes;
-          if (a.b_resident) {
-            // resident weights: nothing to wait for inside the slab — one lane issues all 9 x ksteps MMAs
-            // back to back; descriptors differ only in the 14-bit start-address field (adds on the low word)
-            if (elect_one()) {
-              const uint64_t ad0 = desc_sbo(halo, a.hw * pix_bytes, a.swizzle_bits);
-              const uint64_t bd0 = desc_sbo(b_base + sl * a.taps * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
-              if (a.taps == 9) {
-#pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                  const uint64_t ad = ad0 + (uint32_t)((tap / 3) * HW_ + (tap % 3)) * pstep;
-                  const uint64_t bd = bd0 + (uint32_t)tap * bstep;
-                  for (int k = 0; k < ksteps; ++k)
-                    umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                }
-              } else {
-                int tap = 0;
-                for (int r = 0; r < a.kh; ++r)
-                  for (int q2 = 0; q2 < a.kw; ++q2, ++tap) {
-                    const uint64_t ad = ad0 + (uint32_t)(r * a.hw + q2) * pstep;
-                    const uint64_t bd = bd0 + (uint32_t)tap * bstep;
-                    for (int k = 0; k < ksteps; ++k)
-                      umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                  }
-              }
-            }
-            __syncwarp();
-          } else {
-            for (int tap = 0; tap < a.taps; ++tap) {
-              mbar_wait(bfull0 + 8 * sb, phb);
-              tc_fence_after();
-              if (elect_one()) {
-                const int r = tap / a.kw, s = tap - a.kw * r;
-                const uint64_t ad = desc_sbo(halo + (r * a.hw + s) * pix_bytes, a.hw * pix_bytes, a.swizzle_bits);
-                const uint64_t bd = desc_sbo(b_base + sb * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
-                for (int k = 0; k < ksteps; ++k)
-                  umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (sl > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                umma_commit(bempty0 + 8 * sb);
-              }
-              __syncwarp();
-              if (++sb == a.nb) { sb = 0; phb ^= 1; }
-            }
-          }
-          if (elect_one()) {
-            umma_commit(aempty0 + 8 * sa);
-            if (sl == a.slabs - 1) umma_commit(tfull0 + 8 * acc);
-          }
-          __syncwarp();
-          if (++sa == a.na) { sa = 0; pha ^= 1; }
-        } else if (a.b_resident) {
-          // ---- split operands, resident weights: hi-plane stage (A_hi x [W_hi ; W_lo]), then lo-plane stage (A_lo x W_hi)
-#pragma unroll
-          for (int pl = 0; pl < 2; ++pl) {
-            mbar_wait(afull0 + 8 * sa, pha);
+    } else {
+      // ---- resident weights (the whole filter bank sits in shared memory): same loop style, nothing to wait for inside a
+      // slab but the halo itself; split operands run a hi-plane stage (A_hi x [W_hi ; W_lo]) and then a lo-plane stage
+      // (A_lo x W_hi).  The small cross term joins A_hi x W_lo in the SECOND accumulator half: the tensor core's fp32
+      // accumulator truncates (round toward zero) at every instruction, an error proportional to the accumulator's
+      // magnitude — the large hi x hi sum must see as few additions as possible.
+      if (elect_one()) {
+        const uint64_t dA = desc_sbo(0u, a.hw * pix_bytes, a.swizzle_bits), dB = desc_sbo(0u, 8 * pix_bytes, a.swizzle_bits);
+        const uint32_t a_lo14 = (a_base & 0x3FFFFu) >> 4, b_lo14 = (b_base & 0x3FFFFu) >> 4;
+        const uint32_t astep = a.a_stage_bytes >> 4, rowstep = (uint32_t)a.hw * pstep;
+        auto run = [&](auto KS_) {
+          constexpr int KS = decltype(KS_)::value;
+          uint32_t peek = mbar_try_once(afull0 + 8 * sa, pha);
+          for (int it = 0; tile_at(it, n_, h0_, w0_, nt_, valid_); ++it) {
+            mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
             tc_fence_after();
-            if (elect_one()) {
-              const uint64_t ad0 = desc_sbo(a_base + sa * a.a_stage_bytes, a.hw * pix_bytes, a.swizzle_bits);
-              const uint64_t bd0 = desc_sbo(b_base + sl * a.taps * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
-              int tap = 0;
-              for (int r = 0; r < a.kh; ++r)
-                for (int q2 = 0; q2 < a.kw; ++q2, ++tap) {
-                  const uint64_t ad = ad0 + (uint32_t)(r * a.hw + q2) * pstep;
-                  const uint64_t bd = bd0 + (uint32_t)tap * bstep;
-                  for (int k = 0; k < ksteps; ++k) {
-                    const uint32_t first = (sl > 0 || tap > 0 || k > 0) ? 1u : 0u;
-                    if (pl == 0) {
-                      if constexpr (NCAT) {
-                        umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc2, first);
-                      } else {
+            const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+            uint32_t accf = 0u;                                  // 0 for the tile's very first MMA, 1 afterwards
+            for (int sl = 0; sl < a.slabs; ++sl) {
+              const uint64_t bd0 = dB + (b_lo14 + (uint32_t)(sl * a.taps) * bstep);
+#pragma unroll
+              for (int pl = 0; pl < P; ++pl) {
+                if (!peek) mbar_wait(afull0 + 8 * sa, pha);
+                tc_fence_after();
+                const uint64_t ad0 = dA + (a_lo14 + (uint32_t)sa * astep);
+                const uint32_t aempty = aempty0 + 8 * sa;
+                if (++sa == a.na) { sa = 0; pha ^= 1; }
+                peek = mbar_try_once(afull0 + 8 * sa, pha);          // next halo stage: poll early
+                uint64_t bd = bd0;
+                uint32_t roff = 0u;
+                for (int r = 0; r < a.kh; ++r, roff += rowstep) {
+                  uint64_t ad = ad0 + roff;
+                  for (int q2 = 0; q2 < a.kw; ++q2, ad += pstep, bd += bstep) {
+#pragma unroll
+                    for (int k = 0; k < KS; ++k) {
+                      const uint32_t first = k == 0 ? accf : 1u;
+                      if constexpr (P == 1) {
                         umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, first);
-                        umma_bf16(d_tmem, ad + 2 * k, bd + btile + 2 * k, idesc, 1u);
+                      } else if (pl == 0) {
+                        if constexpr (NCAT) {
+                          umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc2, first);
+                        } else {
+                          umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, first);
+                          umma_bf16(d_tmem, ad + 2 * k, bd + btile + 2 * k, idesc, 1u);
+                        }
+                      } else {
+                        umma_bf16(d_tmem + (NCAT ? BN : 0), ad + 2 * k, bd + 2 * k, idesc, 1u);
                       }
-                    } else {
-                      // the small cross term joins A_hi x W_lo in the SECOND accumulator half: the tensor core's fp32
-                      // accumulator truncates (round toward zero) at every instruction, an error proportional to the
-                      // accumulator's magnitude — the large hi x hi sum must see as few additions as possible
-                      umma_bf16(d_tmem + (NCAT ? BN : 0), ad + 2 * k, bd + 2 * k, idesc, 1u);
                     }
+                    if (pl == 0) accf = 1u;
                   }
                 }
-              umma_commit(aempty0 + 8 * sa);
-              if (pl == 1 && sl == a.slabs - 1) umma_commit(tfull0 + 8 * acc);
-            }
-            __syncwarp();
-            if (++sa == a.na) { sa = 0; pha ^= 1; }
-          }
-        } else {
-          // ---- split operands, streamed weights: both planes of the slab resident, one [W_hi | W_lo] stage per tap
-          const int sa_h = sa; const uint32_t pha_h = pha;
-          if (++sa == a.na) { sa = 0; pha ^= 1; }
-          const int sa_l = sa; const uint32_t pha_l = pha;
-          if (++sa == a.na) { sa = 0; pha ^= 1; }
-          mbar_wait(afull0 + 8 * sa_h, pha_h);
-          mbar_wait(afull0 + 8 * sa_l, pha_l);
-          tc_fence_after();
-          const uint32_t halo_h = a_base + sa_h * a.a_stage_bytes, halo_l = a_base + sa_l * a.a_stage_bytes;
-          for (int tap = 0; tap < a.taps; ++tap) {
-            mbar_wait(bfull0 + 8 * sb, phb);
-            tc_fence_after();
-            if (elect_one()) {
-              const int r = tap / a.kw, s = tap - a.kw * r;
-              const uint32_t toff = (r * a.hw + s) * pix_bytes;
-              const uint64_t adh = desc_sbo(halo_h + toff, a.hw * pix_bytes, a.swizzle_bits);
-              const uint64_t adl = desc_sbo(halo_l + toff, a.hw * pix_bytes, a.swizzle_bits);
-              const uint64_t bd = desc_sbo(b_base + sb * a.b_stage_bytes, 8 * pix_bytes, a.swizzle_bits);
-              for (int k = 0; k < ksteps; ++k) {
-                const uint32_t first = (sl > 0 || tap > 0 || k > 0) ? 1u : 0u;
-                if constexpr (NCAT) {
-                  umma_bf16(d_tmem, adh + 2 * k, bd + 2 * k, idesc2, first);
-                } else {
-                  umma_bf16(d_tmem, adh + 2 * k, bd + 2 * k, idesc, first);
-                  umma_bf16(d_tmem, adh + 2 * k, bd + btile + 2 * k, idesc, 1u);
-                }
-                umma_bf16(d_tmem + (NCAT ? BN : 0), adl + 2 * k, bd + 2 * k, idesc, 1u);   // small terms share the second half
+                umma_commit(aempty);
+                if (pl == P - 1 && sl == a.slabs - 1) umma_commit(tfull0 + 8 * acc);
               }
-              umma_commit(bempty0 + 8 * sb);
             }
-            __syncwarp();
-            if (++sb == a.nb) { sb = 0; phb ^= 1; }
+            if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
           }
-          if (elect_one()) {
-            umma_commit(aempty0 + 8 * sa_h);
-            umma_commit(aempty0 + 8 * sa_l);
-            if (sl == a.slabs - 1) umma_commit(tfull0 + 8 * acc);
-          }
-          __syncwarp();
-        }
+        };
+        if (ksteps == 4) run(std::integral_constant<int, 4>{});
+        else if (ksteps == 2) run(std::integral_constant<int, 2>{});
+        else run(std::integral_constant<int, 1>{});
       }
-      if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
+      __syncwarp();
     }
   } else {
     // =============================== epilogue (two groups of four warps) ===============================
@@ -511,7 +458,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
     int n, h0, w0, nt; bool valid;
     const int c_first = esplit ? grp * (BN / 32) : 0, c_last = esplit ? c_first + BN / 32 : BN / 16;
     const int tstep = esplit ? 1 : 2;
-    for (int it = esplit ? 0 : grp; tile_at(it, n, h0, w0, nt, valid); it += tstep) {
+    for (int it = esplit ? 0 : grp; !(a.dbg & 4u) && tile_at(it, n, h0, w0, nt, valid); it += tstep) {
       const int n0 = nt * BN;
       float *sbias = s_bias[grp][par];
       if (a.n_tiles > 1 || !bias_loaded) {      // one N tile: the bias never changes — load it once
@@ -530,7 +477,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       const size_t pix = ((size_t)n * a.Ho + ho) * a.Wo + wo;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
 #pragma unroll 1
-      for (int c = c_first; c < c_last; ++c) {
+      for (int c = (a.dbg & 2u) ? c_last : c_first; c < c_last; ++c) {
         uint32_t v[16];
         tmem_ld16(taddr + c * 16, v);
         if constexpr (NCAT) {
@@ -555,11 +502,20 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
           if (out_f32) {
             float *o = static_cast<float *>(a.dst) + pix * a.cout_store + nb;
             if (nb + 16 <= a.cout && (a.cout_store & 3) == 0) {
+              if (act) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                float4 v4 = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                if (act) { v4.x = cpb::act_out<__nv_bfloat16>(v4.x, act); v4.y = cpb::act_out<__nv_bfloat16>(v4.y, act); v4.z = cpb::act_out<__nv_bfloat16>(v4.z, act); v4.w = cpb::act_out<__nv_bfloat16>(v4.w, act); }
-                *reinterpret_cast<float4 *>(o + j) = v4;
+                for (int j = 0; j < 16; ++j) f[j] = cpb::act_out<__nv_bfloat16>(f[j], act);
+              }
+              if ((a.cout_store & 7) == 0) {            // 32-byte rows: two sector-sized stores
+#pragma unroll
+                for (int j = 0; j < 16; j += 8) {
+                  const uint32_t ow[8] = {__float_as_uint(f[j]), __float_as_uint(f[j + 1]), __float_as_uint(f[j + 2]), __float_as_uint(f[j + 3]),
+                                          __float_as_uint(f[j + 4]), __float_as_uint(f[j + 5]), __float_as_uint(f[j + 6]), __float_as_uint(f[j + 7])};
+                  st_global_32B(o + j, ow);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
               }
             } else {
 #pragma unroll
@@ -585,10 +541,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               split2(cpb::act_fn(f[2 * j], act), cpb::act_fn(f[2 * j + 1], act), a.fmt, oh[j], ol[j]);
-            reinterpret_cast<uint4 *>(o)[0] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-            reinterpret_cast<uint4 *>(o)[1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
-            reinterpret_cast<uint4 *>(o + a.dst_plane)[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-            reinterpret_cast<uint4 *>(o + a.dst_plane)[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+            st_global_32B(o, oh);                       // one 32-byte sector per thread and plane: every thread owns a pixel row,
+            st_global_32B(o + a.dst_plane, ol);         // so a warp store touches 32 lines — halve the number of such stores
           } else {
             __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(a.dst) + pix * a.cout_store + nb;
             if (a.res) {
@@ -613,8 +567,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
               ob0[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
               ob1[j] = __floats2bfloat162_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
             }
-            reinterpret_cast<uint4 *>(o)[0] = o0;
-            reinterpret_cast<uint4 *>(o)[1] = o1;
+            const uint32_t ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+            st_global_32B(o, ow);
           }
         }
       }
@@ -722,6 +676,7 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   const size_t budget = (P == 2 ? 220 : 200) * 1024;
   a.na = 3;
   if (a.a_stage_bytes <= 12 * 1024) a.na = (a.a_stage_bytes <= 6 * 1024) ? 16 : 8;   // small halos: deeper ring hides TMA latency
+  if (const char *e = getenv("CPB200_C3_DBG")) a.dbg = (unsigned)atoi(e);      // timing experiments (results are garbage)
   if (const char *e = getenv("CPB200_C3_NA")) { int v = atoi(e); if (v >= 2 && v <= MAX_NA) a.na = v; }
   if (P == 2 && a.na < 4) a.na = 4;                         // two slabs' worth of planes in flight
   const size_t resident_bytes = (size_t)a.taps * a.slabs * a.b_stage_bytes;

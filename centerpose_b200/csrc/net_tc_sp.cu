@@ -291,10 +291,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_sp_kernel(const SpArgs a) 
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               split2(cpb::act_fn(f[2 * j], a.act), cpb::act_fn(f[2 * j + 1], a.act), a.fmt, oh[j], ol[j]);
-            reinterpret_cast<uint4 *>(oh_)[0] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-            reinterpret_cast<uint4 *>(oh_)[1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
-            reinterpret_cast<uint4 *>(oh_ + a.y_plane)[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-            reinterpret_cast<uint4 *>(oh_ + a.y_plane)[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+            st_global_32B(oh_, oh);
+            st_global_32B(oh_ + a.y_plane, ol);
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[c * 16 + j];
@@ -314,8 +312,8 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_sp_kernel(const SpArgs a) 
               ob0[j] = __floats2bfloat162_rn(cpb::act_out<__nv_bfloat16>(f[2 * j], a.act), cpb::act_out<__nv_bfloat16>(f[2 * j + 1], a.act));
               ob1[j] = __floats2bfloat162_rn(cpb::act_out<__nv_bfloat16>(f[8 + 2 * j], a.act), cpb::act_out<__nv_bfloat16>(f[8 + 2 * j + 1], a.act));
             }
-            reinterpret_cast<uint4 *>(o + c * 16)[0] = o0;
-            reinterpret_cast<uint4 *>(o + c * 16)[1] = o1;
+            const uint32_t ow[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+            st_global_32B(o + c * 16, ow);
           }
         }
       }

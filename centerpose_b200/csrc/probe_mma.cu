@@ -109,6 +109,79 @@ __global__ void __launch_bounds__(128, 1) mma_probe_kernel(const MmaProbeArgs a)
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
   }
 }
+
+// ---- pipe2: the issue loop written the way the production kernels should run it ------------------------------------
+// K steps unrolled at compile time, no integer division, the NEXT stage's full barrier polled once before this stage's
+// MMAs (its round trip overlaps queued tensor work), and — UNIFORM — the whole warp running the loop with uniform control
+// flow and only the tcgen05 instructions themselves under elect.sync, so that descriptors live in uniform registers.
+struct PipeArgs { int n, iters, nacc, alt, ring; };
+
+template <int KS, bool UNIFORM>
+__global__ void __launch_bounds__(128, 1) mma_pipe2_kernel(const PipeArgs a) {
+  extern __shared__ __align__(1024) uint8_t raw[];
+  const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t ring[16];
+  __shared__ uint32_t s_tmem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 96 * 1024 / 16; i += 128)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + i * 16), "r"(0u) : "memory");
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 16; ++i) mbar_init(smem_u32(&ring[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s_tmem;
+  if (warp == 1 && (UNIFORM || elect_one())) {
+    const uint32_t idesc = idesc_mn(128, a.n, 1u), idesc_half = idesc_mn(128, a.n / 2, 1u);
+    const uint64_t ad0 = make_desc(base, 128, 2), bd0 = make_desc(base + 32 * 1024, 128, 2);
+    const uint32_t full0 = smem_u32(&ring[0]), empty0 = smem_u32(&ring[8]);
+    int stage = 0, acc = 0; uint32_t phase = 0, first = 1;
+    uint32_t peek = mbar_try_once(full0, 0);
+    for (int i = 0; i < a.iters; ++i) {
+      if (!peek) mbar_wait(full0 + 8 * stage, phase);
+      tc_fence_after();
+      const uint32_t d = tmem + (uint32_t)acc * (uint32_t)a.n;
+      int ns = stage + 1; uint32_t np = phase;
+      if (ns == a.ring) { ns = 0; np ^= 1; }
+      peek = mbar_try_once(full0 + 8 * ns, np);
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        if (!UNIFORM || elect_one()) {
+          umma_bf16(d, ad0 + 2 * k, bd0 + 2 * k, idesc, (k > 0 || !first) ? 1u : 0u);
+          if (a.alt) umma_bf16(d + (uint32_t)a.n / 2, ad0 + 2 * k + 64, bd0 + 2 * k, idesc_half, 1u);
+        }
+      }
+      if (!UNIFORM || elect_one()) umma_commit(empty0 + 8 * stage);
+      stage = ns; phase = np;
+      if (++acc == a.nacc) { acc = 0; first = 0; }
+    }
+    // drain: wait until the last commit has landed
+    if (!UNIFORM || lane == 0) {
+      int ls = (a.iters - 1) % a.ring;
+      mbar_wait(empty0 + 8 * ls, (uint32_t)(((a.iters - 1) / a.ring) & 1));
+    }
+  } else if (warp == 2 && lane == 0) {
+    int stage = 0; uint32_t phase = 0;
+    for (int i = 0; i < a.iters; ++i) {
+      if (i >= a.ring) mbar_wait(smem_u32(&ring[8 + stage]), phase ^ 1);
+      mbar_arrive(smem_u32(&ring[stage]));
+      if (++stage == a.ring) { stage = 0; phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+}
 }  // namespace
 
 extern "C" int cpb200_probe_mma_ex(int n, int cg, int iters, int nacc, int stride_bytes, int a_sbo, int a_shift, int alt, void *stream);
@@ -148,4 +221,25 @@ extern "C" int cpb200_probe_mma_ex(int n, int cg, int iters, int nacc, int strid
     CPB_CUDA(cudaLaunchKernelEx(&cfg, mma_probe_kernel<2>, a));
   }
   return cpb::check_launch("mma_probe_kernel");
+}
+
+extern "C" int cpb200_probe_mma_pipe2(int n, int iters, int nacc, int alt, int ring, int ksteps, int uniform, void *stream) {
+  if (n < 32 || n > 256 || n % 32 || nacc < 1 || nacc * n > 512 || iters < 1 || ring < 1 || ring > 8 || (ksteps != 4 && ksteps != 8))
+    return cpb::fail(CPB200_ERR_ARG, "probe_mma_pipe2: bad arguments");
+  PipeArgs a{n, iters, nacc, alt, ring};
+  const size_t smem = 100 * 1024;
+  const int sms = tc::num_sms();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define PIPE2(KS, U)                                                                  \
+  {                                                                                   \
+    static tc::SmemAttrCache c;                                                       \
+    if (int rc = tc::ensure_smem(mma_pipe2_kernel<KS, U>, smem, c)) return rc;        \
+    mma_pipe2_kernel<KS, U><<<sms, 128, smem, st>>>(a);                               \
+  }
+  if (ksteps == 4 && uniform) PIPE2(4, true)
+  else if (ksteps == 4) PIPE2(4, false)
+  else if (uniform) PIPE2(8, true)
+  else PIPE2(8, false)
+#undef PIPE2
+  return cpb::check_launch("mma_pipe2_kernel");
 }

@@ -59,3 +59,18 @@ for n, alt, nacc in ((256, 1, 2), (128, 0, 2)):
             ns_stage = e0.elapsed_time(e1) * 1e6 / stages_n
             print(f"pipe N={n:3d} {'split K step' if alt else 'one MMA/step '} ring 4 x {ksteps:2d} K steps, {label:36s}: "
                   f"{ns_stage:7.1f} ns / stage = {ns_stage / ksteps:6.1f} ns / K step")
+
+# ---- pipe2: unrolled K steps, early poll of the next stage, single-thread loop vs whole-warp loop + per-instruction elect
+L.cpb200_probe_mma_pipe2.restype = ctypes.c_int
+L.cpb200_probe_mma_pipe2.argtypes = [ctypes.c_int] * 7 + [ctypes.c_void_p]
+for n, alt, nacc in ((256, 1, 2), (256, 0, 2), (128, 0, 2)):
+    for ksteps in (4, 8):
+        for uniform in (0, 1):
+            args = (n, stages_n, nacc, alt, 4, ksteps, uniform, st)
+            _lib.check(L.cpb200_probe_mma_pipe2(n, 500, nacc, alt, 4, ksteps, uniform, st), "probe"); torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); _lib.check(L.cpb200_probe_mma_pipe2(*args), "probe"); e1.record(); torch.cuda.synchronize()
+            ns_stage = e0.elapsed_time(e1) * 1e6 / stages_n
+            print(f"pipe2 N={n:3d} {'split K step' if alt else 'one MMA/step '} ring 4 x {ksteps} K steps, "
+                  f"{'whole warp + elect per instruction' if uniform else 'one elected thread            '}: "
+                  f"{ns_stage:7.1f} ns / stage = {ns_stage / ksteps:6.1f} ns / K step")
