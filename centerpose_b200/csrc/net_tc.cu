@@ -23,6 +23,7 @@
 // [A_hi | A_lo | W_hi | W_lo]; per K step the issuer emits A_hi x [W_hi ; W_lo] as one N = 2*BN instruction when
 // 2*BN <= 256 (two adjacent accumulator halves, added in the epilogue) plus A_lo x W_hi, or three N = BN instructions
 // for BN = 256.  The DCN gather blends the four corners of BOTH planes in fp32 and re-splits the sample.
+#include <type_traits>
 #include "tc_common.cuh"
 #include <mutex>
 #include <cstdlib>
@@ -158,44 +159,60 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
     const uint32_t idesc = P == 1 ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24))
                                   : idesc_m128(BN, a.fmt);
     const uint32_t idesc2 = idesc_m128(NCAT ? 2 * BN : BN, a.fmt);
-    int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t accphase = 0;
-    const uint32_t row_bytes = a.BK * 2;
-    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-      mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        mbar_wait(full0 + 8 * stage, phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sa = smem_base + stage * stage_bytes, sb = sa + P * a_bytes;
-          const uint64_t ad = make_desc(sa, row_bytes, a.swizzle_bits), bd = make_desc(sb, row_bytes, a.swizzle_bits);
-          if constexpr (P == 1) {
-            for (int k = 0; k < a.BK / 16; ++k)
-              umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          } else {
-            const uint32_t aplane = a_bytes >> 4, bplane = b_bytes >> 4;      // descriptor start-address units
-            for (int k = 0; k < a.BK / 16; ++k) {
-              const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
-              if constexpr (NCAT) {
-                umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc2, first);                 // A_hi x [W_hi ; W_lo]
+    // ONE elected thread runs the whole issue loop in the form tools/mma_probe.py's `pipe2` mode shows to reach the back-to-back
+    // MMA rate (profiles/r02_mma_probe_pipe*.log): K steps unrolled at compile time, descriptor templates + a 14-bit start
+    // address, the accumulate flag in a register, and the next stage's full barrier polled before this stage's MMAs.
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t accphase = 0;
+      const uint32_t row_bytes = a.BK * 2;
+      const uint64_t dT = make_desc(0u, row_bytes, a.swizzle_bits);
+      const uint32_t base14 = (smem_base & 0x3FFFFu) >> 4, sstep = stage_bytes >> 4;
+      const uint32_t aplane = a_bytes >> 4, bplane = b_bytes >> 4, boff = (uint32_t)(P * a_bytes) >> 4;   // descriptor start-address units
+      auto run = [&](auto KS_) {
+        constexpr int KS = decltype(KS_)::value;
+        uint32_t peek = mbar_try_once(full0 + 8 * stage, phase);
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+          mbar_wait(tempty0 + 8 * acc, accphase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+          uint32_t accf = 0u;                                    // 0 for the tile's very first MMA, 1 afterwards
+          for (int kb = 0; kb < kblocks; ++kb) {
+            if (!peek) mbar_wait(full0 + 8 * stage, phase);
+            tc_fence_after();
+            const uint64_t ad = dT + (base14 + (uint32_t)stage * sstep), bd = ad + boff;
+            const uint32_t empty = empty0 + 8 * stage;
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            peek = mbar_try_once(full0 + 8 * stage, phase);
+#pragma unroll
+            for (int k = 0; k < KS; ++k) {
+              const uint32_t first = k == 0 ? accf : 1u;
+              if constexpr (P == 1) {
+                umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, first);
               } else {
-                umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, first);                  // A_hi x W_hi
-                umma_bf16(d_tmem, ad + 2 * k, bd + bplane + 2 * k, idesc, 1u);            // A_hi x W_lo
+                if constexpr (NCAT) {
+                  umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc2, first);                 // A_hi x [W_hi ; W_lo]
+                } else {
+                  umma_bf16(d_tmem, ad + 2 * k, bd + 2 * k, idesc, first);                  // A_hi x W_hi
+                  umma_bf16(d_tmem, ad + 2 * k, bd + bplane + 2 * k, idesc, 1u);            // A_hi x W_lo
+                }
+                // A_lo x W_hi joins the other small term in the second accumulator half (see net_tc3.cu: the fp32
+                // accumulator truncates per instruction in proportion to its magnitude)
+                umma_bf16(d_tmem + (NCAT ? BN : 0), ad + aplane + 2 * k, bd + 2 * k, idesc, 1u);
               }
-              // A_lo x W_hi joins the other small term in the second accumulator half (see net_tc3.cu: the fp32
-              // accumulator truncates per instruction in proportion to its magnitude)
-              umma_bf16(d_tmem + (NCAT ? BN : 0), ad + aplane + 2 * k, bd + 2 * k, idesc, 1u);
             }
+            accf = 1u;
+            umma_commit(empty);                         // frees the smem slot when these MMAs retire
+            if (kb == kblocks - 1) umma_commit(tfull0 + 8 * acc);
           }
-          umma_commit(empty0 + 8 * stage);              // frees the smem slot when these MMAs retire
-          if (kb == kblocks - 1) umma_commit(tfull0 + 8 * acc);
+          if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == a.stages) { stage = 0; phase ^= 1; }
-      }
-      if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
+      };
+      const int ksteps = a.BK / 16;
+      if (ksteps == 4) run(std::integral_constant<int, 4>{});
+      else if (ksteps == 2) run(std::integral_constant<int, 2>{});
+      else run(std::integral_constant<int, 1>{});
     }
+    __syncwarp();
   } else if (DCN && warp >= 6) {
     // =============================== DCN gather producers (warps 6..21) ===============================
     // A[row = pixel][k = channel] of tap t is  sigmoid(mask_t) * bilinear(x, p + tap_t + offset_t)

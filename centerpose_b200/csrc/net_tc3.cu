@@ -44,7 +44,7 @@ constexpr int TW = 8, TH = 16, HW_ = TW + 2, HH_ = TH + 2;
 constexpr int MAX_NA = 16, MAX_NB = 8;
 
 struct alignas(64) C3Args {
-  CUtensorMap amap, bmap;
+  CUtensorMap amap, bmap, dmap;    // dmap: the OUTPUT tensor (TMA-store epilogue), box {32 channels, TW, TH, 1}, 64-byte swizzle
   int cin, slabs, BK;
   int B, Ho, Wo, tiles_h, tiles_w, n_tiles, total_tiles;
   int cout, cout_store;
@@ -64,6 +64,8 @@ struct alignas(64) C3Args {
   // CTA pairs (mcast = 1 -> conv3x3_tc_kernel<BN, P, 2>): the two CTAs of a cluster walk the same (pixel-tile pair, N tile)
   // sequence; every weight operand is split between them (bmap box = BN/2 rows)
   int mcast, n_pix_tiles;
+  // TMA-store epilogue: byte offset of the staging area (2 epilogue groups x P planes x 128 rows x 64 B) behind the rings
+  int tstore; unsigned stg_off;
 };
 
 __device__ __forceinline__ uint64_t desc_sbo(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
@@ -100,12 +102,11 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool mc = CG == 2;
   // Two accumulator stages only (ACC_COLS = 256): tile t+2 reuses the stage tile t is being read out of, so ONE read-out must
-  // fit into ONE tile's MMA time whatever the number of epilogue groups — alternating tiles between the groups does not help
-  // (measured: the 64->256 head conv 420 us, 338 us with the epilogue switched off).  Both groups then share every tile,
-  // each reading half of its column chunks: bf16 head conv 166 -> 161 us together with the single-thread issue loop; with
-  // split operands (two TMEM reads per chunk from eight warps at once) it measured SLOWER, 424 -> 456 us, so P = 2 keeps
-  // the alternating scheme.
-  const bool esplit = P == 1 && a.nacc == 2 && BN >= 32;
+  // fit into ONE tile's MMA time whatever the number of epilogue groups — alternating tiles between the groups does not help.
+  // Both groups then share every tile, each reading half of its column chunks.  History: with 16-byte direct stores this
+  // measured slower for split operands (424 -> 456 us on the 64->256 head conv: eight warps' stores at once on the L1 path);
+  // with the TMA-store epilogue it is the faster form for both (fp16x2 385 -> 345 us, bf16 137 -> 122 us).
+  const bool esplit = a.nacc == 2 && BN >= 32;
   const uint32_t crank = mc ? cluster_ctarank() : 0u;
   const bool leader = crank == 0;
   const uint32_t need_cols = (uint32_t)a.nacc * ACC_COLS;
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
 
   if (warp == 0 && lane == 0) {
     tmap_prefetch(&a.amap); tmap_prefetch(&a.bmap);
+    if (a.tstore) tmap_prefetch(&a.dmap);
     for (int s = 0; s < MAX_NA; ++s) { mbar_init(afull0 + 8 * s, 1); mbar_init(aempty0 + 8 * s, 1); }
     for (int s = 0; s < MAX_NB; ++s) { mbar_init(bfull0 + 8 * s, 1); mbar_init(bempty0 + 8 * s, 1); }
     mbar_init(ball, 1);
@@ -476,6 +478,104 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       const bool ok = valid && ho < a.Ho && wo < a.Wo;
       const size_t pix = ((size_t)n * a.Ho + ho) * a.Wo + wo;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
+      if (a.tstore) {
+        // ---- TMA-store epilogue.  Every thread owns one pixel row, so direct global stores touch 32 lines per warp
+        // instruction and their L1 wavefronts compete with the MMAs' operand reads for the shared-memory data path
+        // (profiles/r02_head3x3_whatif.md).  Here 32 channels at a time go to a staging tile in shared memory (16-byte
+        // st.shared in the 64-byte-swizzle pattern: conflict-free, 4 wavefronts per 512 B) and ONE thread of the group
+        // hands the tile (both planes) to the copy engine; rows / channels outside the tensor are clipped by TMA.
+        const uint32_t stg = smem_base + a.stg_off + (uint32_t)grp * (uint32_t)(P * 8192);
+        const uint32_t srow = stg + (uint32_t)row * 64u, sx = ((uint32_t)row >> 1) & 3u;
+#pragma unroll 1
+        for (int c = (a.dbg & 2u) ? c_last : c_first; c < c_last; c += 2) {
+          if (n0 + c * 16 >= a.cout) break;                       // uniform over the group
+          uint32_t wh[2][8], wl[2][8];
+          // all accumulator reads of the round (2 chunks x both halves) are issued before the one wait
+          uint32_t va[2][16], vb[NCAT ? 2 : 1][16];
+          tmem_ld16(taddr + c * 16, va[0]);
+          tmem_ld16(taddr + (c + 1) * 16, va[1]);
+          if constexpr (NCAT) {
+            tmem_ld16(taddr + BN + c * 16, vb[0]);
+            tmem_ld16(taddr + BN + (c + 1) * 16, vb[1]);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc) {
+            uint32_t (&v)[16] = va[hc];
+            if constexpr (NCAT) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vb[hc][j]));
+            }
+            const int nb = n0 + (c + hc) * 16;
+            float f[16];
+            if constexpr (P == 2) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), a.acc_scale, sbias[(c + hc) * 16 + j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + sbias[(c + hc) * 16 + j];
+            }
+            if (a.res && ok && nb < a.cout) {
+              if constexpr (P == 2) {
+                const uint16_t *rh = static_cast<const uint16_t *>(a.res) + pix * a.cout_store + nb;
+                const uint4 h0_ = __ldg(reinterpret_cast<const uint4 *>(rh)), h1_ = __ldg(reinterpret_cast<const uint4 *>(rh) + 1);
+                const uint4 l0_ = __ldg(reinterpret_cast<const uint4 *>(rh + a.dst_plane)), l1_ = __ldg(reinterpret_cast<const uint4 *>(rh + a.dst_plane) + 1);
+                const uint32_t hw_[8] = {h0_.x, h0_.y, h0_.z, h0_.w, h1_.x, h1_.y, h1_.z, h1_.w};
+                const uint32_t lw_[8] = {l0_.x, l0_.y, l0_.z, l0_.w, l1_.x, l1_.y, l1_.z, l1_.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float2 x = join2(hw_[j], lw_[j], a.fmt);
+                  f[2 * j] += x.x; f[2 * j + 1] += x.y;
+                }
+              } else {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(static_cast<const __nv_bfloat16 *>(a.res) + pix * a.cout_store + nb);
+                const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rw[j]));
+                  f[2 * j] += x.x; f[2 * j + 1] += x.y;
+                }
+              }
+            }
+            if constexpr (P == 2) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                split2(cpb::act_fn(f[2 * j], act), cpb::act_fn(f[2 * j + 1], act), a.fmt, wh[hc][j], wl[hc][j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const __nv_bfloat162 b2 = __floats2bfloat162_rn(cpb::act_out<__nv_bfloat16>(f[2 * j], act), cpb::act_out<__nv_bfloat16>(f[2 * j + 1], act));
+                wh[hc][j] = *reinterpret_cast<const uint32_t *>(&b2);
+              }
+            }
+          }
+          if (a.dbg & 32u) {                                       // timing knob: accumulators read and converted, nothing stored
+            if (wh[0][0] == 0x12345678u && wl[1][7] == 0x9abcdef0u) asm volatile("st.shared.b32 [%0], %1;" ::"r"(srow), "r"(wh[1][3]) : "memory");
+            continue;
+          }
+          // the copy engine has finished READING the staging tile of the previous round
+          if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t d = srow + (((uint32_t)j ^ sx) << 4);
+            const uint32_t *w_ = &wh[j >> 1][(j & 1) * 4];
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d), "r"(w_[0]), "r"(w_[1]), "r"(w_[2]), "r"(w_[3]) : "memory");
+            if constexpr (P == 2) {
+              const uint32_t *l_ = &wl[j >> 1][(j & 1) * 4];
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(d + 8192u), "r"(l_[0]), "r"(l_[1]), "r"(l_[2]), "r"(l_[3]) : "memory");
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(3 + grp) : "memory");
+          if (et == 0 && valid) {
+            tma_store_4d(&a.dmap, stg, n0 + c * 16, w0, h0, n);
+            if constexpr (P == 2) tma_store_4d(&a.dmap, stg + 8192u, n0 + c * 16, w0, h0, n + a.B);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c = (a.dbg & 2u) ? c_last : c_first; c < c_last; ++c) {
         uint32_t v[16];
@@ -578,6 +678,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
       acc += tstep; par ^= 1;
       if (acc >= a.nacc) { acc -= a.nacc; accphase ^= 1; }
     }
+    if (a.tstore && et == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // staging is read out before the CTA ends
   }
 
   tc_fence_before();
@@ -594,6 +695,8 @@ struct C3Op {
   C3Args args;
   int BN, P, grid;
   size_t smem;
+  void *dst_mapped = nullptr;   // the output pointer args.dmap was encoded for
+  int B = 0, Ho = 0, Wo = 0, cout = 0;
 };
 
 template <int BN, int P>
@@ -643,7 +746,7 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
   C3Args &a = t->args;
   memset(&a, 0, sizeof(a));
   const int P = op.act_dtype == CPB200_BF16 ? 1 : 2;
-  t->P = P;
+  t->P = P; t->B = op.B; t->Ho = op.Ho; t->Wo = op.Wo; t->cout = op.cout;
   a.fmt = op.act_dtype == CPB200_F16X2 ? 1u : 0u;
   a.acc_scale = (op.acc_scale != 0.f ? op.acc_scale : 1.f);
   a.dst_plane = (long long)op.B * op.Ho * op.Wo * op.cout;
@@ -721,6 +824,36 @@ void *c3_prepare(const cpb200_op &op, int *rc) {
     }
   }
   const CUtensorMapDataType dt = a.fmt ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  // TMA-store epilogue (16-bit NHWC outputs): staging = 2 epilogue groups x P planes x (128 rows x 64 B) behind the rings.  It is
+  // taken from what the 227 KB leave after the static part; a streamed-weight ring gives up one stage for it if it has more
+  // than two, resident weights keep the direct 32-byte stores when the staging does not fit.
+  a.tstore = 0;
+  {
+    const char *e = getenv("CPB200_C3_TSTORE");
+    const size_t stg_bytes = (size_t)2 * P * 8192;
+    const size_t max_dyn = 232448 - (1536 + 16 * (size_t)BN);
+    const bool want = !(e && e[0] == '0') && !(op.flags & CPB200_FLAG_OUT_F32) && BN >= 32 && !a.mcast && op.cout % 8 == 0 &&
+                      (reinterpret_cast<uintptr_t>(op.dst) & 15) == 0;
+    if (want) {
+      if (t->smem + stg_bytes > max_dyn && !a.b_resident && a.nb > 2) {
+        --a.nb;
+        t->smem = a.na * (size_t)a.a_stage_bytes + a.nb * (size_t)a.b_stage_bytes + 1024;
+      }
+      if (t->smem + stg_bytes <= max_dyn) {
+        a.tstore = 1;
+        a.stg_off = (unsigned)(t->smem - 1024);
+        t->smem += stg_bytes;
+        const cuuint64_t dims[4] = {(cuuint64_t)op.cout, (cuuint64_t)op.Wo, (cuuint64_t)op.Ho, (cuuint64_t)op.B * P};
+        const cuuint64_t strides[3] = {(cuuint64_t)op.cout * 2, (cuuint64_t)op.Wo * op.cout * 2, (cuuint64_t)op.Ho * op.Wo * op.cout * 2};
+        const cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+        const cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&a.dmap, dt, 4, op.dst, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { delete t; *rc = fail(CPB200_ERR_CUDA, "tc3: cuTensorMapEncodeTiled(dst) failed: %d", (int)r); return nullptr; }
+        t->dst_mapped = op.dst;
+      }
+    }
+  }
   {
     // split activations: the lo plane follows the hi plane, i.e. a batch of 2B images
     const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)op.W, (cuuint64_t)op.H, (cuuint64_t)op.B * P};
@@ -752,6 +885,20 @@ int c3_run(const void *h, const cpb200_op &op, cudaStream_t st) {
   const C3Op *t = static_cast<const C3Op *>(h);
   C3Args args = t->args;
   args.dst = op.dst; args.res = op.res; args.bias = op.bias;
+  if (args.tstore && op.dst != t->dst_mapped) {
+    // the caller re-bound the output (cpb200_prepare_ops contract: dst is read live): re-encode the store map for this run
+    if ((reinterpret_cast<uintptr_t>(op.dst) & 15) != 0) return fail(CPB200_ERR_ARG, "tc3: re-bound dst must be 16-byte aligned");
+    EncodeTiledFn enc = get_encode();
+    const int P = t->P;
+    const cuuint64_t dims[4] = {(cuuint64_t)t->cout, (cuuint64_t)t->Wo, (cuuint64_t)t->Ho, (cuuint64_t)t->B * P};
+    const cuuint64_t strides[3] = {(cuuint64_t)t->cout * 2, (cuuint64_t)t->Wo * t->cout * 2, (cuuint64_t)t->Ho * t->Wo * t->cout * 2};
+    const cuuint32_t box[4] = {32, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    if (!enc || enc(&args.dmap, args.fmt ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, op.dst, dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return fail(CPB200_ERR_CUDA, "tc3: cuTensorMapEncodeTiled(dst) failed");
+  }
 #define C3_CASE(N)                                                                                   \
   case N: return t->P == 2 ? launch_c3<N, 2>(*t, args, st) : launch_c3<N, 1>(*t, args, st);
   switch (t->BN) {
