@@ -270,10 +270,11 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
                   if constexpr (P == 2) return __float_as_uint(w);
                   __nv_bfloat162 b = __float2bfloat162_rn(w); return *reinterpret_cast<uint32_t *>(&b);
                 };
-                if (h_low >= 0 && w_low >= 0) { pr.off[0] = ((rowb + h_low) * a.W + w_low) * Cin; pr.wt[0] = pk(hh * hw * mk); }
-                if (h_low >= 0 && w_high <= a.W - 1) { pr.off[1] = ((rowb + h_low) * a.W + w_high) * Cin; pr.wt[1] = pk(hh * lw * mk); }
-                if (h_high <= a.H - 1 && w_low >= 0) { pr.off[2] = ((rowb + h_high) * a.W + w_low) * Cin; pr.wt[2] = pk(lh * hw * mk); }
-                if (h_high <= a.H - 1 && w_high <= a.W - 1) { pr.off[3] = ((rowb + h_high) * a.W + w_high) * Cin; pr.wt[3] = pk(lh * lw * mk); }
+                constexpr int OS = P == 2 ? 2 : 1;       // P = 2 gathers with 32-bit BYTE offsets from the tensor base
+                if (h_low >= 0 && w_low >= 0) { pr.off[0] = ((rowb + h_low) * a.W + w_low) * Cin * OS; pr.wt[0] = pk(hh * hw * mk); }
+                if (h_low >= 0 && w_high <= a.W - 1) { pr.off[1] = ((rowb + h_low) * a.W + w_high) * Cin * OS; pr.wt[1] = pk(hh * lw * mk); }
+                if (h_high <= a.H - 1 && w_low >= 0) { pr.off[2] = ((rowb + h_high) * a.W + w_low) * Cin * OS; pr.wt[2] = pk(lh * hw * mk); }
+                if (h_high <= a.H - 1 && w_high <= a.W - 1) { pr.off[3] = ((rowb + h_high) * a.W + w_high) * Cin * OS; pr.wt[3] = pk(lh * lw * mk); }
               }
             }
             s_prm[gw][tap][px] = pr;
@@ -326,13 +327,17 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
       } else {
         uint4 vh[4], vl[4];
         float wq[4];
-        const __nv_bfloat16 *srcl = srcc + a.src_plane;      // lo plane (16-bit elements either format)
+        // addresses = uniform tensor base + a 32-bit byte offset (one integer add per load; the host checks < 4 GiB)
+        const char *srcb = reinterpret_cast<const char *>(a.dcn_src);
+        const uint32_t lane_b = (uint32_t)chunk * 16u, plane_b = (uint32_t)(a.src_plane * 2);
         auto issue = [&](int tap, int c0, int i) {
           const DcnPrm q = s_prm[gw][tap][i * 4 + rsub];
+          const uint32_t cb = lane_b + (uint32_t)c0 * 2u;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {         // invalid corners: weight 0, offset 0 (a safe address)
-            vh[c] = __ldg(reinterpret_cast<const uint4 *>(srcc + (size_t)(unsigned)q.off[c] + c0));
-            vl[c] = __ldg(reinterpret_cast<const uint4 *>(srcl + (size_t)(unsigned)q.off[c] + c0));
+            const uint32_t e = (uint32_t)q.off[c] + cb;
+            vh[c] = __ldg(reinterpret_cast<const uint4 *>(srcb + e));
+            vl[c] = __ldg(reinterpret_cast<const uint4 *>(srcb + (e + plane_b)));
             wq[c] = __uint_as_float(q.wt[c]);
           }
         };
@@ -342,28 +347,65 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
           int tap_n = tap_c, c0_n = c0_c + 64;
           if (c0_n >= Cin) { c0_n = 0; ++tap_n; }
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          if (a.dcn_prefetch & 1) {                              // timing knob (CPB200_TC_DBG=1): no gather work at all
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full0 + 8 * stage);
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           const uint32_t sa = smem_base + stage * stage_bytes;
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = 0.f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const uint32_t hw_[4] = {vh[c].x, vh[c].y, vh[c].z, vh[c].w};
-              const uint32_t lw_[4] = {vl[c].x, vl[c].y, vl[c].z, vl[c].w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 x = join2(hw_[j], lw_[j], a.fmt);
-                f[2 * j] = fmaf(wq[c], x.x, f[2 * j]); f[2 * j + 1] = fmaf(wq[c], x.y, f[2 * j + 1]);
-              }
-            }
-            // the registers are free again: the next unit's corners fly while this one is split and stored
-            if (i == 0) issue(tap_c, c0_c, 1);
-            else if (k + 1 < nk) issue(tap_n, c0_n, 0);
             uint32_t oh[4], ol[4];
+            if (a.fmt) {
+              // fp16 planes: sample = sum_c w_c * hi_c (fp32 FMAs on the unpacked hi plane) + sum_c w_c * lo_c.  The second sum is
+              // 2^-11 of the first, so packed fp16 FMAs on the lo plane as stored (weights rounded to fp16: error 2^-11 of
+              // 2^-11) leave the sample good to 2^-22 — and save the lo plane's unpack and the hi + lo adds (a third of the
+              // gather's arithmetic instructions; the gather's instruction count is what bounds the DCN, r02_dcn_whatif.md).
+              __half2 s2[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) split2_bounded(f[2 * j], f[2 * j + 1], a.fmt, oh[j], ol[j]);   // |blend| <= max|x|: no saturation needed
+              for (int j = 0; j < 4; ++j) s2[j] = __float2half2_rn(0.f);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t hw_[4] = {vh[c].x, vh[c].y, vh[c].z, vh[c].w};
+                const uint32_t lw_[4] = {vl[c].x, vl[c].y, vl[c].z, vl[c].w};
+                const __half2 w2 = __float2half2_rn(wq[c]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 x = __half22float2(*reinterpret_cast<const __half2 *>(&hw_[j]));
+                  f[2 * j] = fmaf(wq[c], x.x, f[2 * j]); f[2 * j + 1] = fmaf(wq[c], x.y, f[2 * j + 1]);
+                  s2[j] = __hfma2(w2, *reinterpret_cast<const __half2 *>(&lw_[j]), s2[j]);
+                }
+              }
+              // the registers are free again: the next unit's corners fly while this one is split and stored
+              if (i == 0) issue(tap_c, c0_c, 1);
+              else if (k + 1 < nk) issue(tap_n, c0_n, 0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {                  // |blend| <= max|x|: no saturation needed
+                const __half2 h = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __hadd2(__floats2half2_rn(f[2 * j] - hf.x, f[2 * j + 1] - hf.y), s2[j]);
+                oh[j] = *reinterpret_cast<const uint32_t *>(&h); ol[j] = *reinterpret_cast<const uint32_t *>(&l);
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const uint32_t hw_[4] = {vh[c].x, vh[c].y, vh[c].z, vh[c].w};
+                const uint32_t lw_[4] = {vl[c].x, vl[c].y, vl[c].z, vl[c].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 x = join2(hw_[j], lw_[j], 0u);
+                  f[2 * j] = fmaf(wq[c], x.x, f[2 * j]); f[2 * j + 1] = fmaf(wq[c], x.y, f[2 * j + 1]);
+                }
+              }
+              if (i == 0) issue(tap_c, c0_c, 1);
+              else if (k + 1 < nk) issue(tap_n, c0_n, 0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) split2_bounded(f[2 * j], f[2 * j + 1], 0u, oh[j], ol[j]);
+            }
             const int row = gw * 8 + i * 4 + rsub;
             const uint32_t dst = sa + row * 128 + ((chunk ^ (row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(oh[0]), "r"(oh[1]), "r"(oh[2]), "r"(oh[3]) : "memory");
@@ -399,7 +441,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
       const size_t pix = ((size_t)n * a.Hd + (ho * a.sy + a.oy)) * a.Wd + (wo * a.sx + a.ox);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
 #pragma unroll 1
-      for (int c = 0; c < BN / 16; ++c) {
+      for (int c = (a.dcn_prefetch & 2) ? BN / 16 : 0; c < BN / 16; ++c) {
         uint32_t v[16];
         tmem_ld16(taddr + c * 16, v);
         if constexpr (NCAT) {
@@ -643,6 +685,8 @@ int tc_prepare_op(cpb200_op &op) {
   a.dst = op.dst; a.res = op.res; a.bias = op.bias; a.flags = op.flags;
   a.dst_plane = (long long)op.B * op.Hd * op.Wd * op.cout;
   a.src_plane = (long long)op.B * op.H * op.W * op.cin[0];
+  if (dcn && P == 2 && a.src_plane * 4 >= (1LL << 32)) { delete t;
+    return fail(CPB200_ERR_ARG, "tc: split-precision DCN input must stay below 4 GiB (32-bit gather offsets)"); }
   a.wplane = op.kh * op.kw * (cin_total / bk);
   const size_t a_bytes = (size_t)P * TILE_M * bk * 2, b_bytes = ((size_t)P * BN * bk * 2 + 1023) / 1024 * 1024;
   const size_t budget = dcn ? 176 * 1024 : 200 * 1024;     // the DCN variant keeps 39 KB of sampling parameters in static smem
@@ -699,6 +743,7 @@ int tc_run_op(const cpb200_op &op, cudaStream_t st) {
   TcArgs args = t->args;
   args.dst = op.dst; args.res = op.res; args.bias = op.bias;
   args.dcn_om = static_cast<const float *>(op.aux);
+  if (const char *e = getenv("CPB200_TC_DBG")) args.dcn_prefetch = atoi(e);      // timing experiments (results are garbage)
 #define TC_CASE(N, D)                                                                                  \
   case N: return t->P == 2 ? launch_tc<N, D, 2>(*t, args, st) : launch_tc<N, D, 1>(*t, args, st);
   if (t->dcn) {
