@@ -718,7 +718,31 @@ class Plan:
         if not self._prepared:
             _lib.check(L.cpb200_prepare_ops(self.ops, self.n), "prepare_ops")
             self._prepared = True
-        _lib.check(L.cpb200_run_ops(self.ops, self.n, stream), "run_ops")
+        _lib.check(L.cpb200_run_ops(self.ops, ctypes.c_int(self.n), ctypes.c_void_p(stream)), "run_ops")
+
+    def profile_ops(self, stream: int, reps: int = 3):
+        """CUDA-event time of every op launched ON ITS OWN (ms, best of ``reps``), after one full run has filled the buffers.
+        Serialised launches on whatever the earlier ops left in the (recycled) buffers: per-op SHARES of a step and per-op
+        rates, not a step time.  Returns [(op type, flags, B, Ho, Wo, cout, cin_total, kh, kw, ms)]."""
+        L = _lib.lib()
+        self.run(stream)
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        out = []
+        step = ctypes.sizeof(OpStruct)
+        base = ctypes.addressof(self.ops)
+        for i in range(self.n):
+            one = ctypes.cast(base + i * step, ctypes.POINTER(OpStruct))
+            best = None
+            for _ in range(reps):
+                ev0.record()
+                _lib.check(L.cpb200_run_ops(one, ctypes.c_int(1), ctypes.c_void_p(stream)), "run_ops")
+                ev1.record(); ev1.synchronize()
+                t = ev0.elapsed_time(ev1)
+                best = t if best is None or t < best else best
+            o = self.ops[i]
+            out.append((int(o.type), int(o.flags), int(o.B), int(o.Ho), int(o.Wo), int(o.cout),
+                        int(sum(o.cin[j] for j in range(o.nsrc))), int(o.kh), int(o.kw), best))
+        return out
 
     def __del__(self):
         try:

@@ -350,3 +350,50 @@ def test_conv_cta_pair_path(precision, B, ci, co, H, W, res):
     err = (got - ref).abs().max().item(); scale = ref.abs().max().item()
     tol = 1e-2 if precision == "bf16" else OP_TOL[precision]
     assert err <= tol * scale, (precision, err, scale, err / scale)
+
+
+@pytest.mark.parametrize("precision", ["fp16x2", "bf16"])
+def test_halo_conv_output_rebinding_and_direct_store_epilogue(precision):
+    """The halo conv's TMA-store epilogue encodes a tensor map for the output at prepare time; `dst` is nevertheless read live
+    (include/centerpose_b200.h, cpb200_prepare_ops): re-binding it after the first run must write the new buffer (the map is
+    re-encoded) and leave the old one untouched.  CPB200_C3_TSTORE=0 (direct 32-byte stores) must give the same bits."""
+    from centerpose_b200.plan import PlanBuilder
+    g = torch.Generator().manual_seed(77)
+    B, ci, co, H, W = 2, 64, 128, 24, 40                     # partial tiles in both directions (TMA clips them)
+    x = torch.randn(B, ci, H, W, generator=g)
+    w = torch.randn(co, ci, 3, 3, generator=g) / (ci * 9) ** 0.5
+    b = torch.randn(co, generator=g)
+    if precision == "bf16":
+        x = x.bfloat16().float(); w = w.bfloat16().float()
+
+    def build():
+        pb = PlanBuilder(B, 1, 1, precision, torch.device(DEV))
+        sx = pb.external(x.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16)) if precision == "bf16" else pb.external(_nhwc(x))
+        y = pb.conv([sx], w.to(DEV), b.to(DEV), stride=1, pad=1, relu=True)
+        return pb, y, pb.build()
+
+    st = torch.cuda.current_stream().cuda_stream
+    pb, y, plan = build()
+    plan.run(st); torch.cuda.synchronize()
+    first = plan.tensor(y).clone()
+    raw_first = y.buf.clone()
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1))
+    err = (_nchw(first) - ref).abs().max().item()
+    assert err <= (1e-2 if precision == "bf16" else OP_TOL[precision]) * ref.abs().max().item()
+    # re-bind: a fresh, poisoned buffer of the same size
+    new = torch.full_like(y.buf, 0x7F)
+    y.buf.fill_(0x55)
+    i = [k for k in range(plan.n) if plan.pb.ops[k].dst is y][0]
+    plan.ops[i].dst = new.data_ptr()
+    plan.run(st); torch.cuda.synchronize()
+    assert bool((y.buf == 0x55).all()), "the old output buffer was written after re-binding"
+    n_used = raw_first.numel() if precision != "bf16" else B * H * W * co * 2
+    assert torch.equal(new[:n_used], raw_first[:n_used])
+    # the direct-store epilogue gives the same bits
+    os.environ["CPB200_C3_TSTORE"] = "0"
+    try:
+        pb2, y2, plan2 = build()
+        plan2.run(st); torch.cuda.synchronize()
+        assert torch.equal(y2.buf[:n_used], raw_first[:n_used])
+    finally:
+        os.environ.pop("CPB200_C3_TSTORE", None)
