@@ -518,19 +518,16 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
             if (a.res && ok && nb < a.cout) {
               if constexpr (P == 2) {
                 const uint16_t *rh = static_cast<const uint16_t *>(a.res) + pix * a.cout_store + nb;
-                const uint4 h0_ = __ldg(reinterpret_cast<const uint4 *>(rh)), h1_ = __ldg(reinterpret_cast<const uint4 *>(rh) + 1);
-                const uint4 l0_ = __ldg(reinterpret_cast<const uint4 *>(rh + a.dst_plane)), l1_ = __ldg(reinterpret_cast<const uint4 *>(rh + a.dst_plane) + 1);
-                const uint32_t hw_[8] = {h0_.x, h0_.y, h0_.z, h0_.w, h1_.x, h1_.y, h1_.z, h1_.w};
-                const uint32_t lw_[8] = {l0_.x, l0_.y, l0_.z, l0_.w, l1_.x, l1_.y, l1_.z, l1_.w};
+                uint32_t hw_[8], lw_[8];                          // 32-byte sector loads, like the stores
+                ld_global_nc_32B(rh, hw_); ld_global_nc_32B(rh + a.dst_plane, lw_);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const float2 x = join2(hw_[j], lw_[j], a.fmt);
                   f[2 * j] += x.x; f[2 * j + 1] += x.y;
                 }
               } else {
-                const uint4 *rp = reinterpret_cast<const uint4 *>(static_cast<const __nv_bfloat16 *>(a.res) + pix * a.cout_store + nb);
-                const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-                const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                uint32_t rw[8];
+                ld_global_nc_32B(static_cast<const __nv_bfloat16 *>(a.res) + pix * a.cout_store + nb, rw);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&rw[j]));

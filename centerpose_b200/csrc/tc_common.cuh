@@ -41,6 +41,11 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// 256-bit read-only global load (sm_100: LDG.E.256.CONSTANT): one 32-byte sector per thread
+__device__ __forceinline__ void ld_global_nc_32B(const void *p, uint32_t (&w)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+}
 // 256-bit global store (sm_100: STG.E.256): one full 32-byte sector per thread
 __device__ __forceinline__ void st_global_32B(void *p, const uint32_t (&w)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
