@@ -15,7 +15,7 @@ OPS = {
     "head3x3": ("conv", 64, 256, 128, 3, 1), "conv64": ("conv", 64, 64, 128, 3, 1), "conv128": ("conv", 128, 128, 64, 3, 1),
     "conv256": ("conv", 256, 256, 32, 3, 1), "conv512": ("conv", 512, 512, 16, 3, 1), "om64": ("conv", 64, 27, 128, 3, 1),
     "level0": ("conv", 16, 16, 512, 3, 1), "level1": ("conv", 16, 32, 512, 3, 2), "root448": ("conv", 448, 128, 64, 1, 1),
-    "head1x1": ("conv", 256, 34, 128, 1, 1), "reshead": ("conv", 256, 64, 128, 3, 1), "res1x1": ("conv", 64, 256, 128, 1, 1), "stem": ("stem",),
+    "up64": ("up", 64, 64, 2), "up64x4": ("up", 64, 32, 4), "pool32": ("pool", 32, 256), "head1x1": ("conv", 256, 34, 128, 1, 1), "reshead": ("conv", 256, 64, 128, 3, 1), "res1x1": ("conv", 64, 256, 128, 1, 1), "stem": ("stem",),
 }
 
 
@@ -36,6 +36,17 @@ def main():
         y = pb.stem(pb.input(3), torch.randn(16, 3, 7, 7, generator=g).to(dev) * 0.1, torch.zeros(16, device=dev), 7, 1, 3)
         flops = 2.0 * B * 512 * 512 * 16 * 147
         name = name + ("(tc)" if (pb.ops[0].flags & 8 or len(pb.ops) == 2) else "(simt)")
+    elif spec[0] == "up":                        # IDAUp depthwise ConvTranspose2d(k=2f, s=f) + skip add
+        _, c, hw, f = spec
+        xin = torch.randn(B, hw, hw, c, generator=g).to(dev, adt)
+        sk = torch.randn(B, hw * f, hw * f, c, generator=g).to(dev, adt)
+        y = pb.up_add(pb.external(xin), pb.external(sk), torch.randn(c, 1, 2 * f, 2 * f, generator=g).to(dev) * 0.2)
+        flops = 2.0 * B * (hw * f) ** 2 * c * 4
+    elif spec[0] == "pool":
+        _, c, hw = spec
+        xin = torch.randn(B, hw, hw, c, generator=g).to(dev, adt)
+        y = pb.maxpool(pb.external(xin), 2, 2)
+        flops = 1.0 * B * (hw // 2) ** 2 * c * 4
     elif spec[0] == "dcn":
         _, ci, co, hw = spec
         xin = torch.randn(B, hw, hw, ci, generator=g).to(dev, adt)
