@@ -842,6 +842,7 @@ __global__ void __launch_bounds__(256) dwdeconv_add_split_fast_kernel(const uint
       o[2 * j] = a.x + c.x; o[2 * j + 1] = a.y + c.y;
     }
   };
+#pragma unroll 2                                             // two pixels' loads in flight per thread (HBM-bound kernel)
   for (int i = i0; i < Wo * CV; i += 256) {
     const int wo = i >> lcv;
     const size_t opix = (orow + wo) * C + cv * VEC;
