@@ -7,7 +7,9 @@ Faithful to the reference's quirks because callers consume the mutated array, no
 moved, the 17 keypoint-score columns 39..55 never move (``nms.pyx:214-217``); a row whose score
 falls below ``threshold`` gets columns 0..4 overwritten by the last live row and columns 5..38
 swapped with it (``:257-268``); all arithmetic is C ``float``.
-N <= 100 x scales, O(N^2) on the host exactly as in the reference (a GPU version is a "next" row)."""
+N <= 100 x scales, O(N^2) on the host exactly as in the reference.  The device version is ``cpb200_soft_nms_39``
+(``csrc/post.cu``; ``detector.merge_outputs_device`` / ``run_batch_fused(nms=True)`` use it); this port serves
+``merge_outputs``, whose inputs are host arrays as in the reference."""
 from __future__ import annotations
 
 import numpy as np

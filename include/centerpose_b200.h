@@ -55,6 +55,8 @@ unsigned long long cpb200_launch_count(void);
  *   out       (B,K,5+3J)  [x1,y1,x2,y2, score, J*(x,y), J*kp_score]
  *
  * 1 <= K <= min(H*W, CPB200_DECODE_MAX_K); 1 <= J <= CPB200_DECODE_MAX_J.
+ * ONE class channel only (`heat` is (B,1,H,W), the COCO pose task): the reference's _topk additionally merges the per-class
+ * top-K lists (decode.py:108-113); a multi-class heat-map is rejected by the host shims instead of being decoded wrongly.
  * Tie order (implementation-defined in the reference) is fixed: value descending, then
  * flat index ascending; nearest-candidate ties -> first (best-scored) candidate.
  * `workspace` must hold cpb200_decode_workspace_bytes(B,J,K) bytes, be 16-byte aligned and
