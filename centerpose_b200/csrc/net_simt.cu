@@ -875,6 +875,39 @@ __global__ void __launch_bounds__(256) dwdeconv_add_split_fast_kernel(const uint
   }
 }
 
+
+// ---- space-to-depth of the network input (CPB200_OP_S2D): NCHW fp32 (B,3,H,W) -> split planes (B,H/2,W/2,16) ----
+// Thread = one output pixel: six coalesced float2 loads (channel c, row parity py: the two column parities), channel
+// (py*2+px)*3 + c, channels 12..15 zero; one 32-byte store per plane.
+__global__ void __launch_bounds__(256) s2d_split_kernel(const float *__restrict__ x, uint16_t *__restrict__ y, int B, int H, int W,
+                                                        size_t plane, uint32_t fmt) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)B * Ho * Wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % Wo);
+    long long p = i / Wo;
+    const int ho = (int)(p % Ho), b = (int)(p / Ho);
+    float v[16];
+#pragma unroll
+    for (int j = 12; j < 16; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int py = 0; py < 2; ++py) {
+        const float2 t = __ldg(reinterpret_cast<const float2 *>(x + (((size_t)b * 3 + c) * H + 2 * ho + py) * W + 2 * wo));
+        v[(py * 2 + 0) * 3 + c] = t.x; v[(py * 2 + 1) * 3 + c] = t.y;
+      }
+    uint32_t oh[8], ol[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) Sp16::split2(v[2 * j], v[2 * j + 1], fmt, oh[j], ol[j]);
+    uint16_t *o = y + (size_t)i * 16;
+    *reinterpret_cast<uint4 *>(o) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<uint4 *>(o + 8) = make_uint4(oh[4], oh[5], oh[6], oh[7]);
+    *reinterpret_cast<uint4 *>(o + plane) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+    *reinterpret_cast<uint4 *>(o + plane + 8) = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+  }
+}
+
 int run_op_split(const cpb200_op &op, cudaStream_t st) {
   const uint32_t fmt = op.act_dtype == CPB200_F16X2 ? 1u : 0u;
   switch (op.type) {
@@ -887,6 +920,15 @@ int run_op_split(const cpb200_op &op, cudaStream_t st) {
       else
         convert_to_split_kernel<<<grid, 256, 0, st>>>(static_cast<const float *>(op.src[0]), static_cast<uint16_t *>(op.dst), n / 4, (size_t)n, fmt);
       return cpb::check_launch("convert_split_kernel");
+    }
+    case CPB200_OP_S2D: {
+      if (op.cin[0] != 3 || op.cout != 16 || (op.H & 1) || (op.W & 1) || op.Ho != op.H / 2 || op.Wo != op.W / 2)
+        return cpb::fail(CPB200_ERR_ARG, "s2d: needs a (B,3,H,W) input with even H, W and a 16-channel (B,H/2,W/2) output");
+      const long long total = (long long)op.B * op.Ho * op.Wo;
+      const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 16);
+      s2d_split_kernel<<<grid, 256, 0, st>>>(static_cast<const float *>(op.src[0]), static_cast<uint16_t *>(op.dst), op.B, op.H, op.W,
+                                             (size_t)total * 16, fmt);
+      return cpb::check_launch("s2d_split_kernel");
     }
     case CPB200_OP_MAXPOOL: {
       if (op.cin[0] % 4) return cpb::fail(CPB200_ERR_ARG, "maxpool: C %% 4 != 0");

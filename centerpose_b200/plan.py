@@ -25,7 +25,7 @@ import torch
 from . import _lib
 
 OP_CONV, OP_STEM, OP_MAXPOOL, OP_DWDECONV_ADD, OP_DCN, OP_IM2COL_W, OP_UPSAMPLE_ADD = 1, 2, 3, 4, 5, 6, 7
-OP_DWCONV, OP_AVGPOOL, OP_SCALE_ADD, OP_CONVERT = 8, 9, 10, 11
+OP_DWCONV, OP_AVGPOOL, OP_SCALE_ADD, OP_CONVERT, OP_S2D = 8, 9, 10, 11, 12
 FLAG_RELU, FLAG_OUT_NCHW_F32, FLAG_OUT_F32, FLAG_TC, FLAG_HSWISH, FLAG_HSIGMOID, FLAG_TO_F32 = 1, 2, 4, 8, 16, 32, 64
 _ACT_FLAG = {None: 0, "relu": FLAG_RELU, "hswish": FLAG_HSWISH, "hsigmoid": FLAG_HSIGMOID}
 F32, BF16, BF16X2, F16X2 = 0, 1, 2, 3
@@ -371,6 +371,28 @@ class PlanBuilder:
             # w2[o, s*ci + c, r, 0] = w[o, c, r, s]
             w2[:, :k * ci, :, 0] = w.float().permute(0, 3, 1, 2).reshape(co, k * ci, k)
             return self.conv([t], w2, b.float(), stride=1, relu=relu, pad_hw=(pad, 0))
+        if (self.use_tc and self.split and mode != "0" and stride == 2 and ci == 3 and k in (3, 7) and pad == k // 2
+                and co % 16 == 0 and x.H % 2 == 0 and x.W % 2 == 0 and x.kind == "nchw_in"
+                and os.environ.get("CPB200_S2D_STEM", "1") != "0"):
+            # Stride-2 stems in split precisions (ResNet 7x7, HRNet 3x3): space-to-depth of the image (OP_S2D: 2x2 pixel
+            # blocks -> 12 of 16 channels) turns  out[o] = sum_r w[r] x[2o - pad + r]  into a STRIDE-1 conv over the half-
+            # resolution map: input index 2o - pad + r = 2 (o + q) + parity with q = floor((r - pad) / 2), parity =
+            # (r - pad) & 1, so a 7-tap filter becomes taps q = -2..1 (a 5x5 conv, pad 2, last tap zero) and a 3-tap filter
+            # q = -1..0 (a 3x3 conv, pad 1).  It then runs on the split tensor-core halo kernel instead of a CUDA-core
+            # fp32 island (ResNet-50 B=16: 954 us + a CONVERT pass).
+            z = self._sym(16, x.H // 2, x.W // 2)
+            self._emit(_PendingOp(type=OP_S2D, flags=0, k=(2, 2), stride=2, pad=(0, 0), weight=None, bias=None, cout=16), [x], z)
+            k2 = (k + 1) // 2 + 1
+            p2 = k2 // 2
+            w2 = torch.zeros(co, 16, k2, k2, dtype=torch.float32, device=w.device)
+            wf = w.float()
+            for r in range(k):
+                qy, py = (r - pad) // 2, (r - pad) & 1
+                for q in range(k):
+                    qx, px = (q - pad) // 2, (q - pad) & 1
+                    c0 = (py * 2 + px) * 3
+                    w2[:, c0:c0 + 3, qy + p2, qx + p2] = wf[:, :, r, q]
+            return self.conv([z], w2, b.float(), stride=1, pad=p2, relu=relu, act=act)
         flags = _ACT_FLAG[act] if act else (FLAG_RELU if relu else 0)
         Ho = (x.H + 2 * pad - k) // stride + 1; Wo = (x.W + 2 * pad - k) // stride + 1
         if (self.use_tc and mode != "0" and k == 7 and ci == 3 and pad == 3 and stride in (1, 2) and co in (16, 64)

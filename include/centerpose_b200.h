@@ -158,9 +158,14 @@ enum cpb200_op_type {
   CPB200_OP_AVGPOOL = 9,     /* global average pool (B,H,W,C) -> (B,1,1,C)  (SeModule, mobilenetv3.py:100)           */
   CPB200_OP_SCALE_ADD = 10,  /* dst = src[0] * res[b,c] (+ aux skip): SE gate + block shortcut (mobilenetv3.py:111,146);
                                 `res` is the (B,1,1,C) gate vector                                                  */
-  CPB200_OP_CONVERT = 11     /* NHWC activation (B,H,W,cin[0]) between fp32 and the split 16-bit pair layout named by
+  CPB200_OP_CONVERT = 11,    /* NHWC activation (B,H,W,cin[0]) between fp32 and the split 16-bit pair layout named by
                                 act_dtype (CPB200_BF16X2 / CPB200_F16X2): fp32 -> planes, or planes -> fp32 with
                                 CPB200_FLAG_TO_F32.  Lets ops without a native split kernel run on fp32 in between.   */
+  CPB200_OP_S2D = 12         /* space-to-depth of the network input for stride-2 stems in split precisions: NCHW fp32
+                                (B,3,H,W) (H, W even) -> split NHWC planes (B,H/2,W/2,16), channel (py*2+px)*3 + c =
+                                x[c][2h+py][2w+px], channels 12..15 zero.  A k x k / stride-2 / pad k/2 stem
+                                (msra_resnet.py:116-117 7x7, pose_higher_hrnet.py:283-284 3x3) is then a stride-1
+                                (k+1)/2+1-tap conv over 16 channels on the tensor-core path; src[0] is read live.   */
 };
 /* A dense ConvTranspose2d(k4,s2,p1) (msra_resnet.py:168-193) is lowered by the host into four
  * 2x2 CONV ops, one per output parity, using pad_h/pad_w and the strided-output fields below. */

@@ -134,17 +134,31 @@ def test_split_roundtrip_maxpool_upadd_stem(precision):
         pb = _builder(B, precision)
         y = pb.up_add(pb.external(_nhwc(xx)), pb.external(_nhwc(skip)), ww.to(DEV))
         _close(_nchw(_run(pb, y)), ref_up + skip.double(), precision, "up_add")
-    # stems: stride 1 on the tensor cores (16 and 64 channels, partial tiles), stride 2 through the fp32 island
-    for (co, stride, H, W) in ((16, 1, 48, 40), (16, 1, 21, 37), (64, 1, 16, 24), (64, 2, 38, 50)):
+    # stems: stride 1 on the tensor cores (16 and 64 channels, partial tiles); stride 2 (ResNet 7x7, HRNet 3x3) as
+    # space-to-depth (OP_S2D) + a stride-1 5x5 / 3x3 conv over 16 channels on the tensor cores; odd sizes and
+    # CPB200_S2D_STEM=0 through the fp32 island
+    for (co, k, stride, H, W, s2d) in ((16, 7, 1, 48, 40, None), (16, 7, 1, 21, 37, None), (64, 7, 1, 16, 24, None),
+                                       (64, 7, 2, 38, 50, True), (64, 3, 2, 64, 48, True), (64, 7, 2, 64, 32, True),
+                                       (64, 7, 2, 37, 50, False), (64, 7, 2, 38, 50, "off")):
         x = torch.randn(B, 3, H, W, generator=g)
-        w = torch.randn(co, 3, 7, 7, generator=g) * 0.1; b = torch.randn(co, generator=g)
-        ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=3))
+        w = torch.randn(co, 3, k, k, generator=g) * 0.1; b = torch.randn(co, generator=g)
+        ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=k // 2))
         pb = _builder(B, precision); pb.H, pb.W = H, W
-        y = pb.stem(pb.input(3), w.to(DEV), b.to(DEV), 7, stride, 3, relu=True)
-        assert (pb.ops[0].flags & 8) == (8 if stride == 1 else 0)
+        if s2d == "off":
+            os.environ["CPB200_S2D_STEM"] = "0"
+        try:
+            y = pb.stem(pb.input(3), w.to(DEV), b.to(DEV), k, stride, k // 2, relu=True)
+        finally:
+            os.environ.pop("CPB200_S2D_STEM", None)
+        if stride == 1:
+            assert pb.ops[0].flags & 8
+        elif s2d is True:
+            assert [o.type for o in pb.ops] == [12, 1] and pb.ops[1].flags & 8 and pb.ops[1].k == ((k + 1) // 2 + 1,) * 2
+        else:
+            assert pb.ops[0].type == 2 and not (pb.ops[0].flags & 8)
         plan = pb.build(); plan.bind(x.to(DEV), {}); plan.run(torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
-        _close(_nchw(plan.tensor(y)), ref, precision, f"stem{co}s{stride}")
+        _close(_nchw(plan.tensor(y)), ref, precision, f"stem{co}k{k}s{stride}")
 
 
 @pytest.mark.parametrize("precision", PRECS)
