@@ -50,6 +50,15 @@ __device__ __forceinline__ float act_fn(float v, uint32_t act) {
 // bf16-output variant: multiply by 1/6 instead of the IEEE division (differs from act_fn by <= 1 ulp of fp32,
 // far below the bf16 rounding that follows).  The division cost 20+ instructions per element and made the
 // MobileNetV3 expand convs and depthwise convs instruction-bound (profiles/r01_launches_mbv3_v1_summary.txt).
+// the multiply-by-1/6 form on its own: used wherever the result is re-split into 16-bit planes (the split tensor-core
+// epilogues and the element-wise kernels on planes).  The exact division cost 64 % on the h-swish 1x1 expand convs of
+// MobileNetV3 in fp16x2 (tools/prof_act.py: 316 vs 193 us); 1 ulp of fp32 is 2^-13 of the planes' own precision.
+__device__ __forceinline__ float act_fast(float v, uint32_t act) {
+  if (act == CPB200_FLAG_RELU) return fmaxf(v, 0.f);
+  if (act == 0u) return v;
+  const float r = fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+  return act == CPB200_FLAG_HSWISH ? v * r : r;
+}
 template <typename T>
 __device__ __forceinline__ float act_out(float v, uint32_t act) {
   if constexpr (sizeof(T) == 4) {

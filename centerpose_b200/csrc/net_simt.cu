@@ -958,7 +958,8 @@ int run_op_split(const cpb200_op &op, cudaStream_t st) {
       return cpb::check_launch("dwdeconv_add_split_kernel");
     }
     // The element-wise MobileNetV3 / HRNet ops run their fp32 kernels straight on the planes (SpC / SpM handles):
-    // no fp32 island, no CONVERT passes.  fp32 arithmetic on hi + lo, exact division in the h-swish, result re-split.
+    // no fp32 island, no CONVERT passes.  fp32 arithmetic on hi + lo, result re-split; the depthwise conv is instantiated
+    // with T = bf16 only to select act_out's multiply-by-1/6 h-swish (VEC stays 4: the handles load 8 bytes per plane).
     case CPB200_OP_DWCONV: {
       constexpr int VEC = 4;
       const int C = op.cin[0];
@@ -969,7 +970,7 @@ int run_op_split(const cpb200_op &op, cudaStream_t st) {
   if (op.kh == KK && op.stride == SS && op.pad_h == KK / 2) {                                                    \
     const long long tot = (long long)op.B * op.Ho * ((op.Wo + PX - 1) / PX) * (C / VEC);                         \
     const unsigned g = (unsigned)std::min<long long>((tot + 255) / 256, 148LL * 32);                            \
-    dwconv_tiled_kernel<float, VEC, KK, SS, PX, SpC, SpM><<<g, 256, 0, st>>>(x, y, static_cast<const float *>(op.weight), \
+    dwconv_tiled_kernel<bf16, VEC, KK, SS, PX, SpC, SpM><<<g, 256, 0, st>>>(x, y, static_cast<const float *>(op.weight), \
         op.bias, tot, op.H, op.W, C, op.Ho, op.Wo, op.flags & CPB_ACT_MASK);                                    \
     return cpb::check_launch("dwconv_tiled_kernel");                                                            \
   }
@@ -977,7 +978,7 @@ int run_op_split(const cpb200_op &op, cudaStream_t st) {
 #undef DW_TILED
       const long long total = (long long)op.B * op.Ho * op.Wo * (C / VEC);
       const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 32);
-      dwconv_kernel<float, VEC, SpC, SpM><<<grid, 256, 0, st>>>(x, y, static_cast<const float *>(op.weight), op.bias, total,
+      dwconv_kernel<bf16, VEC, SpC, SpM><<<grid, 256, 0, st>>>(x, y, static_cast<const float *>(op.weight), op.bias, total,
           op.H, op.W, C, op.Ho, op.Wo, op.kh, op.stride, op.pad_h, op.flags & CPB_ACT_MASK);
       return cpb::check_launch("dwconv_kernel");
     }

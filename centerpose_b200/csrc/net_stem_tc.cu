@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) stem_tc_h_kernel(const StemArgs 
             for (int j = 0; j < 8; ++j) {
               const float x0 = fmaf(__uint_as_float(v[2 * j]) + __uint_as_float(v2[2 * j]), a.acc_scale, s_bias[c * 16 + 2 * j]);
               const float x1 = fmaf(__uint_as_float(v[2 * j + 1]) + __uint_as_float(v2[2 * j + 1]), a.acc_scale, s_bias[c * 16 + 2 * j + 1]);
-              split2(cpb::act_fn(x0, a.act), cpb::act_fn(x1, a.act), a.fmt, oh[j], ol[j]);
+              split2(cpb::act_fast(x0, a.act), cpb::act_fast(x1, a.act), a.fmt, oh[j], ol[j]);
             }
             uint16_t *op_ = reinterpret_cast<uint16_t *>(o) + c * 16;
             st_global_32B(op_, oh);

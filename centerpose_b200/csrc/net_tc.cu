@@ -440,18 +440,25 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
       const bool ok = ho < a.Ho && wo < a.Wo;
       const size_t pix = ((size_t)n * a.Hd + (ho * a.sy + a.oy)) * a.Wd + (wo * a.sx + a.ox);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC_COLS;
+      // two 16-column chunks per round: all their accumulator reads are in flight before the one wait (with a single chunk
+      // per wait the 1x1 convs — one K stage per tile — were bound by the epilogue's load -> wait -> convert -> store chain)
+      constexpr int NCH = BN / 16, CSTEP = (NCH >= 2 && !DCN) ? 2 : 1;      // the 704-thread DCN variant has 80 registers per thread
 #pragma unroll 1
-      for (int c = (a.dcn_prefetch & 2) ? BN / 16 : 0; c < BN / 16; ++c) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c * 16, v);
-        if constexpr (NCAT) {
-          uint32_t v2[16];
-          tmem_ld16(taddr + BN + c * 16, v2);
-          tmem_ld_wait();
+      for (int c2 = (a.dcn_prefetch & 2) ? NCH : 0; c2 < NCH; c2 += CSTEP) {
+        uint32_t va[CSTEP][16], vb[NCAT ? CSTEP : 1][16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-        } else {
-          tmem_ld_wait();
+        for (int hc = 0; hc < CSTEP; ++hc) {
+          tmem_ld16(taddr + (c2 + hc) * 16, va[hc]);
+          if constexpr (NCAT) tmem_ld16(taddr + BN + (c2 + hc) * 16, vb[hc]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+       for (int hc = 0; hc < CSTEP; ++hc) {
+        const int c = c2 + hc;
+        uint32_t (&v)[16] = va[hc];
+        if constexpr (NCAT) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vb[hc][j]));
         }
         const int nb = n0 + c * 16;
         if (ok && nb < a.cout) {
@@ -512,7 +519,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
             uint32_t oh[8], ol[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              split2(cpb::act_fn(f[2 * j], act), cpb::act_fn(f[2 * j + 1], act), a.fmt, oh[j], ol[j]);
+              split2(cpb::act_fast(f[2 * j], act), cpb::act_fast(f[2 * j + 1], act), a.fmt, oh[j], ol[j]);
             st_global_32B(o, oh);                       // 32-byte stores: see net_tc3.cu's epilogue
             st_global_32B(o + a.dst_plane, ol);
           } else {
@@ -543,6 +550,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
             st_global_32B(o, ow);
           }
         }
+       }
       }
       tc_fence_before();
       __syncwarp();

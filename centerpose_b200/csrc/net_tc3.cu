@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
             if constexpr (P == 2) {
 #pragma unroll
               for (int j = 0; j < 8; ++j)
-                split2(cpb::act_fn(f[2 * j], act), cpb::act_fn(f[2 * j + 1], act), a.fmt, wh[hc][j], wl[hc][j]);
+                split2(cpb::act_fast(f[2 * j], act), cpb::act_fast(f[2 * j + 1], act), a.fmt, wh[hc][j], wl[hc][j]);
             } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
             uint32_t oh[8], ol[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              split2(cpb::act_fn(f[2 * j], act), cpb::act_fn(f[2 * j + 1], act), a.fmt, oh[j], ol[j]);
+              split2(cpb::act_fast(f[2 * j], act), cpb::act_fast(f[2 * j + 1], act), a.fmt, oh[j], ol[j]);
             st_global_32B(o, oh);                       // one 32-byte sector per thread and plane: every thread owns a pixel row,
             st_global_32B(o + a.dst_plane, ol);         // so a warp store touches 32 lines — halve the number of such stores
           } else {

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(SP_THREADS, 1) conv_sp_kernel(const SpArgs a) 
             uint32_t oh[8], ol[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              split2(cpb::act_fn(f[2 * j], a.act), cpb::act_fn(f[2 * j + 1], a.act), a.fmt, oh[j], ol[j]);
+              split2(cpb::act_fast(f[2 * j], a.act), cpb::act_fast(f[2 * j + 1], a.act), a.fmt, oh[j], ol[j]);
             st_global_32B(oh_, oh);
             st_global_32B(oh_ + a.y_plane, ol);
           } else {
