@@ -572,19 +572,26 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
-      } else
+      } else {
+      // direct stores (fp32 outputs, BN = 16, resident-weight convs without room for the staging tile): two chunks per round,
+      // their accumulator reads in flight before the one wait
+      constexpr int CSTEP = BN >= 32 ? 2 : 1;
 #pragma unroll 1
-      for (int c = (a.dbg & 2u) ? c_last : c_first; c < c_last; ++c) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c * 16, v);
-        if constexpr (NCAT) {
-          uint32_t v2[16];
-          tmem_ld16(taddr + BN + c * 16, v2);
-          tmem_ld_wait();
+      for (int c2 = (a.dbg & 2u) ? c_last : c_first; c2 < c_last; c2 += CSTEP) {
+        uint32_t va[CSTEP][16], vb[NCAT ? CSTEP : 1][16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
-        } else {
-          tmem_ld_wait();
+        for (int hc = 0; hc < CSTEP; ++hc) {
+          tmem_ld16(taddr + (c2 + hc) * 16, va[hc]);
+          if constexpr (NCAT) tmem_ld16(taddr + BN + (c2 + hc) * 16, vb[hc]);
+        }
+        tmem_ld_wait();
+#pragma unroll
+       for (int hc = 0; hc < CSTEP; ++hc) {
+        const int c = c2 + hc;
+        uint32_t (&v)[16] = va[hc];
+        if constexpr (NCAT) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(vb[hc][j]));
         }
         const int nb = n0 + c * 16;
         if (ok && nb < a.cout) {
@@ -668,6 +675,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc_kernel(const __grid_
             st_global_32B(o, ow);
           }
         }
+       }
+      }
       }
       tc_fence_before();
       __syncwarp();
