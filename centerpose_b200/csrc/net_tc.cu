@@ -30,7 +30,7 @@
 
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;        // TMA producer, MMA issuer, two epilogue groups of four warps (tiles alternate between them)
 constexpr int TILE_M = 128;
 
 struct alignas(64) TcArgs {
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
   const uint32_t stage_bytes = P * a_bytes + ((P * b_bytes + 1023u) & ~1023u);
   __shared__ __align__(8) uint64_t bars[2 * 8 + 16];
   __shared__ uint32_t s_tmem;
-  __shared__ float s_bias[2][BN];
+  __shared__ float s_bias[2][2][BN];      // [epilogue group][tile parity within the group]
   __shared__ DcnPrm s_prm[DCN ? DCN_GW : 1][DCN ? 9 : 1][DCN ? DCN_ROWS : 1];
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[8]);
   const uint32_t tfull0 = smem_u32(&bars[16]), tempty0 = smem_u32(&bars[24]);
@@ -420,19 +420,30 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
       }
     }
   } else {
-    // =============================== epilogue (warps 2..5) ===============================
+    // =============================== epilogue (warps 2..5 and, without the DCN gather warps, 6..9) ===============================
+    // Two groups on alternate tiles (the accumulator stages alternate with them: nacc is even).  The 1x1 convs have ONE K stage
+    // per tile, so their time is the epilogue's: one group read out a 128 x 128 split tile in ~6 us against ~1 us of loads + MMAs.
+    const int grp = (!DCN && warp >= 6) ? 1 : 0;
+    const int ngrp = DCN ? 1 : 2;
     const int q = warp & 3;                              // TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;                     // 0..127
+    const int et = threadIdx.x - 64 - grp * 128;         // 0..127
     const uint32_t act = a.flags & CPB_ACT_MASK;
     const bool out_f32 = a.flags & CPB200_FLAG_OUT_F32;
     const bool out_nchw = a.flags & CPB200_FLAG_OUT_NCHW_F32;
     int acc = 0; uint32_t accphase = 0;
-    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+    int it = 0, par = 0;
+    for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x, ++it) {
+      if ((it % ngrp) != grp) {                          // the other group's tile: just keep the accumulator ring in step
+        if (++acc == a.nacc) { acc = 0; accphase ^= 1; }
+        continue;
+      }
       int n, h0, w0, nt; decode_tile(t, n, h0, w0, nt);
       const int n0 = nt * BN;
-      for (int i = et; i < BN; i += 128) s_bias[acc & 1][i] = (a.bias && n0 + i < a.cout) ? __ldg(a.bias + n0 + i) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float *sb = s_bias[grp][par];
+      par ^= 1;
+      for (int i = et; i < BN; i += 128) sb[i] = (a.bias && n0 + i < a.cout) ? __ldg(a.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
       mbar_wait(tfull0 + 8 * acc, accphase);
       tc_fence_after();
       const int th = row / a.TW, tw = row % a.TW;
@@ -465,10 +476,10 @@ __global__ void __launch_bounds__(DCN ? DCN_THREADS : TC_THREADS, 1) conv_tc_ker
           float f[16];
           if constexpr (P == 2) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), a.acc_scale, s_bias[acc & 1][c * 16 + j]);
+            for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), a.acc_scale, sb[c * 16 + j]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + s_bias[acc & 1][c * 16 + j];
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + sb[c * 16 + j];
           }
           if (out_nchw) {
             // head outputs: lanes are consecutive pixels of a tile row -> coalesced fp32 stores per channel
