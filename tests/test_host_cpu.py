@@ -140,6 +140,37 @@ def test_plan_lowering_shapes():
     assert abs(gmac_512 - 40.17) < 0.1, gmac_512          # SURVEY: 40.24 incl. 0.067 dead project convs
 
 
+def test_stride2_stem_space_to_depth_lowering_is_the_same_convolution():
+    """Split precisions lower a k x k / stride-2 stem to CPB200_OP_S2D + a stride-1 conv over 16 channels (plan.py::stem).
+    The lowering is pure index arithmetic: replay it with torch on the CPU — space-to-depth of the image, the repacked weights
+    the builder emitted — and compare with the strided convolution it replaces (msra_resnet.py:116-117, pose_higher_hrnet.py:283)."""
+    import torch.nn.functional as F
+    from centerpose_b200.plan import OP_S2D, PlanBuilder
+    g = torch.Generator().manual_seed(5)
+    for k, co, H, W in ((7, 64, 20, 28), (3, 64, 16, 24), (3, 16, 12, 20)):
+        x = torch.randn(2, 3, H, W, generator=g, dtype=torch.float64)
+        w = torch.randn(co, 3, k, k, generator=g, dtype=torch.float64)
+        b = torch.randn(co, generator=g, dtype=torch.float64)
+        pb = PlanBuilder(2, H, W, "fp16x2", torch.device("cpu"))
+        y = pb.stem(pb.input(3), w.float(), b.float(), k, 2, k // 2, relu=False)
+        assert [o.type for o in pb.ops] == [OP_S2D, 1]
+        conv = pb.ops[1]
+        k2 = (k + 1) // 2 + 1
+        assert conv.k == (k2, k2) and conv.stride == 1 and conv.pad == (k2 // 2, k2 // 2) and (y.C, y.H, y.W) == (co, H // 2, W // 2)
+        # z[b, (py*2+px)*3 + c, h, w] = x[b, c, 2h+py, 2w+px], channels 12..15 zero (include/centerpose_b200.h, CPB200_OP_S2D)
+        z = torch.zeros(2, 16, H // 2, W // 2, dtype=torch.float64)
+        for py in range(2):
+            for px in range(2):
+                z[:, (py * 2 + px) * 3:(py * 2 + px) * 3 + 3] = x[:, :, py::2, px::2]
+        got = F.conv2d(z, conv.w_raw.double(), b, stride=1, padding=k2 // 2)
+        ref = F.conv2d(x, w.float().double(), b, stride=2, padding=k // 2)
+        assert got.shape == ref.shape and (got - ref).abs().max().item() < 1e-9, (k, (got - ref).abs().max().item())
+    # odd sizes keep the strided stem op
+    pb = PlanBuilder(2, 21, 28, "fp16x2", torch.device("cpu"))
+    pb.stem(pb.input(3), torch.randn(64, 3, 7, 7), torch.zeros(64), 7, 2, 3)
+    assert pb.ops[0].type == 2
+
+
 _WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
