@@ -140,6 +140,42 @@ def test_plan_lowering_shapes():
     assert abs(gmac_512 - 40.17) < 0.1, gmac_512          # SURVEY: 40.24 incl. 0.067 dead project convs
 
 
+def test_split_plane_host_helpers():
+    """Host side of the split-operand precisions (plan.py): hi = rn16(v), lo = rn16(v - hi) reproduces v to 2^-22 (fp16
+    planes) / 2^-16 (bf16 planes); the fp16 weight pre-scale is an exact power of two that keeps the lo plane out of the
+    subnormals; packed tensor-core weights keep hi + lo == w * scale; the accumulator compensation is linear in K."""
+    import math
+    from centerpose_b200.plan import PlanBuilder, pow2_scale, rz_compensation, split_planes
+    g = torch.Generator().manual_seed(3)
+    v = torch.randn(4096, generator=g) * torch.logspace(-2, 3, 4096)
+    for dt, bits in ((torch.float16, 22), (torch.bfloat16, 16)):
+        p = split_planes(v, dt)
+        assert p.shape == (2, 4096) and p.dtype == dt
+        rec = p[0].float() + p[1].float()
+        assert ((rec - v).abs() <= v.abs() * 2.0 ** (-bits) * 1.01 + 1e-7).all()
+        assert torch.equal(p[0], v.to(dt))
+    sat = split_planes(torch.tensor([1e6, -1e6]), torch.float16)              # fp16 planes saturate instead of overflowing
+    assert torch.isfinite(sat.float()).all() and sat[0].float().abs().max() == 65504.0
+    for scale_in in (3e-4, 0.07, 1.0, 513.0):
+        w = torch.randn(64, 32, 3, 3, generator=g) * scale_in
+        s = pow2_scale(w)
+        assert math.log2(s) == round(math.log2(s)) and 2.0 ** 12 <= float(w.abs().max()) * s < 2.0 ** 13
+        lo = split_planes(w * s, torch.float16)[1].float()
+        tiny = (lo != 0) & (lo.abs() < 2.0 ** -14)                                  # fp16 subnormal lo parts
+        assert tiny.float().mean().item() < 1e-2                                   # only the weights that are themselves ~1e-4 of the largest
+    assert pow2_scale(torch.zeros(3)) == 1.0
+    assert rz_compensation("fp32", 576) == 1.0 and rz_compensation("bf16", 576) == 1.0
+    c1, c2 = rz_compensation("fp16x2", 576) - 1.0, rz_compensation("fp16x2", 1152) - 1.0
+    assert 0 < c1 < 1e-5 and abs(c2 - 2 * c1) < 1e-12
+    pb = PlanBuilder(1, 32, 32, "fp16x2", torch.device("cpu"))
+    w = torch.randn(48, 64, 3, 3, generator=g) * 0.05
+    packed = pb._pack_conv_tc(w, 64)                                                # [plane][tap][slab][Co_pad][bk]
+    sc = pb._last_scale
+    rec = (packed[0].float() + packed[1].float())[:, 0, :48, :]                     # [tap][Co][Ci]
+    ref = (w * sc).permute(2, 3, 0, 1).reshape(9, 48, 64)
+    assert (rec - ref).abs().max().item() <= ref.abs().max().item() * 2.0 ** -21
+
+
 def test_stride2_stem_space_to_depth_lowering_is_the_same_convolution():
     """Split precisions lower a k x k / stride-2 stem to CPB200_OP_S2D + a stride-1 conv over 16 channels (plan.py::stem).
     The lowering is pure index arithmetic: replay it with torch on the CPU — space-to-depth of the image, the repacked weights
